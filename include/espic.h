@@ -1,0 +1,153 @@
+/*
+ * espic.h -- C ABI of the B200-native ES-PIC engine (libespic_cuda.so, sm_100a).
+ *
+ * This is the drop-in boundary for the hot path  inject -> push -> deposit -> rho -> Poisson -> E
+ * of particleincell/plasma-simulations-by-example (ch2, ch3/ver2, ch9).  The reference has no FFI:
+ * its boundary is the class API that Main.cpp drives.  The host C++ shim in
+ * plasma-simulations-by-example_b200/host/ (World.h, Species.h, PotentialSolver.h, Source.h, Output.h,
+ * Field.h -- the reference's own file and class names) forwards every hot call to the entry points
+ * below; each entry point cites the reference interface it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative value on error (espic_last_error() has the text);
+ *     there is no CPU fallback: without a CUDA device espic_create fails.
+ *   - node arrays are flat, u = k*ni*nj + j*ni + i (reference Field::U, ch3/ver2/Field.h:161);
+ *     ef is interleaved ef[3*u+c]; object_id is int32.
+ *   - particles are SoA: comp[0..6] = x, y, z, vx, vy, vz, mpw (reference struct Particle, Species.h:11-19).
+ *   - all arithmetic is FP64 and follows the reference's operation order (no FMA contraction), so
+ *     positions, velocities, kill masks, particle order, E and rho-from-density are bit-identical to
+ *     the reference; reductions (deposition sums, dot products, diagnostics) differ by summation order only.
+ *   - calls are asynchronous on the context's stream unless they return a host value.
+ */
+#ifndef ESPIC_H
+#define ESPIC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct espic_ctx espic_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* World::World(ni,nj,nk) + World::setExtents(x0,xm)  (ch3/ver2/World.cpp:14-36): allocates phi, rho,
+ * node_vol, ef, object_id on `device`, computes dh=(xm-x0)/(n-1) and the node volumes (World.cpp:58-69). */
+int  espic_create(espic_ctx **ctx, int ni, int nj, int nk, const double x0[3], const double xm[3], int device);
+void espic_destroy(espic_ctx *ctx);
+const char *espic_last_error(void);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own */
+int  espic_set_stream(espic_ctx *ctx, void *cuda_stream);
+int  espic_sync(espic_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long espic_kernel_launches(espic_ctx *ctx);
+/* dh[3], xc[3] as computed by setExtents */
+int  espic_get_mesh(espic_ctx *ctx, double dh[3], double xc[3]);
+
+/* ---- geometry ------------------------------------------------------------------------------- */
+
+/* World::addSphere (World.cpp:87-105): object_id=1, phi=phi_sphere on nodes with |x-c|^2 <= r^2 */
+int espic_add_sphere(espic_ctx *ctx, const double c[3], double radius, double phi_sphere);
+/* World::addInlet (World.cpp:108-115): object_id=2, phi=0 on k=0 */
+int espic_add_inlet(espic_ctx *ctx);
+
+/* ---- node fields: the public World/Species members Output.cpp and Main.cpp read -------------- */
+
+enum { ESPIC_PHI = 0, ESPIC_RHO = 1, ESPIC_EF = 2, ESPIC_NODE_VOL = 3, ESPIC_OBJECT_ID = 4,
+       ESPIC_DEN = 5, ESPIC_DEN_AVE = 6 };
+int espic_field_download(espic_ctx *ctx, int which, int species, void *host);
+int espic_field_upload(espic_ctx *ctx, int which, int species, const void *host);
+/* device pointer of a field (zero-copy interop: NCCL, torch.from_blob, ...) */
+int espic_field_devptr(espic_ctx *ctx, int which, int species, void **dptr);
+
+/* ---- species -------------------------------------------------------------------------------- */
+
+/* Species::Species(name,mass,charge,mpw0,world) (Species.h:26-29).  Returns the species id (>=0). */
+int espic_species_create(espic_ctx *ctx, double mass, double charge, double mpw0, long long capacity);
+int espic_species_reserve(espic_ctx *ctx, int sp, long long capacity);
+/* Species::getNp (Species.h:32) */
+long long espic_species_count(espic_ctx *ctx, int sp);
+/* raw particle upload/download (std::vector<Particle> particles, Species.h:65); append!=0 keeps existing ones */
+int espic_species_upload(espic_ctx *ctx, int sp, const double *const comp[7], long long n, int append);
+long long espic_species_download(espic_ctx *ctx, int sp, double *const comp[7], long long n_max);
+/* same as espic_species_upload with DEVICE source pointers (device-to-device copy on the context's stream) */
+int espic_species_upload_device(espic_ctx *ctx, int sp, const double *const dcomp[7], long long n, double mpw_max, int append);
+/* Species::addParticle for n particles (Species.cpp:65-81): drop positions outside [x0,xm), gather E,
+ * rewind the velocity by half a step, append in input order. */
+int espic_species_add(espic_ctx *ctx, int sp, const double *const comp[7], long long n, double dt, long long *n_added);
+
+/* Species::advance (ch3/ver2/Species.cpp:7-48; ch2/Species.cpp:7-38). */
+enum { ESPIC_WALL_ABSORB = 0,      /* ch3/ch9: kill on sphere / outside box, swap-with-last removal (same order) */
+       ESPIC_WALL_REFLECT = 1 };   /* ch2: specular reflection at the six walls, nothing removed */
+enum { ESPIC_PUSH_FUSE_DEPOSIT = 1,   /* also scatter the survivors: the next espic_deposit only finalises */
+       ESPIC_PUSH_NO_COMPACT = 2,     /* leave dead particles in place with mpw=0 (kill-mask tests) */
+       ESPIC_PUSH_FIXED_POINT = 256 };/* with FUSE_DEPOSIT: accumulate in int64 fixed point */
+int espic_push(espic_ctx *ctx, int sp, double dt, int wall_mode, int flags);
+
+/* Species::computeNumberDensity (Species.cpp:51-62): den = scatter(mpw) / node_vol. */
+enum { ESPIC_DEPOSIT_FP64 = 0,     /* FP64 atomics (order-dependent rounding) */
+       ESPIC_DEPOSIT_FIXED = 1 };  /* int64 fixed-point accumulation: bit-reproducible for any order / GPU count */
+int espic_deposit(espic_ctx *ctx, int sp, int mode);
+
+/* periodic maintenance, no reference counterpart: reorder particles by cell for gather/scatter locality */
+int espic_sort_by_cell(espic_ctx *ctx, int sp);
+
+/* ColdBeamSource::sample (Source.cpp:4-27) with Philox4x32-10 counters (seed, stream, step, particle). */
+int espic_inject_cold_beam(espic_ctx *ctx, int sp, double v_drift, double den, double dt,
+                           uint64_t seed, uint32_t stream, uint32_t step, long long *n_added);
+
+/* Species::getRealCount/getMomentum/getKE (Species.cpp:84-108): out = {sum mpw, px, py, pz, KE} */
+int espic_species_diag(espic_ctx *ctx, int sp, double out[5]);
+/* Species::updateAverages -> Field::updateAverage (Field.h:214-221) */
+int espic_update_average(espic_ctx *ctx, int sp);
+
+/* ---- fields --------------------------------------------------------------------------------- */
+
+/* World::computeChargeDensity (World.cpp:46-54): rho = sum_s charge_s * den_s over all species */
+int espic_charge_density(espic_ctx *ctx);
+
+enum { ESPIC_SOLVE_GS = 0,      /* PotentialSolver::solveGS, nonlinear Boltzmann SOR w=1.4 (PotentialSolver.cpp:334-430) */
+       ESPIC_SOLVE_PCG = 1,     /* solveNRPCG (:225-296): Newton + Jacobi-PCG on the same discrete equations, with the Dirichlet and
+                                   Neumann rows eliminated exactly so the linear system is SPD and CG cannot break down */
+       ESPIC_SOLVE_QN = 2,      /* solveQN (:204-222) */
+       ESPIC_SOLVE_GS_BOX = 3,  /* ch2 PotentialSolver::solve, linear SOR on interior nodes (ch2/PotentialSolver.cpp:11-67) */
+       ESPIC_SOLVE_PCG_REF = 4 };/* solveNRPCG + solvePCGLinear + solveGSLinear fallback restated operation for operation on the
+                                   reference's non-symmetric 7-band matrix (:225-331,:433-461); inherits its breakdowns */
+
+typedef struct {
+    int type;
+    int max_it;          /* ctor argument max_solver_it */
+    double tol;          /* ctor argument tolerance */
+    double phi0, Te0, n0;/* setReferenceValues (PotentialSolver.h:53-57) */
+    int nr_max_it;       /* NR_MAX_IT, 20 in the reference (:228) */
+    double nr_tol;       /* NR_TOL, 1e-3 in the reference (:229) */
+} espic_solve_params;
+
+typedef struct {
+    int converged;       /* what the reference's solve() returns */
+    int nr_iters;
+    long long lin_iters; /* PCG iterations over all Newton steps */
+    int gs_fallbacks;    /* PCG failures handed to the linear GS */
+    long long gs_iters;  /* SOR sweeps */
+    double residual;     /* last L2 / norm */
+} espic_solve_info;
+
+int espic_solve(espic_ctx *ctx, const espic_solve_params *p, espic_solve_info *info);
+/* PotentialSolver::computeEF (PotentialSolver.cpp:465-504) */
+int espic_compute_ef(espic_ctx *ctx);
+/* World::getPE (World.cpp:72-84) */
+int espic_field_pe(espic_ctx *ctx, double *pe);
+
+/* ---- multi-GPU: particles sharded by index, density summed over ranks ------------ */
+
+int espic_comm_unique_id(void *id128);                                  /* ncclGetUniqueId */
+int espic_comm_init(espic_ctx *ctx, int rank, int nranks, const void *id128);
+/* sum the species' deposited density over all ranks (FP64, or int64 when deposited in fixed point).
+ * Replaces ch9/MPI Field::updateBoundaries (ch9/MPI/include/Field.h:122-179). */
+int espic_allreduce_density(espic_ctx *ctx, int sp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -170,7 +170,14 @@ int main(int argc, char **argv)
     }
 
     double converged = -1;
+    const bool timing = getenv("ESPIC_REF_TIMING") != nullptr;
+    auto t_prev = chrono::high_resolution_clock::now();
     for (int a = 3; a < argc; a++) {
+        if (timing && a > 3) {
+            chrono::duration<double> d = chrono::high_resolution_clock::now() - t_prev;
+            printf("T %s %.9g\n", argv[a - 1], d.count());
+        }
+        t_prev = chrono::high_resolution_clock::now();
         vector<string> c = split(argv[a], ':');
         const string &op = c[0];
         if (op == "advance") { for (Species &sp : species) sp.advance(); }
@@ -243,6 +250,12 @@ int main(int argc, char **argv)
         }
         else { fprintf(stderr, "unknown command %s\n", argv[a]); return 2; }
     }
+
+    if (timing && argc > 3) {
+        chrono::duration<double> d = chrono::high_resolution_clock::now() - t_prev;
+        printf("T %s %.9g\n", argv[argc - 1], d.count());
+    }
+    if (getenv("ESPIC_REF_NODUMP")) return 0;
 
     /* dump */
     from_field(world.phi, st.phi);

@@ -1,0 +1,892 @@
+// espic_fields.cu -- World::computeChargeDensity, PotentialSolver::{solveQN, solveGS, solveNRPCG, solvePCGLinear,
+// solveGSLinear, computeEF}, World::getPE, Field::updateAverage as matrix-free sm_100a kernels (include/espic.h).
+#include "espic_internal.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+#define SP_CHECK(c, sp) do { if ((sp) < 0 || (sp) >= (c)->nsp) { espic_set_error("bad species id %d", (sp)); return -1; } } while (0)
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// reference constants (World.h:12-21)
+#define C_EPS_0 8.85418782e-12
+#define C_QE 1.602176565e-19
+
+// node classes (PotentialSolver.h:64 NodeType, plus which neighbour a Neumann face node mirrors: .cpp:180-187)
+enum { NT_REG = 0, NT_DIRICHLET = 1, NT_I0 = 2, NT_I1 = 3, NT_J0 = 4, NT_J1 = 5, NT_K0 = 6, NT_K1 = 7 };
+
+struct StencilC {
+    int ni, nj, nk;
+    long long nn, sj, sk;
+    double idx, idy, idz;        // 1/dh          (buildMatrix, PotentialSolver.cpp:149-151)
+    double idx2, idy2, idz2;     // idx*idx       (buildMatrix, :152-154)
+    double gdx2, gdy2, gdz2;     // 1/(dh*dh)     (solveGS, :342-344)
+};
+
+static StencilC make_stencil(const MeshC &m)
+{
+    StencilC s;
+    s.ni = m.ni; s.nj = m.nj; s.nk = m.nk; s.nn = m.nn; s.sj = m.ni; s.sk = (long long)m.ni * m.nj;
+    s.idx = 1.0 / m.dh[0]; s.idy = 1.0 / m.dh[1]; s.idz = 1.0 / m.dh[2];
+    s.idx2 = s.idx * s.idx; s.idy2 = s.idy * s.idy; s.idz2 = s.idz * s.idz;
+    s.gdx2 = 1.0 / (m.dh[0] * m.dh[0]); s.gdy2 = 1.0 / (m.dh[1] * m.dh[1]); s.gdz2 = 1.0 / (m.dh[2] * m.dh[2]);
+    return s;
+}
+
+__device__ __forceinline__ long long nbr_of(const StencilC &s, long long u, int t)
+{
+    switch (t) {
+        case NT_I0: return u + 1;
+        case NT_I1: return u - 1;
+        case NT_J0: return u + s.sj;
+        case NT_J1: return u - s.sj;
+        case NT_K0: return u + s.sk;
+        default: return u - s.sk;
+    }
+}
+
+// mode 0: sphere codes (object_id>0 -> Dirichlet, faces -> Neumann with priority i,j,k); mode 1: ch2 box (all faces fixed)
+__global__ void k_node_types(StencilC s, const int32_t *__restrict__ object_id, int mode, uint8_t *__restrict__ type)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= s.nn) return;
+    int i = (int)(u % s.ni), j = (int)((u / s.ni) % s.nj), k = (int)(u / s.sk);
+    int t;
+    if (mode == 1) {
+        t = (i == 0 || i == s.ni - 1 || j == 0 || j == s.nj - 1 || k == 0 || k == s.nk - 1) ? NT_DIRICHLET : NT_REG;
+    } else if (object_id[u] > 0) t = NT_DIRICHLET;
+    else if (i == 0) t = NT_I0;
+    else if (i == s.ni - 1) t = NT_I1;
+    else if (j == 0) t = NT_J0;
+    else if (j == s.nj - 1) t = NT_J1;
+    else if (k == 0) t = NT_K0;
+    else if (k == s.nk - 1) t = NT_K1;
+    else t = NT_REG;
+    type[u] = (uint8_t)t;
+}
+
+static int ensure_node_types(espic_ctx *c, int mode)
+{
+    if (c->node_type && c->node_type_mode == mode && c->node_type_version == c->geom_version) return 0;
+    if (!c->node_type) CK(cudaMalloc(&c->node_type, (size_t)c->m.nn));
+    StencilC s = make_stencil(c->m);
+    k_node_types<<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(s, c->object_id, mode, c->node_type);
+    LAUNCH_CHECK(c);
+    c->node_type_mode = mode;
+    c->node_type_version = c->geom_version;
+    return 0;
+}
+
+static int ensure_sv(espic_ctx *c, int count)
+{
+    for (int q = 0; q < count; q++)
+        if (!c->sv[q]) CK(cudaMalloc(&c->sv[q], (size_t)c->m.nn * sizeof(double)));
+    return 0;
+}
+
+// ---- reductions --------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_sum_final(const double *__restrict__ part, int nparts, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double a = 0;
+    for (int i = threadIdx.x; i < nparts; i += 256) a += part[i];
+    double t = block_sum(a, sh);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+static int read_scalar(espic_ctx *c, const double *dptr, double *host)
+{
+    double *h = reinterpret_cast<double *>(c->hpin) + 16;
+    CK(cudaMemcpyAsync(h, dptr, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *host = h[0];
+    return 0;
+}
+
+// ---- rho ---------------------------------------------------------------------------------------------
+
+struct RhoArgs { const double *den[ESPIC_MAX_SPECIES]; double charge[ESPIC_MAX_SPECIES]; int n; };
+
+// World::computeChargeDensity (World.cpp:46-54): rho = 0; rho += charge*den for charged species, in order
+__global__ void k_rho(long long nn, RhoArgs a, double *__restrict__ rho)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= nn) return;
+    double r = 0;
+    for (int s = 0; s < a.n; s++) r += a.den[s][u] * a.charge[s];
+    rho[u] = r;
+}
+
+extern "C" int espic_charge_density(espic_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    RhoArgs a;
+    a.n = 0;
+    for (int s = 0; s < c->nsp; s++) {
+        if (c->sp[s].charge == 0) continue;
+        a.den[a.n] = c->sp[s].den;
+        a.charge[a.n] = c->sp[s].charge;
+        a.n++;
+    }
+    k_rho<<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, a, c->rho);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+// ---- QN ----------------------------------------------------------------------------------------------
+
+// PotentialSolver::solveQN (PotentialSolver.cpp:204-222)
+__global__ void k_qn(long long nn, const int32_t *__restrict__ object_id, const double *__restrict__ rho,
+                     double *__restrict__ phi, double phi0, double Te0, double rho0)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= nn) return;
+    if (object_id[u] > 0) return;
+    double rho_ratio = rho[u] / rho0;
+    if (rho_ratio < 1e-6) rho_ratio = 1e-6;
+    phi[u] = phi0 + Te0 * log(rho_ratio);
+}
+
+// ---- nonlinear / linear SOR, red-black ordering ------------------------------------------------------------
+
+// One colour of PotentialSolver::solveGS (PotentialSolver.cpp:352-384) / ch2 solve (ch2/PotentialSolver.cpp:27-41).
+// Same node update as the reference; the sweep visits nodes in red-black instead of lexicographic order.
+template <bool BOLTZ>
+__global__ void __launch_bounds__(256) k_sor_color(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                                                   double *__restrict__ phi, int color, double phi0, double Te0, double n0)
+{
+    // thread -> (pair index along i, j, k): only nodes with (i+j+k)&1 == color
+    const int hi = (s.ni + 1) >> 1;
+    long long t = blockIdx.x * 256ll + threadIdx.x;
+    long long total = (long long)hi * s.nj * s.nk;
+    if (t >= total) return;
+    int ih = (int)(t % hi), j = (int)((t / hi) % s.nj), k = (int)(t / ((long long)hi * s.nj));
+    int i = 2 * ih + ((j + k + color) & 1);
+    if (i >= s.ni) return;
+    long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+    int ty = type[u];
+    if (ty == NT_DIRICHLET) return;
+    if (ty != NT_REG) { phi[u] = phi[nbr_of(s, u, ty)]; return; }
+    double p = phi[u];
+    double src;
+    if (BOLTZ) {
+        double ne = n0 * exp((p - phi0) / Te0);
+        src = (rho[u] - C_QE * ne) / C_EPS_0;
+    } else {
+        src = rho[u] / C_EPS_0;
+    }
+    double phi_new = (src + s.gdx2 * (phi[u - 1] + phi[u + 1]) + s.gdy2 * (phi[u - s.sj] + phi[u + s.sj]) +
+                      s.gdz2 * (phi[u - s.sk] + phi[u + s.sk])) / (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2);
+    phi[u] = p + 1.4 * (phi_new - p);
+}
+
+// residual of PotentialSolver.cpp:389-421 (ch2: ch2/PotentialSolver.cpp:46-58), per-block partial sums of R^2
+template <bool BOLTZ>
+__global__ void __launch_bounds__(256) k_sor_residual(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                                                      const double *__restrict__ phi, double phi0, double Te0, double n0,
+                                                      double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double sum = 0;
+    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < s.nn; u += (long long)gridDim.x * 256) {
+        int ty = type[u];
+        if (ty == NT_DIRICHLET) continue;
+        double R;
+        double p = phi[u];
+        if (ty != NT_REG) R = p - phi[nbr_of(s, u, ty)];
+        else {
+            double src;
+            if (BOLTZ) {
+                double ne = n0 * exp((p - phi0) / Te0);
+                src = (rho[u] - C_QE * ne) / C_EPS_0;
+            } else src = rho[u] / C_EPS_0;
+            R = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (phi[u - 1] + phi[u + 1]) +
+                s.gdy2 * (phi[u - s.sj] + phi[u + s.sj]) + s.gdz2 * (phi[u - s.sk] + phi[u + s.sk]);
+        }
+        sum += R * R;
+    }
+    double t = block_sum(sum, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+static int solve_sor(espic_ctx *c, const espic_solve_params *p, bool box, espic_solve_info *info)
+{
+    int r;
+    if ((r = ensure_node_types(c, box ? 1 : 0))) return r;
+    StencilC s = make_stencil(c->m);
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 4 * c->sm_count);
+    if ((r = ensure_buf(&c->red, &c->red_cap, nb_res, c->stream))) return r;
+    const long long half = (long long)((s.ni + 1) >> 1) * s.nj * s.nk;
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    double L2 = 0;
+    bool converged = false;
+    long long it = 0;
+    for (it = 0; it < p->max_it; it++) {
+        for (int color = 0; color < 2; color++) {
+            if (box) k_sor_color<false><<<nblk(half, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, color, 0, 1, 0);
+            else k_sor_color<true><<<nblk(half, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, color, p->phi0, p->Te0, p->n0);
+            LAUNCH_CHECK(c);
+        }
+        if (it % 25 == 0) {
+            if (box) k_sor_residual<false><<<nb_res, 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, 0, 1, 0, c->red);
+            else k_sor_residual<true><<<nb_res, 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, p->phi0, p->Te0, p->n0, c->red);
+            LAUNCH_CHECK(c);
+            k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb_res, dres);
+            LAUNCH_CHECK(c);
+            double sum;
+            if ((r = read_scalar(c, dres, &sum))) return r;
+            L2 = sqrt(sum / ((double)s.ni * s.nj * s.nk));
+            if (L2 < p->tol) { converged = true; it++; break; }
+        }
+    }
+    if (!converged) fprintf(stderr, "GS failed to converge, L2=%g\n", L2);
+    if (info) { info->converged = converged; info->gs_iters = it; info->residual = L2; }
+    return 0;
+}
+
+// ---- matrix-free rows of A and J = A - diag(P) (buildMatrix, PotentialSolver.cpp:146-199) ----------------------
+
+// (J v)[u] accumulated in the reference's slot order (Matrix::operator*, PotentialSolver.cpp:24-35)
+__device__ __forceinline__ double apply_row(const StencilC &s, int ty, double diag, const double *v, long long u)
+{
+    double r = 0;
+    if (ty == NT_REG) {
+        r += s.idz2 * v[u - s.sk];
+        r += s.idy2 * v[u - s.sj];
+        r += s.idx2 * v[u - 1];
+        r += diag * v[u];
+        r += s.idx2 * v[u + 1];
+        r += s.idy2 * v[u + s.sj];
+        r += s.idz2 * v[u + s.sk];
+    } else if (ty == NT_DIRICHLET) {
+        r += diag * v[u];
+    } else {
+        double id = (ty <= NT_I1) ? s.idx : ((ty <= NT_J1) ? s.idy : s.idz);
+        r += diag * v[u];
+        r += (-id) * v[nbr_of(s, u, ty)];
+    }
+    return r;
+}
+
+__device__ __forceinline__ double a_diag(const StencilC &s, int ty)
+{
+    if (ty == NT_REG) return -2.0 * (s.idx2 + s.idy2 + s.idz2);
+    if (ty == NT_DIRICHLET) return 1;
+    return (ty <= NT_I1) ? s.idx : ((ty <= NT_J1) ? s.idy : s.idz);
+}
+
+// b of solveNRPCG (PotentialSolver.cpp:240-245)
+__global__ void k_nr_rhs(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                         const double *__restrict__ x, double *__restrict__ b)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= s.nn) return;
+    int ty = type[u];
+    if (ty == NT_REG) b[u] = -rho[u] / C_EPS_0;
+    else if (ty == NT_DIRICHLET) b[u] = x[u];
+    else b[u] = 0;
+}
+
+// F = A x - b - b(x), P, J diagonal and its inverse (PotentialSolver.cpp:252-267, 304)
+__global__ void k_nr_linearise(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ x,
+                               const double *__restrict__ b, double phi0, double Te0, double n0,
+                               double *__restrict__ F, double *__restrict__ diagJ, double *__restrict__ minv)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= s.nn) return;
+    int ty = type[u];
+    double ad = a_diag(s, ty);
+    double f = apply_row(s, ty, ad, x, u) - b[u];
+    double P = 0;
+    if (ty == NT_REG) {
+        double ex = exp((x[u] - phi0) / Te0);
+        f -= C_QE * n0 * ex / C_EPS_0;
+        P = n0 * C_QE / (C_EPS_0 * Te0) * ex;
+    }
+    double dj = ad - P;
+    F[u] = f;
+    diagJ[u] = dj;
+    minv[u] = 1.0 / dj;
+}
+
+struct PcgArgs {
+    StencilC s;
+    const uint8_t *type;
+    const double *diagJ, *minv, *b;
+    double *x, *g, *sv, *d, *z;
+    double *part;        // 3 * gridDim partial sums
+    int max_it;
+    double tol;
+    double *out;         // out[0] = converged, out[1] = iterations, out[2] = l2
+};
+
+// Sum of the per-block partials, computed redundantly by every block with the same fixed tree: all blocks get the
+// identical value (uniform control flow) and the result is reproducible run to run.
+__device__ __forceinline__ double grid_total(const double *part, int n, double *sh, double *bcast)
+{
+    double a = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += __ldcg(part + i);
+    double t = block_sum(a, sh);
+    if (threadIdx.x == 0) *bcast = t;
+    __syncthreads();
+    t = *bcast;
+    __syncthreads();
+    return t;
+}
+
+// PotentialSolver::solvePCGLinear (PotentialSolver.cpp:299-331) as one persistent cooperative kernel.
+__global__ void __launch_bounds__(512) k_pcg(PcgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    __shared__ double bc;
+    const StencilC &s = a.s;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nb = gridDim.x;
+    double *pA = a.part, *pB = a.part + nb, *pC = a.part + 2 * nb;
+
+    // g = A x - b ; s = M g ; d = -s ; alpha = g.s      (:307-309)
+    double acc = 0;
+    for (long long u = t0; u < s.nn; u += stride) {
+        int ty = a.type[u];
+        double g = apply_row(s, ty, a.diagJ[u], a.x, u) - a.b[u];
+        double sv = 0 + a.minv[u] * g;
+        a.g[u] = g; a.sv[u] = sv; a.d[u] = -1 * sv;
+        acc += g * sv;
+    }
+    double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) pB[blockIdx.x] = t;
+    grid.sync();
+    double alpha = grid_total(pB, nb, sh, &bc);
+    double l2 = 0;
+    int it = 0, converged = 0;
+    for (it = 0; it < a.max_it; it++) {
+        // z = A d ; beta = d.z
+        acc = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            int ty = a.type[u];
+            double z = apply_row(s, ty, a.diagJ[u], a.d, u);
+            a.z[u] = z;
+            acc += a.d[u] * z;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pA[blockIdx.x] = t;
+        grid.sync();
+        double beta = grid_total(pA, nb, sh, &bc);
+        double ab = alpha / beta;
+        // x += ab d ; g += ab z ; s = M g ; alpha' = g.s ; |g|^2
+        acc = 0;
+        double acc2 = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            a.x[u] = a.x[u] + ab * a.d[u];
+            double g = a.g[u] + ab * a.z[u];
+            double sv = 0 + a.minv[u] * g;
+            a.g[u] = g; a.sv[u] = sv;
+            acc += g * sv;
+            acc2 += g * g;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pB[blockIdx.x] = t;
+        t = block_sum(acc2, sh);
+        if (threadIdx.x == 0) pC[blockIdx.x] = t;
+        grid.sync();
+        beta = alpha;
+        alpha = grid_total(pB, nb, sh, &bc);
+        double gg = grid_total(pC, nb, sh, &bc);
+        double cb = alpha / beta;
+        // d = (alpha/beta) d - s
+        for (long long u = t0; u < s.nn; u += stride) a.d[u] = cb * a.d[u] - a.sv[u];
+        l2 = sqrt(gg / (double)s.nn);
+        if (l2 < a.tol) { converged = 1; it++; break; }
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; }
+}
+
+// one colour of PotentialSolver::solveGSLinear (PotentialSolver.cpp:441-449), red-black order, w = 1
+__global__ void __launch_bounds__(256) k_gsl_color(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ diagJ,
+                                                   const double *__restrict__ b, double *__restrict__ x, int color)
+{
+    const int hi = (s.ni + 1) >> 1;
+    long long t = blockIdx.x * 256ll + threadIdx.x;
+    long long total = (long long)hi * s.nj * s.nk;
+    if (t >= total) return;
+    int ih = (int)(t % hi), j = (int)((t / hi) % s.nj), k = (int)(t / ((long long)hi * s.nj));
+    int i = 2 * ih + ((j + k + color) & 1);
+    if (i >= s.ni) return;
+    long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+    int ty = type[u];
+    double dj = diagJ[u];
+    double S = apply_row(s, ty, dj, x, u) - dj * x[u];
+    double phi_new = (b[u] - S) / dj;
+    x[u] = x[u] + 1. * (phi_new - x[u]);
+}
+
+// |J x - b|^2 partial sums (PotentialSolver.cpp:454-456)
+__global__ void __launch_bounds__(256) k_lin_residual(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ diagJ,
+                                                      const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double sum = 0;
+    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < s.nn; u += (long long)gridDim.x * 256) {
+        double R = apply_row(s, type[u], diagJ[u], x, u) - b[u];
+        sum += R * R;
+    }
+    double t = block_sum(sum, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// y[DIRICHLET]=0 ; x -= y ; |y|^2   (PotentialSolver.cpp:274-280)
+__global__ void __launch_bounds__(256) k_nr_update(StencilC s, const uint8_t *__restrict__ type, double *__restrict__ y,
+                                                   double *__restrict__ x, double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double sum = 0;
+    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < s.nn; u += (long long)gridDim.x * 256) {
+        double yy = y[u];
+        if (type[u] == NT_DIRICHLET) { yy = 0; y[u] = 0; }
+        x[u] = x[u] - yy;
+        sum += yy * yy;
+    }
+    double t = block_sum(sum, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+static int solve_gs_linear(espic_ctx *c, const StencilC &s, const double *diagJ, const double *b, double *x,
+                           int max_it, double tol, espic_solve_info *info)
+{
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 4 * c->sm_count);
+    const long long half = (long long)((s.ni + 1) >> 1) * s.nj * s.nk;
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    double L2 = 0;
+    bool converged = false;
+    int r;
+    long long it;
+    for (it = 0; it < max_it; it++) {
+        for (int color = 0; color < 2; color++) {
+            k_gsl_color<<<nblk(half, 256), 256, 0, c->stream>>>(s, c->node_type, diagJ, b, x, color);
+            LAUNCH_CHECK(c);
+        }
+        if (it % 25 == 0) {
+            k_lin_residual<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, diagJ, b, x, c->red);
+            LAUNCH_CHECK(c);
+            k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb_res, dres);
+            LAUNCH_CHECK(c);
+            double sum;
+            if ((r = read_scalar(c, dres, &sum))) return r;
+            L2 = sqrt(sum / (double)s.nn);
+            if (L2 < tol) { converged = true; it++; break; }
+        }
+    }
+    if (!converged) fprintf(stderr, "GS failed to converge, L2=%g\n", L2);
+    info->gs_iters += it;
+    info->residual = L2;
+    return 0;
+}
+
+static int solve_nrpcg_ref(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info)
+{
+    int r;
+    if ((r = ensure_node_types(c, 0))) return r;
+    if ((r = ensure_sv(c, 8))) return r;
+    StencilC s = make_stencil(c->m);
+    double *b = c->sv[0], *F = c->sv[1], *diagJ = c->sv[2], *minv = c->sv[3];
+    double *y = c->sv[4], *g = c->sv[5], *sv = c->sv[6], *d = c->sv[7];
+    // ninth vector z and the partial sums share the reduction scratch: [0,nn) = z, behind it the partials
+    if ((r = ensure_buf(&c->red, &c->red_cap, std::max<long long>(s.nn + 4096, 8192), c->stream))) return r;
+    double *z = c->red;
+    double *part = c->red + s.nn;
+
+    // cooperative grid: as many co-resident blocks as useful
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_pcg, 512, 0));
+    if (bps < 1) { espic_set_error("k_pcg cannot be made resident"); return -1; }
+    long long want = (s.nn + 511) / 512;
+    int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
+    if (3 * grid > 4096) grid = 4096 / 3;
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
+
+    double *dout = reinterpret_cast<double *>(c->dscal + 24);
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    k_nr_rhs<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, b);
+    LAUNCH_CHECK(c);
+    CK(cudaMemsetAsync(y, 0, (size_t)s.nn * sizeof(double), c->stream));
+    double norm = 0;
+    bool converged = false;
+    for (int it = 0; it < p->nr_max_it; it++) {
+        info->nr_iters++;
+        k_nr_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, b, p->phi0, p->Te0, p->n0, F, diagJ, minv);
+        LAUNCH_CHECK(c);
+        PcgArgs a;
+        a.s = s; a.type = c->node_type; a.diagJ = diagJ; a.minv = minv; a.b = F;
+        a.x = y; a.g = g; a.sv = sv; a.d = d; a.z = z; a.part = part;
+        a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
+        void *args[] = {&a};
+        CK(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(grid), dim3(512), args, 0, c->stream));
+        LAUNCH_CHECK(c);
+        double *h = reinterpret_cast<double *>(c->hpin) + 24;
+        CK(cudaMemcpyAsync(h, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        info->lin_iters += (long long)h[1];
+        if (h[0] == 0.0) {
+            fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
+            info->gs_fallbacks++;
+            if ((r = solve_gs_linear(c, s, diagJ, F, y, p->max_it, p->tol, info))) return r;
+        }
+        k_nr_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, y, c->phi, part);
+        LAUNCH_CHECK(c);
+        k_sum_final<<<1, 256, 0, c->stream>>>(part, nb_res, dres);
+        LAUNCH_CHECK(c);
+        double sum;
+        if ((r = read_scalar(c, dres, &sum))) return r;
+        norm = sqrt(sum / (double)s.nn);
+        if (norm < p->nr_tol) { converged = true; break; }
+    }
+    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
+    info->converged = converged;
+    info->residual = norm;
+    return 0;
+}
+
+// ================================================================================================================
+// Robust Newton + Jacobi-PCG on the symmetric positive definite form of the same discrete system.
+//
+// The reference assembles identity rows for Dirichlet nodes and one-sided first-order rows for Neumann face nodes
+// (buildMatrix, PotentialSolver.cpp:171-198); the resulting matrix is non-symmetric and indefinite and the
+// reference's own CG breaks down on it (7 "PCG failed" fall-backs in its shipped run; NaN on every mesh we tried with
+// n0=1e12 -- reproduced with the oracle).  The discrete equations themselves are fine, so this solver eliminates
+// them exactly instead of iterating on them:
+//   * unknowns are the REG nodes only; a Dirichlet neighbour's value is known and enters the residual;
+//   * a Neumann face neighbour equals its inner node (phi_face = phi_inner, the face row of the reference), and for a REG
+//     node next to a face that inner node is the REG node itself -> the coefficient folds into the diagonal;
+//   * K = -(L - diag(P)) on the REG nodes is symmetric positive definite, so Jacobi-PCG is guaranteed to converge;
+//   * afterwards the face, edge and corner nodes are set from their mirrors in the reference's priority order i,j,k.
+// The converged phi satisfies exactly the equations the reference's solveGS / solveNRPCG iterate on (same residual
+// formula, PotentialSolver.cpp:389-421), so it is compared against the reference at the solver tolerance.
+// ================================================================================================================
+
+// diag0[u] = 2(idx2+idy2+idz2) - sum over Neumann neighbours of their coefficient (REG nodes), 0 elsewhere
+__global__ void __launch_bounds__(256) k_spd_diag0(StencilC s, const uint8_t *__restrict__ type, double *__restrict__ diag0)
+{
+    long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= s.nn) return;
+    double d = 0;
+    if (type[u] == NT_REG) {
+        d = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
+        if (type[u - 1] >= NT_I0) d -= s.gdx2;
+        if (type[u + 1] >= NT_I0) d -= s.gdx2;
+        if (type[u - s.sj] >= NT_I0) d -= s.gdy2;
+        if (type[u + s.sj] >= NT_I0) d -= s.gdy2;
+        if (type[u - s.sk] >= NT_I0) d -= s.gdz2;
+        if (type[u + s.sk] >= NT_I0) d -= s.gdz2;
+    }
+    diag0[u] = d;
+}
+
+// Newton residual R (the reference's GS residual with face neighbours folded), Jacobian diagonal and its inverse.
+__global__ void __launch_bounds__(256) k_spd_linearise(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                                                       const double *__restrict__ phi, const double *__restrict__ diag0,
+                                                       double phi0, double Te0, double n0,
+                                                       double *__restrict__ R, double *__restrict__ diagJ, double *__restrict__ minv,
+                                                       double *__restrict__ delta)
+{
+    long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= s.nn) return;
+    double r = 0, dj = 0, mi = 0;
+    if (type[u] == NT_REG) {
+        const double p = phi[u];
+        const double ex = exp((p - phi0) / Te0);
+        const double src = (rho[u] - C_QE * (n0 * ex)) / C_EPS_0;
+        const double xm = (type[u - 1] >= NT_I0) ? p : phi[u - 1];
+        const double xp = (type[u + 1] >= NT_I0) ? p : phi[u + 1];
+        const double ym = (type[u - s.sj] >= NT_I0) ? p : phi[u - s.sj];
+        const double yp = (type[u + s.sj] >= NT_I0) ? p : phi[u + s.sj];
+        const double zm = (type[u - s.sk] >= NT_I0) ? p : phi[u - s.sk];
+        const double zp = (type[u + s.sk] >= NT_I0) ? p : phi[u + s.sk];
+        r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
+        dj = diag0[u] + n0 * C_QE / (C_EPS_0 * Te0) * ex;
+        mi = 1.0 / dj;
+    }
+    R[u] = r; diagJ[u] = dj; minv[u] = mi; delta[u] = 0;
+}
+
+struct SpdArgs {
+    StencilC s;
+    const double *diagJ, *minv;
+    double *delta, *r, *sv, *d, *z;    // r enters holding the right-hand side R; all vectors are 0 on non-REG nodes
+    double *part;
+    int max_it;
+    double tol;
+    double *out;                       // converged, iterations, l2
+};
+
+// (K d)[u] = diagJ d_u - sum_nbr c d_nbr : d is identically 0 outside the REG set, so no neighbour masks are needed
+__device__ __forceinline__ double apply_K(const StencilC &s, double dj, const double *d, long long u)
+{
+    return dj * d[u] - (s.gdx2 * (d[u - 1] + d[u + 1]) + s.gdy2 * (d[u - s.sj] + d[u + s.sj]) + s.gdz2 * (d[u - s.sk] + d[u + s.sk]));
+}
+
+__global__ void __launch_bounds__(512) k_spd_pcg(SpdArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    __shared__ double bc;
+    const StencilC &s = a.s;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nb = gridDim.x;
+    double *pA = a.part, *pB = a.part + nb, *pC = a.part + 2 * nb;
+    // delta = 0: r = R, s = M r, d = s
+    double acc = 0, acc2 = 0;
+    for (long long u = t0; u < s.nn; u += stride) {
+        double r = a.r[u];
+        double sv = a.minv[u] * r;
+        a.sv[u] = sv; a.d[u] = sv;
+        acc += r * sv; acc2 += r * r;
+    }
+    double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) pB[blockIdx.x] = t;
+    t = block_sum(acc2, sh);
+    if (threadIdx.x == 0) pC[blockIdx.x] = t;
+    grid.sync();
+    double alpha = grid_total(pB, nb, sh, &bc);
+    double l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+    int it = 0, converged = l2 < a.tol;
+    while (!converged && it < a.max_it) {
+        acc = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            double dj = a.diagJ[u];
+            double z = 0;
+            if (dj != 0) { z = apply_K(s, dj, a.d, u); acc += a.d[u] * z; }
+            a.z[u] = z;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pA[blockIdx.x] = t;
+        grid.sync();
+        const double beta = grid_total(pA, nb, sh, &bc);
+        const double ab = alpha / beta;
+        acc = 0; acc2 = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            a.delta[u] = a.delta[u] + ab * a.d[u];
+            double r = a.r[u] - ab * a.z[u];
+            double sv = a.minv[u] * r;
+            a.r[u] = r; a.sv[u] = sv;
+            acc += r * sv; acc2 += r * r;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pB[blockIdx.x] = t;
+        t = block_sum(acc2, sh);
+        if (threadIdx.x == 0) pC[blockIdx.x] = t;
+        grid.sync();
+        const double alpha_new = grid_total(pB, nb, sh, &bc);
+        l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+        const double cb = alpha_new / alpha;
+        alpha = alpha_new;
+        it++;
+        if (l2 < a.tol) { converged = 1; break; }
+        for (long long u = t0; u < s.nn; u += stride) a.d[u] = a.sv[u] + cb * a.d[u];
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; }
+}
+
+// phi += delta on REG nodes; sum of delta^2 counted once per node that takes the value (REG + the face nodes mirroring it)
+__global__ void __launch_bounds__(256) k_spd_update(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ delta,
+                                                    double *__restrict__ phi, double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double sum = 0;
+    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < s.nn; u += (long long)gridDim.x * 256) {
+        if (type[u] != NT_REG) continue;
+        double dl = delta[u];
+        phi[u] = phi[u] + dl;
+        int cnt = 1 + (type[u - 1] >= NT_I0) + (type[u + 1] >= NT_I0) + (type[u - s.sj] >= NT_I0) + (type[u + s.sj] >= NT_I0) +
+                  (type[u - s.sk] >= NT_I0) + (type[u + s.sk] >= NT_I0);
+        sum += cnt * (dl * dl);
+    }
+    double t = block_sum(sum, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// Neumann nodes take their mirror's value (PotentialSolver.cpp:358-369).  level 0: faces (mirror is REG/Dirichlet),
+// level 1: edges (mirror is a face node), level 2: corners.
+__global__ void __launch_bounds__(256) k_mirror(StencilC s, const uint8_t *__restrict__ type, double *__restrict__ phi, int level)
+{
+    long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= s.nn) return;
+    int ty = type[u];
+    if (ty < NT_I0) return;
+    int i = (int)(u % s.ni), j = (int)((u / s.ni) % s.nj), k = (int)(u / s.sk);
+    int nb = (i == 0 || i == s.ni - 1) + (j == 0 || j == s.nj - 1) + (k == 0 || k == s.nk - 1);
+    if (nb - 1 != level) return;
+    phi[u] = phi[nbr_of(s, u, ty)];
+}
+
+static int solve_nrpcg_spd(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info)
+{
+    int r;
+    if ((r = ensure_node_types(c, 0))) return r;
+    if ((r = ensure_sv(c, 8))) return r;
+    StencilC s = make_stencil(c->m);
+    double *diag0 = c->sv[0], *R = c->sv[1], *diagJ = c->sv[2], *minv = c->sv[3];
+    double *delta = c->sv[4], *sv = c->sv[5], *d = c->sv[6], *z = c->sv[7];
+    if ((r = ensure_buf(&c->red, &c->red_cap, 8192, c->stream))) return r;
+    double *part = c->red;
+    if (c->diag0_version != c->geom_version) {
+        k_spd_diag0<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, diag0);
+        LAUNCH_CHECK(c);
+        c->diag0_version = c->geom_version;
+    }
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_spd_pcg, 512, 0));
+    if (bps < 1) { espic_set_error("k_spd_pcg cannot be made resident"); return -1; }
+    long long want = (s.nn + 511) / 512;
+    int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
+    if (3 * grid > 4096) grid = 4096 / 3;
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
+    double *dout = reinterpret_cast<double *>(c->dscal + 24);
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    double norm = 0;
+    bool converged = false;
+    for (int it = 0; it < p->nr_max_it; it++) {
+        info->nr_iters++;
+        k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, diag0, p->phi0, p->Te0, p->n0,
+                                                                R, diagJ, minv, delta);
+        LAUNCH_CHECK(c);
+        SpdArgs a;
+        a.s = s; a.diagJ = diagJ; a.minv = minv; a.delta = delta; a.r = R; a.sv = sv; a.d = d; a.z = z;
+        a.part = part + 1024; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
+        void *args[] = {&a};
+        CK(cudaLaunchCooperativeKernel((void *)k_spd_pcg, dim3(grid), dim3(512), args, 0, c->stream));
+        LAUNCH_CHECK(c);
+        k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
+        LAUNCH_CHECK(c);
+        k_sum_final<<<1, 256, 0, c->stream>>>(part, nb_res, dres);
+        LAUNCH_CHECK(c);
+        double *h = reinterpret_cast<double *>(c->hpin) + 24;
+        CK(cudaMemcpyAsync(h, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        double sum;
+        if ((r = read_scalar(c, dres, &sum))) return r;
+        info->lin_iters += (long long)h[1];
+        if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
+        norm = sqrt(sum / (double)s.nn);
+        if (norm < p->nr_tol) { converged = true; break; }
+    }
+    for (int level = 0; level < 3; level++) {
+        k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
+        LAUNCH_CHECK(c);
+    }
+    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
+    info->converged = converged;
+    info->residual = norm;
+    return 0;
+}
+
+extern "C" int espic_solve(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info_out)
+{
+    CK(cudaSetDevice(c->device));
+    espic_solve_info info;
+    memset(&info, 0, sizeof(info));
+    int r = 0;
+    switch (p->type) {
+        case ESPIC_SOLVE_QN:
+            k_qn<<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, c->object_id, c->rho, c->phi, p->phi0, p->Te0, p->n0 * C_QE);
+            LAUNCH_CHECK(c);
+            info.converged = 1;
+            break;
+        case ESPIC_SOLVE_GS: r = solve_sor(c, p, false, &info); break;
+        case ESPIC_SOLVE_GS_BOX: r = solve_sor(c, p, true, &info); break;
+        case ESPIC_SOLVE_PCG: r = solve_nrpcg_spd(c, p, &info); break;
+        case ESPIC_SOLVE_PCG_REF: r = solve_nrpcg_ref(c, p, &info); break;
+        default: espic_set_error("espic_solve: unknown solver type %d", p->type); return -1;
+    }
+    if (info_out) *info_out = info;
+    return r;
+}
+
+// ---- E = -grad(phi) -------------------------------------------------------------------------------------
+
+// PotentialSolver::computeEF (PotentialSolver.cpp:465-504)
+__global__ void __launch_bounds__(256) k_ef(StencilC s, double dx, double dy, double dz, const double *__restrict__ phi,
+                                            double *__restrict__ ef)
+{
+    long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= s.nn) return;
+    int i = (int)(u % s.ni), j = (int)((u / s.ni) % s.nj), k = (int)(u / s.sk);
+    double p = phi[u];
+    double ex, ey, ez;
+    if (i == 0) ex = -(-3 * p + 4 * phi[u + 1] - phi[u + 2]) / (2 * dx);
+    else if (i == s.ni - 1) ex = -(phi[u - 2] - 4 * phi[u - 1] + 3 * p) / (2 * dx);
+    else ex = -(phi[u + 1] - phi[u - 1]) / (2 * dx);
+    if (j == 0) ey = -(-3 * p + 4 * phi[u + s.sj] - phi[u + 2 * s.sj]) / (2 * dy);
+    else if (j == s.nj - 1) ey = -(phi[u - 2 * s.sj] - 4 * phi[u - s.sj] + 3 * p) / (2 * dy);
+    else ey = -(phi[u + s.sj] - phi[u - s.sj]) / (2 * dy);
+    if (k == 0) ez = -(-3 * p + 4 * phi[u + s.sk] - phi[u + 2 * s.sk]) / (2 * dz);
+    else if (k == s.nk - 1) ez = -(phi[u - 2 * s.sk] - 4 * phi[u - s.sk] + 3 * p) / (2 * dz);
+    else ez = -(phi[u + s.sk] - phi[u - s.sk]) / (2 * dz);
+    ef[3 * u] = ex; ef[3 * u + 1] = ey; ef[3 * u + 2] = ez;
+}
+
+extern "C" int espic_compute_ef(espic_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    StencilC s = make_stencil(c->m);
+    k_ef<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->m.dh[0], c->m.dh[1], c->m.dh[2], c->phi, c->ef);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+// World::getPE (World.cpp:72-84)
+__global__ void __launch_bounds__(256) k_pe(long long nn, const double *__restrict__ ef, const double *__restrict__ node_vol,
+                                            double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double sum = 0;
+    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < nn; u += (long long)gridDim.x * 256) {
+        double a = ef[3 * u], b = ef[3 * u + 1], cc = ef[3 * u + 2];
+        double ef2 = a * a + b * b + cc * cc;
+        sum += ef2 * node_vol[u];
+    }
+    double t = block_sum(sum, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+extern "C" int espic_field_pe(espic_ctx *c, double *pe)
+{
+    CK(cudaSetDevice(c->device));
+    const int nb = std::min<long long>(nblk(c->m.nn, 256), 4 * c->sm_count);
+    int r;
+    if ((r = ensure_buf(&c->red, &c->red_cap, nb, c->stream))) return r;
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    k_pe<<<nb, 256, 0, c->stream>>>(c->m.nn, c->ef, c->node_vol, c->red);
+    LAUNCH_CHECK(c);
+    k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb, dres);
+    LAUNCH_CHECK(c);
+    double sum;
+    if ((r = read_scalar(c, dres, &sum))) return r;
+    *pe = 0.5 * C_EPS_0 * sum;
+    return 0;
+}
+
+// Field::updateAverage (Field.h:214-221)
+__global__ void k_update_average(long long nn, const double *__restrict__ inst, double *__restrict__ ave, int samples)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= nn) return;
+    ave[u] = (inst[u] + samples * ave[u]) / (samples + 1);
+}
+
+extern "C" int espic_update_average(espic_ctx *c, int sp)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    k_update_average<<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, s.den, s.den_ave, s.ave_samples);
+    LAUNCH_CHECK(c);
+    s.ave_samples++;
+    return 0;
+}

@@ -1,0 +1,173 @@
+// espic_internal.cuh -- shared state and device helpers of libespic_cuda.so (sm_100a only).
+// Compiled with -fmad=false: every FP64 expression keeps the reference's operation order and
+// rounding, so per-particle and per-node results are bit-identical to g++ -O2 on x86-64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "espic.h"
+
+#define ESPIC_MAX_SPECIES 8
+
+struct MeshC {
+    int ni, nj, nk;
+    long long nn;
+    double x0[3], xm[3], dh[3];
+    double sc[3];     // sphere centre
+    double sr2;       // sphere radius^2 (0: World default, World.h:136-137)
+};
+
+struct Species {
+    double mass = 0, charge = 0, mpw0 = 0;
+    long long np = 0, cap = 0;
+    double *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // x y z vx vy vz mpw
+    double *alt[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};    // sort double buffer
+    long long alt_cap = 0;
+    double *den = nullptr, *den_ave = nullptr;
+    double *acc = nullptr;             // FP64 scatter accumulator (also aliased as int64 in fixed-point mode)
+    int ave_samples = 0;
+    bool acc_fresh = false;            // accumulator holds the scatter of the current particle state
+    int acc_mode = ESPIC_DEPOSIT_FP64;
+    int acc_shift = 0;                 // fixed point: value * 2^shift
+    double mpw_max = 0;                // upper bound of any mpw seen (fixed-point scale)
+};
+
+struct espic_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    MeshC m;
+    double xc[3];
+    double *phi = nullptr, *rho = nullptr, *ef = nullptr, *node_vol = nullptr;
+    int32_t *object_id = nullptr;
+    int nsp = 0;
+    Species sp[ESPIC_MAX_SPECIES];
+    long long launches = 0;
+    // scratch
+    uint32_t *dead_words = nullptr; long long dead_words_cap = 0;
+    uint32_t *scan_pre = nullptr;  long long scan_cap = 0;
+    uint32_t *scan_coff = nullptr; long long scan_coff_cap = 0;
+    long long *lists = nullptr;    long long lists_cap = 0;   // holes | fillers
+    double *red = nullptr;         long long red_cap = 0;     // reduction partials
+    unsigned long long *dscal = nullptr;                      // small device scalars (64 x 8 B)
+    void *hpin = nullptr;                                     // pinned host mirror of dscal (64 x 8 B)
+    uint32_t *cell_cnt = nullptr;  long long cell_cap = 0;
+    // solver work vectors
+    double *sv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t *node_type = nullptr;
+    int node_type_mode = -1;       // which solver family node_type was built for
+    long long geom_version = 0, node_type_version = -1, diag0_version = -1;
+    int sm_count = 148;
+    // comm
+    void *nccl = nullptr; int rank = 0, nranks = 1;
+};
+
+void espic_set_error(const char *fmt, ...);
+int  espic_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return espic_cuda_fail(e_, #call, __FILE__, __LINE__); } while (0)
+#define LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return espic_cuda_fail(e_, "kernel launch", __FILE__, __LINE__); } while (0)
+
+int espic_ensure(void **ptr, long long *cap, long long need, size_t elem, cudaStream_t s);
+template <typename T> static inline int ensure_buf(T **ptr, long long *cap, long long need, cudaStream_t s)
+{
+    return espic_ensure((void **)ptr, cap, need, sizeof(T), s);
+}
+
+// generic exclusive scan of uint32 (two level).  After the call: prefix of element w is
+// pre[w] + coff[w >> SCAN_CHUNK_LOG2]; the grand total is in *d_total (device, 64 bit).
+#define SCAN_CHUNK_LOG2 13
+int espic_scan_u32(espic_ctx *ctx, const uint32_t *in, long long n, unsigned long long *d_total);
+
+// espic_comm.cu
+void espic_comm_destroy(espic_ctx *c);
+int  espic_comm_max_double(espic_ctx *c, double *v);
+int  espic_comm_allreduce_acc(espic_ctx *c, Species &s);
+
+// ---- device helpers ---------------------------------------------------------------------------
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ long long node_u(const MeshC &m, int i, int j, int k)
+{
+    return ((long long)k * m.nj + j) * (long long)m.ni + i;
+}
+
+// World::XtoL (World.h:75-81) + (int) truncation of Field::gather/scatter (Field.h:169-176).
+// lc can round to exactly n-1 just below xm; the reference then reads node n (UB) with weight 0:
+// clamp the cell to n-2 (fraction becomes exactly 1), see oracle cell_of().
+__device__ __forceinline__ void cell_frac(double x, double x0, double dh, int n, int &i, double &d)
+{
+    double lc = (x - x0) / dh;
+    int ii = (int)lc;
+    if (ii > n - 2) ii = n - 2;
+    i = ii;
+    d = lc - (double)ii;
+}
+
+// Field3::gather (Field.h:189-211): eight terms, each data*w_i*w_j*w_k left to right, summed in the reference's order.
+__device__ __forceinline__ void gather_ef(const MeshC &m, const double *__restrict__ ef,
+                                          int i, int j, int k, double di, double dj, double dk, double e[3])
+{
+    const long long u000 = node_u(m, i, j, k);
+    const long long sj = m.ni, sk = (long long)m.ni * m.nj;
+    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
+    const long long n0 = u000, n1 = u000 + 1, n2 = u000 + 1 + sj, n3 = u000 + sj;
+    const long long n4 = n0 + sk, n5 = n1 + sk, n6 = n2 + sk, n7 = n3 + sk;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double v = __ldg(ef + 3 * n0 + c) * ai * aj * ak;
+        v = v + __ldg(ef + 3 * n1 + c) * di * aj * ak;
+        v = v + __ldg(ef + 3 * n2 + c) * di * dj * ak;
+        v = v + __ldg(ef + 3 * n3 + c) * ai * dj * ak;
+        v = v + __ldg(ef + 3 * n4 + c) * ai * aj * dk;
+        v = v + __ldg(ef + 3 * n5 + c) * di * aj * dk;
+        v = v + __ldg(ef + 3 * n6 + c) * di * dj * dk;
+        v = v + __ldg(ef + 3 * n7 + c) * ai * dj * dk;
+        e[c] = v;
+    }
+}
+
+// World::inSphere (World.cpp:118-125)
+__device__ __forceinline__ bool in_sphere(const MeshC &m, double x, double y, double z)
+{
+    double r0 = x - m.sc[0], r1 = y - m.sc[1], r2 = z - m.sc[2];
+    double r_mag2 = (r0 * r0 + r1 * r1 + r2 * r2);
+    return r_mag2 <= m.sr2;
+}
+
+// World::inBounds (World.h:59-63)
+__device__ __forceinline__ bool in_bounds(const MeshC &m, double x, double y, double z)
+{
+    if (x < m.x0[0] || x >= m.xm[0]) return false;
+    if (y < m.x0[1] || y >= m.xm[1]) return false;
+    if (z < m.x0[2] || z >= m.xm[2]) return false;
+    return true;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0.  blockDim.x must be a multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 */)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,653 @@
+// espic_particles.cu -- Species::advance / computeNumberDensity / addParticle / ColdBeamSource::sample /
+// diagnostics as sm_100a kernels over SoA particle arrays (include/espic.h).
+#include "espic_internal.cuh"
+#include <algorithm>
+#include <math.h>
+
+#define SP_CHECK(c, sp) do { if ((sp) < 0 || (sp) >= (c)->nsp) { espic_set_error("bad species id %d", (sp)); return -1; } } while (0)
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// =====================================================================================================
+// exclusive scan of uint32 (two level, chunk = 8192 elements)
+// =====================================================================================================
+
+#define SCAN_CHUNK (1 << SCAN_CHUNK_LOG2)
+
+__global__ void __launch_bounds__(256) k_scan_l1(const uint32_t *__restrict__ in, long long n,
+                                                 uint32_t *__restrict__ pre, uint32_t *__restrict__ ctot)
+{
+    __shared__ uint32_t wsum[8];
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * 32;
+    uint32_t v[32];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        long long i = base + q;
+        v[q] = (i < n) ? in[i] : 0u;
+        tsum += v[q];
+    }
+    // block exclusive scan of tsum
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int q = 0; q < w; q++) woff += wsum[q];
+    uint32_t run = woff + inc - tsum;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        long long i = base + q;
+        if (i < n) pre[i] = run;
+        run += v[q];
+    }
+    if (threadIdx.x == 255) ctot[blockIdx.x] = woff + inc;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_l2(uint32_t *__restrict__ ctot, long long nchunks, unsigned long long *total)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long long b = 0; b < nchunks; b += 1024) {
+        long long i = b + threadIdx.x;
+        unsigned long long v = (i < nchunks) ? ctot[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        unsigned long long woff = 0;
+        for (int q = 0; q < w; q++) woff += wsum[q];
+        unsigned long long carry = carry_s;
+        if (i < nchunks) ctot[i] = (uint32_t)(carry + woff + inc - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+int espic_scan_u32(espic_ctx *c, const uint32_t *in, long long n, unsigned long long *d_total)
+{
+    long long nchunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (nchunks < 1) nchunks = 1;
+    int r;
+    if ((r = ensure_buf(&c->scan_pre, &c->scan_cap, n, c->stream))) return r;
+    if ((r = ensure_buf(&c->scan_coff, &c->scan_coff_cap, nchunks, c->stream))) return r;
+    k_scan_l1<<<(unsigned)nchunks, 256, 0, c->stream>>>(in, n, c->scan_pre, c->scan_coff);
+    LAUNCH_CHECK(c);
+    k_scan_l2<<<1, 1024, 0, c->stream>>>(c->scan_coff, nchunks, d_total);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+__device__ __forceinline__ unsigned long long scan_at(const uint32_t *__restrict__ pre, const uint32_t *__restrict__ coff, long long w)
+{
+    return (unsigned long long)pre[w] + coff[w >> SCAN_CHUNK_LOG2];
+}
+
+// =====================================================================================================
+// scatter (Field::scatter, Field.h:167-186) into an accumulator
+// =====================================================================================================
+
+template <int MODE>
+__device__ __forceinline__ void acc_add(double *acc, long long u, double w, double scale)
+{
+    if (MODE == ESPIC_DEPOSIT_FP64) {
+        atomicAdd(acc + u, w);
+    } else {
+        long long q = __double2ll_rn(w * scale);
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + u, (unsigned long long)q);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void scatter_particle(const MeshC &m, double *acc, double x, double y, double z, double mpw, double scale)
+{
+    int i, j, k; double di, dj, dk;
+    cell_frac(x, m.x0[0], m.dh[0], m.ni, i, di);
+    cell_frac(y, m.x0[1], m.dh[1], m.nj, j, dj);
+    cell_frac(z, m.x0[2], m.dh[2], m.nk, k, dk);
+    if (i < 0 || j < 0 || k < 0) return;     // never for in-bounds particles; keeps stray input from writing out of range
+    const long long u = node_u(m, i, j, k);
+    const long long sj = m.ni, sk = (long long)m.ni * m.nj;
+    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
+    acc_add<MODE>(acc, u, mpw * ai * aj * ak, scale);
+    acc_add<MODE>(acc, u + 1, mpw * di * aj * ak, scale);
+    acc_add<MODE>(acc, u + 1 + sj, mpw * di * dj * ak, scale);
+    acc_add<MODE>(acc, u + sj, mpw * ai * dj * ak, scale);
+    acc_add<MODE>(acc, u + sk, mpw * ai * aj * dk, scale);
+    acc_add<MODE>(acc, u + 1 + sk, mpw * di * aj * dk, scale);
+    acc_add<MODE>(acc, u + 1 + sj + sk, mpw * di * dj * dk, scale);
+    acc_add<MODE>(acc, u + sj + sk, mpw * ai * dj * dk, scale);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                 const double *__restrict__ z, const double *__restrict__ mpw,
+                                                 long long n, double *acc, double scale)
+{
+    long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n) return;
+    scatter_particle<MODE>(m, acc, x[idx], y[idx], z[idx], mpw[idx], scale);
+}
+
+// den = acc / node_vol (0 where node_vol == 0): Field::operator/= (Field.h:125-134)
+template <int MODE>
+__global__ void k_den_finalize(long long nn, const double *__restrict__ acc, const double *__restrict__ node_vol,
+                               double *__restrict__ den, double inv_scale)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= nn) return;
+    double a;
+    if (MODE == ESPIC_DEPOSIT_FP64) a = acc[u];
+    else a = (double)reinterpret_cast<const long long *>(acc)[u] * inv_scale;
+    double v = node_vol[u];
+    den[u] = (v != 0) ? a / v : 0.0;
+}
+
+// =====================================================================================================
+// push (Species::advance)
+// =====================================================================================================
+
+template <int WALL, bool FUSE, int MODE>
+__global__ void __launch_bounds__(256) k_push(MeshC m, const double *__restrict__ ef,
+                                              double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
+                                              double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
+                                              double *__restrict__ pmpw, long long n, double s, double dt,
+                                              uint32_t *__restrict__ dead_words, double *acc, double scale)
+{
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    const bool valid = idx < n;
+    bool dead = false;
+    if (valid) {
+        double x = px[idx], y = py[idx], z = pz[idx];
+        double vx = pvx[idx], vy = pvy[idx], vz = pvz[idx];
+        double mpw = pmpw[idx];
+        int i, j, k; double di, dj, dk;
+        cell_frac(x, m.x0[0], m.dh[0], m.ni, i, di);
+        cell_frac(y, m.x0[1], m.dh[1], m.nj, j, dj);
+        cell_frac(z, m.x0[2], m.dh[2], m.nk, k, dk);
+        if (i < 0) i = 0;
+        if (j < 0) j = 0;
+        if (k < 0) k = 0;
+        double e[3];
+        gather_ef(m, ef, i, j, k, di, dj, dk, e);
+        // part.vel += ef_part*(dt*charge/mass);  part.pos += part.vel*dt;   (Species.cpp:22-25)
+        vx = vx + e[0] * s; vy = vy + e[1] * s; vz = vz + e[2] * s;
+        x = x + vx * dt; y = y + vy * dt; z = z + vz * dt;
+        if (WALL == ESPIC_WALL_ABSORB) {
+            // Species.cpp:28-32
+            if (in_sphere(m, x, y, z) || !in_bounds(m, x, y, z)) { mpw = 0; pmpw[idx] = 0; }
+            dead = !(mpw > 0);       // removal test of Species.cpp:39
+        } else {
+            // ch2/Species.cpp:32-36
+            if (x < m.x0[0]) { x = 2 * m.x0[0] - x; vx *= -1.0; } else if (x >= m.xm[0]) { x = 2 * m.xm[0] - x; vx *= -1.0; }
+            if (y < m.x0[1]) { y = 2 * m.x0[1] - y; vy *= -1.0; } else if (y >= m.xm[1]) { y = 2 * m.xm[1] - y; vy *= -1.0; }
+            if (z < m.x0[2]) { z = 2 * m.x0[2] - z; vz *= -1.0; } else if (z >= m.xm[2]) { z = 2 * m.xm[2] - z; vz *= -1.0; }
+        }
+        px[idx] = x; py[idx] = y; pz[idx] = z;
+        pvx[idx] = vx; pvy[idx] = vy; pvz[idx] = vz;
+        if (FUSE && !dead) scatter_particle<MODE>(m, acc, x, y, z, mpw, scale);
+    }
+    if (WALL == ESPIC_WALL_ABSORB) {
+        unsigned w = __ballot_sync(0xffffffffu, valid && dead);
+        if ((threadIdx.x & 31) == 0 && (idx - (threadIdx.x & 31)) < n) dead_words[idx >> 5] = w;
+    }
+}
+
+// ---- removal in the reference's swap-with-last order (Species.cpp:36-46) ------------------------------
+// With D dead among n, L = n-D survivors.  The sequential loop fills the holes (dead, idx < L) in ascending
+// order with the live particles of the tail (idx >= L) taken from the end: hole rank r <- tail-live rank r.
+// e(idx) = #dead before idx (exclusive scan of the per-warp dead words).
+
+__global__ void __launch_bounds__(256) k_dead_popc(const uint32_t *__restrict__ words, long long nw, uint32_t *__restrict__ cnt)
+{
+    long long w = blockIdx.x * 256ll + threadIdx.x;
+    if (w < nw) cnt[w] = __popc(words[w]);
+}
+
+__global__ void __launch_bounds__(256) k_fill_lists(const uint32_t *__restrict__ words, long long nw, long long n,
+                                                    const uint32_t *__restrict__ pre, const uint32_t *__restrict__ coff,
+                                                    const unsigned long long *__restrict__ d_total,
+                                                    long long *__restrict__ holes, long long *__restrict__ fillers)
+{
+    long long w = blockIdx.x * 256ll + threadIdx.x;
+    if (w >= nw) return;
+    const long long D = (long long)*d_total;
+    const long long L = n - D;
+    const uint32_t bitsw = words[w];
+    const long long first = w * 32;
+    if (first + 32 <= L && bitsw == 0) return;          // fully live head word: nothing to record
+    const long long e0 = (long long)scan_at(pre, coff, w);
+    for (int b = 0; b < 32; b++) {
+        long long idx = first + b;
+        if (idx >= n) break;
+        bool dead = (bitsw >> b) & 1u;
+        long long e = e0 + __popc(bitsw & ((1u << b) - 1u));
+        if (dead) { if (idx < L) holes[e] = idx; }
+        else if (idx >= L) fillers[(n - 1 - idx) - D + e] = idx;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_move(long long dmax, const long long *__restrict__ holes, const long long *__restrict__ fillers,
+                                              double *p0, double *p1, double *p2, double *p3, double *p4, double *p5, double *p6)
+{
+    long long r = blockIdx.x * 256ll + threadIdx.x;
+    if (r >= dmax) return;
+    long long h = holes[r];
+    if (h < 0) return;
+    long long f = fillers[r];
+    p0[h] = p0[f]; p1[h] = p1[f]; p2[h] = p2[f]; p3[h] = p3[f]; p4[h] = p4[f]; p5[h] = p5[f]; p6[h] = p6[f];
+}
+
+
+// Fixed point: weights are accumulated as round(w * 2^shift) in int64.  2^shift is chosen so that the sum of every
+// weight in the whole system (all ranks) stays below 2^62; all ranks agree on it through a max-allreduce.
+static int prepare_acc(espic_ctx *c, Species &s, int mode)
+{
+    CK(cudaMemsetAsync(s.acc, 0, (size_t)c->m.nn * sizeof(double), c->stream));
+    s.acc_mode = mode;
+    s.acc_shift = 0;
+    if (mode == ESPIC_DEPOSIT_FIXED) {
+        double bound = (double)std::max<long long>(s.np, 1) * (s.mpw_max > 0 ? s.mpw_max : 1.0);
+        int r = espic_comm_max_double(c, &bound);
+        if (r) return r;
+        bound *= c->nranks;
+        int e;
+        frexp(bound, &e);         // bound < 2^e
+        s.acc_shift = std::min(62 - e, 62);
+    }
+    return 0;
+}
+
+extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int flags)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    const long long n = s.np;
+    const bool fuse = (flags & ESPIC_PUSH_FUSE_DEPOSIT) != 0;
+    const int mode = (flags & ESPIC_PUSH_FIXED_POINT) ? ESPIC_DEPOSIT_FIXED : ESPIC_DEPOSIT_FP64;
+    s.acc_fresh = false;
+    if (fuse) { int r = prepare_acc(c, s, mode); if (r) return r; }
+    if (n == 0) { if (fuse) s.acc_fresh = true; return 0; }
+    const double sfac = dt * s.charge / s.mass;     // Species.cpp:22, evaluated as the reference does
+    const double scale = ldexp(1.0, s.acc_shift);
+    const long long nw = (n + 31) / 32;
+    int r;
+    if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw, c->stream))) return r; }
+    const unsigned grid = nblk(n, 256);
+#define PUSH_ARGS c->m, c->ef, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale
+    if (wall_mode == ESPIC_WALL_ABSORB) {
+        if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FIXED><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+    } else if (wall_mode == ESPIC_WALL_REFLECT) {
+        if (!fuse) k_push<ESPIC_WALL_REFLECT, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_REFLECT, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else k_push<ESPIC_WALL_REFLECT, true, ESPIC_DEPOSIT_FIXED><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+    } else { espic_set_error("espic_push: bad wall mode %d", wall_mode); return -1; }
+#undef PUSH_ARGS
+    LAUNCH_CHECK(c);
+    if (fuse) s.acc_fresh = true;
+    if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) return 0;
+
+    // count the dead, then remove them in the reference's order
+    if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
+    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, c->cell_cnt);
+    LAUNCH_CHECK(c);
+    if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
+    unsigned long long *h = (unsigned long long *)c->hpin;
+    CK(cudaMemcpyAsync(h, c->dscal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const long long D = (long long)h[0];
+    if (D == 0) return 0;
+    if (D < n) {
+        if ((r = ensure_buf(&c->lists, &c->lists_cap, 2 * D, c->stream))) return r;
+        CK(cudaMemsetAsync(c->lists, 0xff, (size_t)D * sizeof(long long), c->stream));
+        k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
+                                                           c->lists, c->lists + D);
+        LAUNCH_CHECK(c);
+        k_move<<<nblk(D, 256), 256, 0, c->stream>>>(D, c->lists, c->lists + D, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
+        LAUNCH_CHECK(c);
+    }
+    s.np = n - D;
+    return 0;
+}
+
+extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    if (mode != ESPIC_DEPOSIT_FP64 && mode != ESPIC_DEPOSIT_FIXED) { espic_set_error("espic_deposit: bad mode %d", mode); return -1; }
+    if (!(s.acc_fresh && s.acc_mode == mode)) {
+        int r = prepare_acc(c, s, mode);
+        if (r) return r;
+        if (s.np > 0) {
+            const double scale = ldexp(1.0, s.acc_shift);
+            if (mode == ESPIC_DEPOSIT_FP64)
+                k_deposit<ESPIC_DEPOSIT_FP64><<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
+            else
+                k_deposit<ESPIC_DEPOSIT_FIXED><<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
+            LAUNCH_CHECK(c);
+        }
+    }
+    int r = espic_comm_allreduce_acc(c, s);
+    if (r) return r;
+    const double inv_scale = ldexp(1.0, -s.acc_shift);
+    if (mode == ESPIC_DEPOSIT_FP64)
+        k_den_finalize<ESPIC_DEPOSIT_FP64><<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, s.acc, c->node_vol, s.den, inv_scale);
+    else
+        k_den_finalize<ESPIC_DEPOSIT_FIXED><<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, s.acc, c->node_vol, s.den, inv_scale);
+    LAUNCH_CHECK(c);
+    s.acc_fresh = false;      // the accumulator now holds the cross-rank sum / has been consumed
+    return 0;
+}
+
+// =====================================================================================================
+// sort by cell (counting sort; cell key as ch4 World::XtoC: c = k*(nj-1)*(ni-1) + j*(ni-1) + i)
+// =====================================================================================================
+
+__device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y, double z)
+{
+    int i, j, k; double d;
+    cell_frac(x, m.x0[0], m.dh[0], m.ni, i, d);
+    cell_frac(y, m.x0[1], m.dh[1], m.nj, j, d);
+    cell_frac(z, m.x0[2], m.dh[2], m.nk, k, d);
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (k < 0) k = 0;
+    return ((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i;
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                    const double *__restrict__ z, long long n, uint32_t *__restrict__ cnt)
+{
+    long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n) return;
+    long long cell = cell_key(m, x[idx], y[idx], z[idx]);
+    // warp-aggregate equal keys (sorted input: most of a warp shares a cell)
+    unsigned act = __activemask();
+    unsigned peers = __match_any_sync(act, cell);
+    int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader) atomicAdd(cnt + cell, (uint32_t)__popc(peers));
+}
+
+__global__ void __launch_bounds__(256) k_cell_scatter(MeshC m, long long n, uint32_t *__restrict__ cnt,
+                                                      const uint32_t *__restrict__ pre, const uint32_t *__restrict__ coff,
+                                                      const double *__restrict__ s0, const double *__restrict__ s1, const double *__restrict__ s2,
+                                                      const double *__restrict__ s3, const double *__restrict__ s4, const double *__restrict__ s5,
+                                                      const double *__restrict__ s6,
+                                                      double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
+                                                      double *__restrict__ d3, double *__restrict__ d4, double *__restrict__ d5,
+                                                      double *__restrict__ d6)
+{
+    long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n) return;
+    double x = s0[idx], y = s1[idx], z = s2[idx];
+    long long cell = cell_key(m, x, y, z);
+    unsigned act = __activemask();
+    unsigned peers = __match_any_sync(act, cell);
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(peers) - 1;
+    uint32_t basec = 0;
+    if (lane == leader) basec = atomicSub(cnt + cell, (uint32_t)__popc(peers));
+    basec = __shfl_sync(peers, basec, leader);
+    // slots [basec - popc, basec) of the cell; ranks in lane order keep the previous relative order inside a warp
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    long long dst = (long long)scan_at(pre, coff, cell) + (basec - __popc(peers)) + rank;
+    d0[dst] = x; d1[dst] = y; d2[dst] = z;
+    d3[dst] = s3[idx]; d4[dst] = s4[idx]; d5[dst] = s5[idx]; d6[dst] = s6[idx];
+}
+
+extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    const long long n = s.np;
+    if (n < 2) return 0;
+    const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1);
+    int r;
+    if (s.alt_cap < s.cap) {
+        for (int q = 0; q < 7; q++) {
+            if (s.alt[q]) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(s.alt[q])); s.alt[q] = nullptr; }
+            CK(cudaMalloc(&s.alt[q], (size_t)s.cap * sizeof(double)));
+        }
+        s.alt_cap = s.cap;
+    }
+    if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nc, c->stream))) return r;
+    CK(cudaMemsetAsync(c->cell_cnt, 0, (size_t)nc * sizeof(uint32_t), c->stream));
+    k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt);
+    LAUNCH_CHECK(c);
+    if ((r = espic_scan_u32(c, c->cell_cnt, nc, c->dscal + 1))) return r;
+    k_cell_scatter<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, n, c->cell_cnt, c->scan_pre, c->scan_coff,
+                                                        s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
+                                                        s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6]);
+    LAUNCH_CHECK(c);
+    for (int q = 0; q < 7; q++) std::swap(s.p[q], s.alt[q]);
+    std::swap(s.cap, s.alt_cap);
+    return 0;
+}
+
+// =====================================================================================================
+// addParticle (Species.cpp:65-81) and ColdBeamSource::sample (Source.cpp:4-27)
+// =====================================================================================================
+
+// Philox4x32-10 (Salmon et al. 2011); counter = (idx_lo, idx_hi, step, stream), key = (seed_lo, seed_hi).
+__device__ __forceinline__ void philox_uniform2(uint64_t seed, uint32_t stream, uint32_t step, uint64_t idx, double &u0, double &u1)
+{
+    uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = step, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    uint64_t a = ((uint64_t)c1 << 32) | c0, b = ((uint64_t)c3 << 32) | c2;
+    u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+    u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct AddSrc {
+    int philox;                 // 1: cold beam from Philox, 0: staged host particles
+    const double *in[7];
+    uint64_t seed; uint32_t stream, step;
+    double Lx, Ly, v_drift, mpw0;
+};
+
+__device__ __forceinline__ void add_candidate(const MeshC &m, const AddSrc &a, long long i, double q[7])
+{
+    if (a.philox) {
+        double u0, u1;
+        philox_uniform2(a.seed, a.stream, a.step, (uint64_t)i, u0, u1);
+        q[0] = m.x0[0] + u0 * a.Lx;       // Source.cpp:22
+        q[1] = m.x0[1] + u1 * a.Ly;
+        q[2] = m.x0[2];
+        q[3] = 0; q[4] = 0; q[5] = a.v_drift;
+        q[6] = a.mpw0;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 7; t++) q[t] = a.in[t][i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_add_flags(MeshC m, AddSrc a, long long n, uint32_t *__restrict__ flags)
+{
+    long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n) return;
+    double q[7];
+    add_candidate(m, a, i, q);
+    flags[i] = in_bounds(m, q[0], q[1], q[2]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_add_write(MeshC m, AddSrc a, long long n, const double *__restrict__ ef,
+                                                   const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pre,
+                                                   const uint32_t *__restrict__ coff, long long base, double qm, double hdt,
+                                                   double *p0, double *p1, double *p2, double *p3, double *p4, double *p5, double *p6)
+{
+    long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    double q[7];
+    add_candidate(m, a, i, q);
+    int ci, cj, ck; double di, dj, dk;
+    cell_frac(q[0], m.x0[0], m.dh[0], m.ni, ci, di);
+    cell_frac(q[1], m.x0[1], m.dh[1], m.nj, cj, dj);
+    cell_frac(q[2], m.x0[2], m.dh[2], m.nk, ck, dk);
+    double e[3];
+    gather_ef(m, ef, ci, cj, ck, di, dj, dk, e);
+    // vel -= charge/mass*ef_part*(0.5*dt)   (Species.cpp:77)
+    long long dst = base + (long long)scan_at(pre, coff, i);
+    p0[dst] = q[0]; p1[dst] = q[1]; p2[dst] = q[2];
+    p3[dst] = q[3] - e[0] * qm * hdt;
+    p4[dst] = q[4] - e[1] * qm * hdt;
+    p5[dst] = q[5] - e[2] * qm * hdt;
+    p6[dst] = q[6];
+}
+
+static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, long long *n_added)
+{
+    Species &s = c->sp[sp];
+    if (n_added) *n_added = 0;
+    if (n <= 0) return 0;
+    int r;
+    if ((r = espic_species_reserve(c, sp, s.np + n))) return r;
+    if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, n, c->stream))) return r;
+    k_add_flags<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->cell_cnt);
+    LAUNCH_CHECK(c);
+    if ((r = espic_scan_u32(c, c->cell_cnt, n, c->dscal + 2))) return r;
+    const double qm = s.charge / s.mass, hdt = 0.5 * dt;
+    k_add_write<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->ef, c->cell_cnt, c->scan_pre, c->scan_coff, s.np, qm, hdt,
+                                                     s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
+    LAUNCH_CHECK(c);
+    unsigned long long *h = (unsigned long long *)c->hpin;
+    CK(cudaMemcpyAsync(h + 2, c->dscal + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.np += (long long)h[2];
+    s.acc_fresh = false;
+    if (n_added) *n_added = (long long)h[2];
+    return 0;
+}
+
+extern "C" int espic_species_add(espic_ctx *c, int sp, const double *const comp[7], long long n, double dt, long long *n_added)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    if (n <= 0) { if (n_added) *n_added = 0; return 0; }
+    Species &s = c->sp[sp];
+    // stage the candidates in the sort double buffer region of the reduction scratch
+    int r;
+    if ((r = ensure_buf(&c->red, &c->red_cap, 7 * n, c->stream))) return r;
+    AddSrc a;
+    memset(&a, 0, sizeof(a));
+    a.philox = 0;
+    for (int q = 0; q < 7; q++) {
+        CK(cudaMemcpyAsync(c->red + q * n, comp[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        a.in[q] = c->red + q * n;
+    }
+    for (long long i = 0; i < n; i++) if (comp[6][i] > s.mpw_max) s.mpw_max = comp[6][i];
+    return add_common(c, sp, a, n, dt, n_added);
+}
+
+extern "C" int espic_inject_cold_beam(espic_ctx *c, int sp, double v_drift, double den, double dt,
+                                      uint64_t seed, uint32_t stream, uint32_t step, long long *n_added)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    const MeshC &m = c->m;
+    // Source.cpp:6-18
+    double Lx = m.dh[0] * (m.ni - 1);
+    double Ly = m.dh[1] * (m.nj - 1);
+    double A = Lx * Ly;
+    double num_real = den * v_drift * A * dt;
+    // the Bernoulli fraction comes from counter idx = 2^64-1 (host evaluation of the same Philox block)
+    uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = step, c3 = stream, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    uint64_t a64 = ((uint64_t)c1 << 32) | c0;
+    double u = (double)(a64 >> 11) * (1.0 / 9007199254740992.0);
+    long long num_sim = (int)(num_real / s.mpw0 + u);
+    AddSrc a;
+    memset(&a, 0, sizeof(a));
+    a.philox = 1; a.seed = seed; a.stream = stream; a.step = step;
+    a.Lx = Lx; a.Ly = Ly; a.v_drift = v_drift; a.mpw0 = s.mpw0;
+    if (s.mpw0 > s.mpw_max) s.mpw_max = s.mpw0;
+    return add_common(c, sp, a, num_sim, dt, n_added);
+}
+
+// =====================================================================================================
+// diagnostics (Species.cpp:84-108)
+// =====================================================================================================
+
+__global__ void __launch_bounds__(256) k_diag(const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
+                                              const double *__restrict__ mpw, long long n, double *__restrict__ part)
+{
+    __shared__ double sh[32];
+    double a[5] = {0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        double w = mpw[i], x = vx[i], y = vy[i], z = vz[i];
+        a[0] += w;
+        a[1] += x * w; a[2] += y * w; a[3] += z * w;
+        double v2 = x * x + y * y + z * z;
+        a[4] += w * v2;
+    }
+    for (int q = 0; q < 5; q++) {
+        double t = block_sum(a[q], sh);
+        if (threadIdx.x == 0) part[(size_t)q * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_final(const double *__restrict__ part, int nparts, int nq, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    for (int q = 0; q < nq; q++) {
+        double a = 0;
+        for (int i = threadIdx.x; i < nparts; i += 256) a += part[(size_t)q * nparts + i];
+        double t = block_sum(a, sh);
+        if (threadIdx.x == 0) out[q] = t;
+    }
+}
+
+extern "C" int espic_species_diag(espic_ctx *c, int sp, double out[5])
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    for (int q = 0; q < 5; q++) out[q] = 0;
+    if (s.np == 0) return 0;
+    int nb = (int)std::min<long long>(nblk(s.np, 256), 4 * c->sm_count);
+    int r;
+    if ((r = ensure_buf(&c->red, &c->red_cap, 5ll * nb, c->stream))) return r;
+    k_diag<<<nb, 256, 0, c->stream>>>(s.p[3], s.p[4], s.p[5], s.p[6], s.np, c->red);
+    LAUNCH_CHECK(c);
+    double *dout = reinterpret_cast<double *>(c->dscal + 8);
+    k_reduce_final<<<1, 256, 0, c->stream>>>(c->red, nb, 5, dout);
+    LAUNCH_CHECK(c);
+    double *h = reinterpret_cast<double *>(c->hpin) + 8;
+    CK(cudaMemcpyAsync(h, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out[0] = h[0];
+    out[1] = h[1] * s.mass; out[2] = h[2] * s.mass; out[3] = h[3] * s.mass;    // mass*mom (Species.cpp:97)
+    out[4] = 0.5 * s.mass * h[4];                                             // Species.cpp:107
+    return 0;
+}

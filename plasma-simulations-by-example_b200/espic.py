@@ -1,0 +1,271 @@
+"""ctypes binding of libespic_cuda.so (include/espic.h) -- the Python-side caller of the C ABI.
+
+Used by the GPU parity tests, bench.py and __graft_entry__.smoke().  There is no CPU fallback: loading fails
+loudly if the CUDA library has not been built (python __graft_entry__.py build), and Engine() raises if the
+library reports an error (e.g. no CUDA device).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libespic_cuda.so")
+
+PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE = range(7)
+WALL_ABSORB, WALL_REFLECT = 0, 1
+PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_FIXED_POINT = 1, 2, 256
+DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
+SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "espic_create", "espic_destroy", "espic_last_error", "espic_set_stream", "espic_sync", "espic_kernel_launches",
+    "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
+    "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
+    "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_deposit",
+    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_species_diag", "espic_update_average",
+    "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
+    "espic_comm_init", "espic_allreduce_density",
+]
+
+
+class SolveParams(C.Structure):
+    _fields_ = [("type", C.c_int), ("max_it", C.c_int), ("tol", C.c_double), ("phi0", C.c_double), ("Te0", C.c_double),
+                ("n0", C.c_double), ("nr_max_it", C.c_int), ("nr_tol", C.c_double)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("converged", C.c_int), ("nr_iters", C.c_int), ("lin_iters", C.c_longlong), ("gs_fallbacks", C.c_int),
+                ("gs_iters", C.c_longlong), ("residual", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class EspicError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libespic_cuda.so; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EspicError("CUDA extension %s is not built: run `python __graft_entry__.py build`" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp, vp = C.POINTER(C.c_double), C.c_void_p
+    comp = C.POINTER(dp)
+    L.espic_last_error.restype = C.c_char_p
+    L.espic_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, dp, dp, C.c_int]
+    L.espic_destroy.argtypes = [vp]
+    L.espic_destroy.restype = None
+    L.espic_set_stream.argtypes = [vp, vp]
+    L.espic_sync.argtypes = [vp]
+    L.espic_kernel_launches.argtypes = [vp]
+    L.espic_kernel_launches.restype = C.c_longlong
+    L.espic_get_mesh.argtypes = [vp, dp, dp]
+    L.espic_add_sphere.argtypes = [vp, dp, C.c_double, C.c_double]
+    L.espic_add_inlet.argtypes = [vp]
+    L.espic_field_download.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.espic_field_upload.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.espic_field_devptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.espic_species_create.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_longlong]
+    L.espic_species_reserve.argtypes = [vp, C.c_int, C.c_longlong]
+    L.espic_species_count.argtypes = [vp, C.c_int]
+    L.espic_species_count.restype = C.c_longlong
+    L.espic_species_upload.argtypes = [vp, C.c_int, comp, C.c_longlong, C.c_int]
+    L.espic_species_upload_device.argtypes = [vp, C.c_int, comp, C.c_longlong, C.c_double, C.c_int]
+    L.espic_species_download.argtypes = [vp, C.c_int, comp, C.c_longlong]
+    L.espic_species_download.restype = C.c_longlong
+    L.espic_species_add.argtypes = [vp, C.c_int, comp, C.c_longlong, C.c_double, C.POINTER(C.c_longlong)]
+    L.espic_push.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
+    L.espic_deposit.argtypes = [vp, C.c_int, C.c_int]
+    L.espic_sort_by_cell.argtypes = [vp, C.c_int]
+    L.espic_inject_cold_beam.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
+                                         C.c_uint32, C.POINTER(C.c_longlong)]
+    L.espic_species_diag.argtypes = [vp, C.c_int, dp]
+    L.espic_update_average.argtypes = [vp, C.c_int]
+    L.espic_charge_density.argtypes = [vp]
+    L.espic_solve.argtypes = [vp, C.POINTER(SolveParams), C.POINTER(SolveInfo)]
+    L.espic_compute_ef.argtypes = [vp]
+    L.espic_field_pe.argtypes = [vp, dp]
+    L.espic_comm_unique_id.argtypes = [vp]
+    L.espic_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.espic_allreduce_density.argtypes = [vp, C.c_int]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _comp(arr7):
+    """(7,n) C-contiguous float64 -> double*[7]"""
+    ptrs = (C.POINTER(C.c_double) * 7)()
+    for q in range(7):
+        ptrs[q] = _dp(arr7[q])
+    return ptrs
+
+
+class Engine:
+    """One World on one GPU (reference World + PotentialSolver entry points); species are integer ids."""
+
+    def __init__(self, ni, nj, nk, x0, xm, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        x0a = np.asarray(x0, dtype=np.float64)
+        xma = np.asarray(xm, dtype=np.float64)
+        r = self.L.espic_create(C.byref(self.h), ni, nj, nk, _dp(x0a), _dp(xma), device)
+        if r:
+            raise EspicError(self.L.espic_last_error().decode())
+        self.ni, self.nj, self.nk = ni, nj, nk
+        self.nn = ni * nj * nk
+        self.phi0, self.Te0, self.n0 = 0.0, 1.5, 1e12
+        self.nr_max_it, self.nr_tol = 20, 1e-3
+
+    def close(self):
+        if self.h:
+            self.L.espic_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r):
+        if r < 0:
+            raise EspicError(self.L.espic_last_error().decode())
+        return r
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.espic_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(self.L.espic_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.espic_kernel_launches(self.h))
+
+    def mesh(self):
+        dh, xc = np.zeros(3), np.zeros(3)
+        self._ck(self.L.espic_get_mesh(self.h, _dp(dh), _dp(xc)))
+        return dh, xc
+
+    # ---- World
+    def add_sphere(self, c, radius, phi_sphere):
+        ca = np.asarray(c, dtype=np.float64)
+        self._ck(self.L.espic_add_sphere(self.h, _dp(ca), radius, phi_sphere))
+
+    def add_inlet(self):
+        self._ck(self.L.espic_add_inlet(self.h))
+
+    def field(self, which, sp=0):
+        if which == OBJECT_ID:
+            out = np.zeros(self.nn, dtype=np.int32)
+        else:
+            out = np.zeros(self.nn * (3 if which == EF else 1))
+        self._ck(self.L.espic_field_download(self.h, which, sp, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_field(self, which, arr, sp=0):
+        arr = np.ascontiguousarray(arr, dtype=np.int32 if which == OBJECT_ID else np.float64)
+        assert arr.size == self.nn * (3 if which == EF else 1)
+        self._ck(self.L.espic_field_upload(self.h, which, sp, arr.ctypes.data_as(C.c_void_p)))
+
+    def field_devptr(self, which, sp=0):
+        p = C.c_void_p()
+        self._ck(self.L.espic_field_devptr(self.h, which, sp, C.byref(p)))
+        return p.value
+
+    def set_reference_values(self, phi0, Te0, n0):
+        self.phi0, self.Te0, self.n0 = float(phi0), float(Te0), float(n0)
+
+    def compute_charge_density(self):
+        self._ck(self.L.espic_charge_density(self.h))
+
+    def solve(self, solver, max_it, tol):
+        p = SolveParams(solver, int(max_it), float(tol), self.phi0, self.Te0, self.n0, self.nr_max_it, self.nr_tol)
+        info = SolveInfo()
+        self._ck(self.L.espic_solve(self.h, C.byref(p), C.byref(info)))
+        return info.as_dict()
+
+    def compute_ef(self):
+        self._ck(self.L.espic_compute_ef(self.h))
+
+    def pe(self):
+        out = np.zeros(1)
+        self._ck(self.L.espic_field_pe(self.h, _dp(out)))
+        return float(out[0])
+
+    # ---- Species
+    def add_species(self, mass, charge, mpw0=1.0, capacity=1024):
+        return self._ck(self.L.espic_species_create(self.h, mass, charge, mpw0, int(capacity)))
+
+    def reserve(self, sp, capacity):
+        self._ck(self.L.espic_species_reserve(self.h, sp, int(capacity)))
+
+    def count(self, sp):
+        return int(self._ck(self.L.espic_species_count(self.h, sp)))
+
+    def upload(self, sp, soa, append=False):
+        soa = np.ascontiguousarray(soa, dtype=np.float64)
+        assert soa.shape[0] == 7
+        self._ck(self.L.espic_species_upload(self.h, sp, _comp(soa), soa.shape[1], int(append)))
+
+    def upload_device(self, sp, dev_ptrs, n, mpw_max, append=False):
+        """dev_ptrs: 7 device addresses (e.g. torch tensor.data_ptr()) of float64 arrays with n elements"""
+        ptrs = (C.POINTER(C.c_double) * 7)()
+        for q in range(7):
+            ptrs[q] = C.cast(C.c_void_p(int(dev_ptrs[q])), C.POINTER(C.c_double))
+        self._ck(self.L.espic_species_upload_device(self.h, sp, ptrs, int(n), float(mpw_max), int(append)))
+
+    def download(self, sp):
+        n = self.count(sp)
+        out = np.zeros((7, n))
+        got = self._ck(self.L.espic_species_download(self.h, sp, _comp(out), n))
+        assert got == n
+        return out
+
+    def add_particles(self, sp, soa, dt):
+        soa = np.ascontiguousarray(soa, dtype=np.float64)
+        added = C.c_longlong(0)
+        self._ck(self.L.espic_species_add(self.h, sp, _comp(soa), soa.shape[1], dt, C.byref(added)))
+        return added.value
+
+    def push(self, sp, dt, wall=WALL_ABSORB, flags=0):
+        self._ck(self.L.espic_push(self.h, sp, dt, wall, flags))
+
+    def deposit(self, sp, mode=DEPOSIT_FP64):
+        self._ck(self.L.espic_deposit(self.h, sp, mode))
+
+    def sort_by_cell(self, sp):
+        self._ck(self.L.espic_sort_by_cell(self.h, sp))
+
+    def inject_cold_beam(self, sp, v_drift, den, dt, seed, stream, step):
+        added = C.c_longlong(0)
+        self._ck(self.L.espic_inject_cold_beam(self.h, sp, v_drift, den, dt, seed, stream, step, C.byref(added)))
+        return added.value
+
+    def diag(self, sp):
+        out = np.zeros(5)
+        self._ck(self.L.espic_species_diag(self.h, sp, _dp(out)))
+        return out
+
+    def update_average(self, sp):
+        self._ck(self.L.espic_update_average(self.h, sp))
+
+    # ---- multi GPU
+    def unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ck(self.L.espic_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank, nranks, uid):
+        self._ck(self.L.espic_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
