@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -326,6 +328,8 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for i in range(args.steps):
         pe = phase_ev[i]
@@ -347,6 +351,8 @@ def main():
         counts.append((n_before, n_live, inf))
     ev1.record()
     torch.cuda.synchronize()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     launches = e.kernel_launches() - launches0
