@@ -39,5 +39,55 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST = os.path.join(HERE, "host")
+HOST_SRC = ["World.cpp", "Species.cpp", "Source.cpp", "PotentialSolver.cpp", "Output.cpp"]
+BIN = os.path.join(HERE, "bin")
+CXX = os.environ.get("CXX", "g++")
+CXXFLAGS = ["-O2", "-std=c++11", "-Wall", "-I" + HOST, "-I" + os.path.join(ROOT, "include")]
+LINK = ["-L" + os.path.join(HERE, "lib"), "-lespic_host", "-lespic_cuda", "-Wl,-rpath,$ORIGIN/../lib"]
+# the book's drivers that must compile UNCHANGED against host/*.h; read from the reference tree where it lies
+REF_MAINS = {"main_ch2": "ch2/Main.cpp", "main_ch3": "ch3/ver2/Main.cpp", "main_ch9": "ch9/Main.cpp",
+             "main_ch9mt": "ch9/MT/Main.cpp", "main_ch9cuda": "ch9/CUDA/Main.cpp"}
+
+
+def build_host(force=False, reference="/root/reference"):
+    """Host C++ shim (the reference's class API over the C ABI): lib/libespic_host.a, bin/shim_check and -- when the
+    reference tree is present -- bin/main_* linked from the book's unmodified Main.cpp files.  A quoted #include looks in
+    the including file's directory first, so each Main.cpp is fed to g++ on stdin: that way "World.h" resolves to
+    host/World.h, not to the reference header next to it."""
+    os.makedirs(BIN, exist_ok=True)
+    os.makedirs(os.path.join(HERE, "lib"), exist_ok=True)
+    lib = os.path.join(HERE, "lib", "libespic_host.a")
+    hdrs = [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith(".h")] + [os.path.join(ROOT, "include", "espic.h")]
+    srcs = [os.path.join(HOST, s) for s in HOST_SRC]
+    newest = max(os.path.getmtime(f) for f in hdrs + srcs)
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < newest:
+        objs = []
+        for s in srcs:
+            o = os.path.join(HERE, "lib", "host_" + os.path.basename(s)[:-4] + ".o")
+            subprocess.check_call([CXX] + CXXFLAGS + ["-fPIC", "-c", "-o", o, s])
+            objs.append(o)
+        if os.path.exists(lib):
+            os.remove(lib)
+        subprocess.check_call(["ar", "rcs", lib] + objs)
+    deps = max(os.path.getmtime(lib), os.path.getmtime(OUT) if os.path.exists(OUT) else 0)
+    chk = os.path.join(BIN, "shim_check")
+    src = os.path.join(HOST, "shim_check.cpp")
+    if force or not os.path.exists(chk) or os.path.getmtime(chk) < max(deps, os.path.getmtime(src)):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-o", chk, src] + LINK)
+    built = [chk]
+    for name, rel in REF_MAINS.items():
+        main = os.path.join(reference, rel)
+        exe = os.path.join(BIN, name)
+        if not os.path.exists(main):
+            continue
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < deps:
+            with open(main, "rb") as f:
+                subprocess.check_call([CXX] + CXXFLAGS + ["-w", "-x", "c++", "-", "-x", "none", "-o", exe] + LINK, stdin=f, cwd=BIN)
+        built.append(exe)
+    return built
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

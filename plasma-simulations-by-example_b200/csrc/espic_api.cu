@@ -69,6 +69,22 @@ __global__ void k_add_inlet(MeshC m, int32_t *__restrict__ object_id, double *__
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// ef (API layout, 3 doubles per node) -> ef4 (gather layout, 4 doubles per node)
+__global__ void k_repack_ef(long long nn, const double *__restrict__ ef, double *__restrict__ ef4)
+{
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= nn) return;
+    double4 v = make_double4(ef[3 * u], ef[3 * u + 1], ef[3 * u + 2], 0.0);
+    *reinterpret_cast<double4 *>(ef4 + 4 * u) = v;
+}
+
+int espic_repack_ef(espic_ctx *c)
+{
+    k_repack_ef<<<(unsigned)((c->m.nn + 255) / 256), 256, 0, c->stream>>>(c->m.nn, c->ef, c->ef4);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
 // ---- lifetime -------------------------------------------------------------------------------------
 
 extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const double x0[3], const double xm[3], int device)
@@ -98,6 +114,7 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
         m.x0[a] = x0[a];
         m.xm[a] = xm[a];
         m.dh[a] = (xm[a] - x0[a]) / (nn3[a] - 1);
+        m.rdh[a] = 1.0 / m.dh[a];
         c->xc[a] = (x0[a] + xm[a]) * 0.5;
         m.sc[a] = 0;
     }
@@ -106,6 +123,7 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
     CK(cudaMalloc(&c->phi, nb));
     CK(cudaMalloc(&c->rho, nb));
     CK(cudaMalloc(&c->ef, 3 * nb));
+    CK(cudaMalloc(&c->ef4, 4 * nb));
     CK(cudaMalloc(&c->node_vol, nb));
     CK(cudaMalloc(&c->object_id, (size_t)m.nn * sizeof(int32_t)));
     CK(cudaMalloc(&c->dscal, 64 * sizeof(unsigned long long)));
@@ -113,6 +131,7 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
     CK(cudaMemsetAsync(c->phi, 0, nb, c->stream));
     CK(cudaMemsetAsync(c->rho, 0, nb, c->stream));
     CK(cudaMemsetAsync(c->ef, 0, 3 * nb, c->stream));
+    CK(cudaMemsetAsync(c->ef4, 0, 4 * nb, c->stream));
     CK(cudaMemsetAsync(c->object_id, 0, (size_t)m.nn * sizeof(int32_t), c->stream));
     CK(cudaMemsetAsync(c->dscal, 0, 64 * sizeof(unsigned long long), c->stream));
     k_node_volumes<<<nblk(m.nn, 256), 256, 0, c->stream>>>(m, c->node_vol);
@@ -127,7 +146,7 @@ extern "C" void espic_destroy(espic_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     espic_comm_destroy(c);
-    cudaFree(c->phi); cudaFree(c->rho); cudaFree(c->ef); cudaFree(c->node_vol); cudaFree(c->object_id);
+    cudaFree(c->phi); cudaFree(c->rho); cudaFree(c->ef); cudaFree(c->ef4); cudaFree(c->node_vol); cudaFree(c->object_id);
     for (int s = 0; s < c->nsp; s++) {
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }
         cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc);
@@ -226,6 +245,7 @@ extern "C" int espic_field_upload(espic_ctx *c, int which, int sp, const void *h
     CK(cudaMemcpyAsync(p, host, b, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (which == ESPIC_OBJECT_ID) c->geom_version++;
+    if (which == ESPIC_EF) { int r = espic_repack_ef(c); if (r) return r; }
     if (which == ESPIC_DEN) c->sp[sp].acc_fresh = false;
     return 0;
 }

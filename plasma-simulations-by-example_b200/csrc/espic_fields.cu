@@ -812,7 +812,7 @@ extern "C" int espic_solve(espic_ctx *c, const espic_solve_params *p, espic_solv
 
 // PotentialSolver::computeEF (PotentialSolver.cpp:465-504)
 __global__ void __launch_bounds__(256) k_ef(StencilC s, double dx, double dy, double dz, const double *__restrict__ phi,
-                                            double *__restrict__ ef)
+                                            double *__restrict__ ef, double *__restrict__ ef4)
 {
     long long u = blockIdx.x * 256ll + threadIdx.x;
     if (u >= s.nn) return;
@@ -829,13 +829,14 @@ __global__ void __launch_bounds__(256) k_ef(StencilC s, double dx, double dy, do
     else if (k == s.nk - 1) ez = -(phi[u - 2 * s.sk] - 4 * phi[u - s.sk] + 3 * p) / (2 * dz);
     else ez = -(phi[u + s.sk] - phi[u - s.sk]) / (2 * dz);
     ef[3 * u] = ex; ef[3 * u + 1] = ey; ef[3 * u + 2] = ez;
+    *reinterpret_cast<double4 *>(ef4 + 4 * u) = make_double4(ex, ey, ez, 0.0);     // the particles' gather copy
 }
 
 extern "C" int espic_compute_ef(espic_ctx *c)
 {
     CK(cudaSetDevice(c->device));
     StencilC s = make_stencil(c->m);
-    k_ef<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->m.dh[0], c->m.dh[1], c->m.dh[2], c->phi, c->ef);
+    k_ef<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->m.dh[0], c->m.dh[1], c->m.dh[2], c->phi, c->ef, c->ef4);
     LAUNCH_CHECK(c);
     return 0;
 }

@@ -16,6 +16,7 @@ struct MeshC {
     int ni, nj, nk;
     long long nn;
     double x0[3], xm[3], dh[3];
+    double rdh[3];    // RN(1/dh): div_by_dh() turns it back into the exactly rounded quotient
     double sc[3];     // sphere centre
     double sr2;       // sphere radius^2 (0: World default, World.h:136-137)
 };
@@ -42,6 +43,7 @@ struct espic_ctx {
     MeshC m;
     double xc[3];
     double *phi = nullptr, *rho = nullptr, *ef = nullptr, *node_vol = nullptr;
+    double *ef4 = nullptr;             // gather copy of ef, one 32-byte {ex,ey,ez,0} record per node (one LDG.256 per node)
     int32_t *object_id = nullptr;
     int nsp = 0;
     Species sp[ESPIC_MAX_SPECIES];
@@ -82,6 +84,8 @@ template <typename T> static inline int ensure_buf(T **ptr, long long *cap, long
 #define SCAN_CHUNK_LOG2 13
 int espic_scan_u32(espic_ctx *ctx, const uint32_t *in, long long n, unsigned long long *d_total);
 
+int espic_repack_ef(espic_ctx *c);     // espic_api.cu: refresh ef4 after ef was written from outside
+
 // espic_comm.cu
 void espic_comm_destroy(espic_ctx *c);
 int  espic_comm_max_double(espic_ctx *c, double *v);
@@ -99,9 +103,21 @@ __device__ __forceinline__ long long node_u(const MeshC &m, int i, int j, int k)
 // World::XtoL (World.h:75-81) + (int) truncation of Field::gather/scatter (Field.h:169-176).
 // lc can round to exactly n-1 just below xm; the reference then reads node n (UB) with weight 0:
 // clamp the cell to n-2 (fraction becomes exactly 1), see oracle cell_of().
-__device__ __forceinline__ void cell_frac(double x, double x0, double dh, int n, int &i, double &d)
+// a / dh, IEEE correctly rounded, without the division sequence (about 10 FP64 instructions + MUFU.RCP64H): with
+// y = RN(1/dh) from the host, q = RN(a*y), r = a - dh*q (exact, one FMA), q' = RN(q + r*y) is the correctly rounded
+// quotient (Markstein's division theorem; checked against a/dh on 9.6e8 host samples incl. cell boundaries +-3 ulp,
+// oracle/div_check.c).  Tiny |a| (subnormal intermediate results) takes the true division.
+__device__ __forceinline__ double div_by_dh(double a, double dh, double rdh)
 {
-    double lc = (x - x0) / dh;
+    if (fabs(a) < 1e-280) return a / dh;
+    const double q = a * rdh;
+    const double r = __fma_rn(-dh, q, a);
+    return __fma_rn(r, rdh, q);
+}
+
+__device__ __forceinline__ void cell_frac(double x, double x0, double dh, double rdh, int n, int &i, double &d)
+{
+    double lc = div_by_dh(x - x0, dh, rdh);
     int ii = (int)lc;
     if (ii > n - 2) ii = n - 2;
     i = ii;
@@ -109,24 +125,34 @@ __device__ __forceinline__ void cell_frac(double x, double x0, double dh, int n,
 }
 
 // Field3::gather (Field.h:189-211): eight terms, each data*w_i*w_j*w_k left to right, summed in the reference's order.
-__device__ __forceinline__ void gather_ef(const MeshC &m, const double *__restrict__ ef,
+// one node of the padded gather field: a single 256-bit read-only load (LDG.E.256, sm_100+)
+__device__ __forceinline__ void ld_node(const double *__restrict__ ef4, long long u, double v[3])
+{
+    double pad;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(pad) : "l"(ef4 + 4 * u));
+}
+
+__device__ __forceinline__ void gather_ef(const MeshC &m, const double *__restrict__ ef4,
                                           int i, int j, int k, double di, double dj, double dk, double e[3])
 {
     const long long u000 = node_u(m, i, j, k);
     const long long sj = m.ni, sk = (long long)m.ni * m.nj;
     const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
-    const long long n0 = u000, n1 = u000 + 1, n2 = u000 + 1 + sj, n3 = u000 + sj;
-    const long long n4 = n0 + sk, n5 = n1 + sk, n6 = n2 + sk, n7 = n3 + sk;
+    double n0[3], n1[3], n2[3], n3[3], n4[3], n5[3], n6[3], n7[3];
+    ld_node(ef4, u000, n0);           ld_node(ef4, u000 + 1, n1);
+    ld_node(ef4, u000 + 1 + sj, n2);  ld_node(ef4, u000 + sj, n3);
+    ld_node(ef4, u000 + sk, n4);      ld_node(ef4, u000 + 1 + sk, n5);
+    ld_node(ef4, u000 + 1 + sj + sk, n6); ld_node(ef4, u000 + sj + sk, n7);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        double v = __ldg(ef + 3 * n0 + c) * ai * aj * ak;
-        v = v + __ldg(ef + 3 * n1 + c) * di * aj * ak;
-        v = v + __ldg(ef + 3 * n2 + c) * di * dj * ak;
-        v = v + __ldg(ef + 3 * n3 + c) * ai * dj * ak;
-        v = v + __ldg(ef + 3 * n4 + c) * ai * aj * dk;
-        v = v + __ldg(ef + 3 * n5 + c) * di * aj * dk;
-        v = v + __ldg(ef + 3 * n6 + c) * di * dj * dk;
-        v = v + __ldg(ef + 3 * n7 + c) * ai * dj * dk;
+        double v = n0[c] * ai * aj * ak;
+        v = v + n1[c] * di * aj * ak;
+        v = v + n2[c] * di * dj * ak;
+        v = v + n3[c] * ai * dj * ak;
+        v = v + n4[c] * ai * aj * dk;
+        v = v + n5[c] * di * aj * dk;
+        v = v + n6[c] * di * dj * dk;
+        v = v + n7[c] * ai * dj * dk;
         e[c] = v;
     }
 }

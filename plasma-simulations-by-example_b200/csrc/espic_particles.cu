@@ -98,48 +98,141 @@ __device__ __forceinline__ unsigned long long scan_at(const uint32_t *__restrict
 
 // =====================================================================================================
 // scatter (Field::scatter, Field.h:167-186) into an accumulator
+//
+// Particles are kept (approximately) sorted by cell, so neighbouring lanes mostly deposit on the same eight nodes.
+// Instead of 8 atomics per particle the warp first adds up, in registers and with shuffles, every run of consecutive
+// lanes that sit in the same cell (segmented reduction) and only the first lane of each run issues the 8 atomics.
+// FP64 mode: the additions happen in a different order than the reference's particle loop (rounding only).
+// Fixed-point mode: every particle's eight weights are rounded to int64 multiples of 2^-shift FIRST, all later
+// additions are integer and therefore exact: the result does not depend on particle order, run lengths or GPU count.
 // =====================================================================================================
 
-template <int MODE>
-__device__ __forceinline__ void acc_add(double *acc, long long u, double w, double scale)
-{
-    if (MODE == ESPIC_DEPOSIT_FP64) {
-        atomicAdd(acc + u, w);
-    } else {
-        long long q = __double2ll_rn(w * scale);
-        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + u, (unsigned long long)q);
+template <int MODE> struct AccVal;
+template <> struct AccVal<ESPIC_DEPOSIT_FP64> {
+    typedef double T;
+    static __device__ __forceinline__ T quant(double w, double) { return w; }
+    static __device__ __forceinline__ void red(double *acc, long long u, T v) { atomicAdd(acc + u, v); }
+};
+template <> struct AccVal<ESPIC_DEPOSIT_FIXED> {
+    typedef long long T;
+    static __device__ __forceinline__ T quant(double w, double scale) { return __double2ll_rn(w * scale); }
+    static __device__ __forceinline__ void red(double *acc, long long u, T v)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + u, (unsigned long long)v);
     }
+};
+
+__device__ __forceinline__ void cell3(const MeshC &m, double x, double y, double z, int &i, int &j, int &k,
+                                      double &di, double &dj, double &dk)
+{
+    cell_frac(x, m.x0[0], m.dh[0], m.rdh[0], m.ni, i, di);
+    cell_frac(y, m.x0[1], m.dh[1], m.rdh[1], m.nj, j, dj);
+    cell_frac(z, m.x0[2], m.dh[2], m.rdh[2], m.nk, k, dk);
+}
+
+// the eight node weights in the reference's node order, each mpw*w_i*w_j*w_k multiplied left to right (Field.h:177-184)
+template <int MODE>
+__device__ __forceinline__ long long particle_weights(const MeshC &m, double x, double y, double z, double mpw, double scale,
+                                                      typename AccVal<MODE>::T w[8])
+{
+    int i, j, k; double di, dj, dk;
+    cell3(m, x, y, z, i, j, k, di, dj, dk);
+    if (i < 0 || j < 0 || k < 0) return -1;     // never for in-bounds particles; keeps stray input from writing out of range
+    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
+    w[0] = AccVal<MODE>::quant(mpw * ai * aj * ak, scale);
+    w[1] = AccVal<MODE>::quant(mpw * di * aj * ak, scale);
+    w[2] = AccVal<MODE>::quant(mpw * di * dj * ak, scale);
+    w[3] = AccVal<MODE>::quant(mpw * ai * dj * ak, scale);
+    w[4] = AccVal<MODE>::quant(mpw * ai * aj * dk, scale);
+    w[5] = AccVal<MODE>::quant(mpw * di * aj * dk, scale);
+    w[6] = AccVal<MODE>::quant(mpw * di * dj * dk, scale);
+    w[7] = AccVal<MODE>::quant(mpw * ai * dj * dk, scale);
+    return node_u(m, i, j, k);
 }
 
 template <int MODE>
-__device__ __forceinline__ void scatter_particle(const MeshC &m, double *acc, double x, double y, double z, double mpw, double scale)
+__device__ __forceinline__ void red8(const MeshC &m, double *acc, long long u, const typename AccVal<MODE>::T w[8])
 {
-    int i, j, k; double di, dj, dk;
-    cell_frac(x, m.x0[0], m.dh[0], m.ni, i, di);
-    cell_frac(y, m.x0[1], m.dh[1], m.nj, j, dj);
-    cell_frac(z, m.x0[2], m.dh[2], m.nk, k, dk);
-    if (i < 0 || j < 0 || k < 0) return;     // never for in-bounds particles; keeps stray input from writing out of range
-    const long long u = node_u(m, i, j, k);
     const long long sj = m.ni, sk = (long long)m.ni * m.nj;
-    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
-    acc_add<MODE>(acc, u, mpw * ai * aj * ak, scale);
-    acc_add<MODE>(acc, u + 1, mpw * di * aj * ak, scale);
-    acc_add<MODE>(acc, u + 1 + sj, mpw * di * dj * ak, scale);
-    acc_add<MODE>(acc, u + sj, mpw * ai * dj * ak, scale);
-    acc_add<MODE>(acc, u + sk, mpw * ai * aj * dk, scale);
-    acc_add<MODE>(acc, u + 1 + sk, mpw * di * aj * dk, scale);
-    acc_add<MODE>(acc, u + 1 + sj + sk, mpw * di * dj * dk, scale);
-    acc_add<MODE>(acc, u + sj + sk, mpw * ai * dj * dk, scale);
+    AccVal<MODE>::red(acc, u, w[0]);
+    AccVal<MODE>::red(acc, u + 1, w[1]);
+    AccVal<MODE>::red(acc, u + 1 + sj, w[2]);
+    AccVal<MODE>::red(acc, u + sj, w[3]);
+    AccVal<MODE>::red(acc, u + sk, w[4]);
+    AccVal<MODE>::red(acc, u + 1 + sk, w[5]);
+    AccVal<MODE>::red(acc, u + 1 + sj + sk, w[6]);
+    AccVal<MODE>::red(acc, u + sj + sk, w[7]);
 }
+
+// Whole-warp call.  u = lower node of the lane's cell (-1: nothing to deposit), w = its eight weights.
+template <int MODE>
+__device__ __forceinline__ void warp_deposit(const MeshC &m, double *acc, long long u, typename AccVal<MODE>::T w[8])
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long up = __shfl_up_sync(FULL, u, 1);
+    const unsigned heads = __ballot_sync(FULL, lane == 0 || up != u);
+    if (heads == FULL) {                   // no two neighbours share a cell: nothing to combine
+        if (u >= 0) red8<MODE>(m, acc, u, w);
+        return;
+    }
+    // last lane of this lane's run = lane before the next head
+    const unsigned above = heads & ~((2u << lane) - 1u);       // heads strictly above this lane (lane 31: 2u<<31 == 0 -> mask 0xffffffff)
+    const int run_end = (lane == 31 || above == 0) ? 31 : (__ffs(above) - 2);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane + o <= run_end;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            typename AccVal<MODE>::T t = __shfl_down_sync(FULL, w[q], o);
+            if (take) w[q] += t;
+        }
+    }
+    if (((heads >> lane) & 1u) && u >= 0) red8<MODE>(m, acc, u, w);
+}
+
+// two particles per thread (adjacent in memory: one 128-bit load per array), merged in registers when they share a cell
+template <int MODE>
+__device__ __forceinline__ void deposit_pair(const MeshC &m, double *acc, double scale, bool live0, double x0, double y0, double z0,
+                                             double w0, bool live1, double x1, double y1, double z1, double w1)
+{
+    typename AccVal<MODE>::T a[8], b[8];
+    long long ua = -1, ub = -1;
+    if (live0) ua = particle_weights<MODE>(m, x0, y0, z0, w0, scale, a);
+    if (live1) ub = particle_weights<MODE>(m, x1, y1, z1, w1, scale, b);
+    if (ub >= 0) {
+        if (ua == ub) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] += b[q];
+        } else if (ua < 0) {
+            ua = ub;
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] = b[q];
+        } else {
+            red8<MODE>(m, acc, ub, b);     // the pair straddles two cells: the second one goes out on its own
+        }
+    }
+    if (ua < 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = 0;
+    }
+    warp_deposit<MODE>(m, acc, ua, a);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
                                                  const double *__restrict__ z, const double *__restrict__ mpw,
                                                  long long n, double *acc, double scale)
 {
-    long long idx = blockIdx.x * 256ll + threadIdx.x;
-    if (idx >= n) return;
-    scatter_particle<MODE>(m, acc, x[idx], y[idx], z[idx], mpw[idx], scale);
+    const long long i0 = 2 * (blockIdx.x * 256ll + threadIdx.x);
+    if (i0 - 2 * (threadIdx.x & 31) >= n) return;            // whole warp past the end
+    const bool v0 = i0 < n, v1 = i0 + 1 < n;
+    double2 X = make_double2(0, 0), Y = X, Z = X, W = X;
+    if (v0) { X = ld2(x + i0); Y = ld2(y + i0); Z = ld2(z + i0); W = ld2(mpw + i0); }   // capacity is even: slot i0+1 is allocated
+    deposit_pair<MODE>(m, acc, scale, v0, X.x, Y.x, Z.x, W.x, v1, X.y, Y.y, Z.y, W.y);
 }
 
 // den = acc / node_vol (0 where node_vol == 0): Field::operator/= (Field.h:125-134)
@@ -157,53 +250,92 @@ __global__ void k_den_finalize(long long nn, const double *__restrict__ acc, con
 }
 
 // =====================================================================================================
-// push (Species::advance)
+// push (Species::advance): two particles per thread, 128-bit streaming loads/stores of the seven SoA arrays,
+// E gathered with one 256-bit load per node from the padded copy of ef, kill bits collected per warp, the density
+// scatter of the survivors fused in (the new position is still in registers).
 // =====================================================================================================
 
+// spread the low 16 bits of v to the even bit positions
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+template <int WALL>
+__device__ __forceinline__ bool push_one(const MeshC &m, const double *__restrict__ ef4, double s, double dt,
+                                         double &x, double &y, double &z, double &vx, double &vy, double &vz, double &mpw)
+{
+    int i, j, k; double di, dj, dk;
+    cell3(m, x, y, z, i, j, k, di, dj, dk);
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (k < 0) k = 0;
+    double e[3];
+    gather_ef(m, ef4, i, j, k, di, dj, dk, e);
+    // part.vel += ef_part*(dt*charge/mass);  part.pos += part.vel*dt;   (Species.cpp:22-25)
+    vx = vx + e[0] * s; vy = vy + e[1] * s; vz = vz + e[2] * s;
+    x = x + vx * dt; y = y + vy * dt; z = z + vz * dt;
+    if (WALL == ESPIC_WALL_ABSORB) {
+        // Species.cpp:28-32, removal test of Species.cpp:39
+        if (in_sphere(m, x, y, z) || !in_bounds(m, x, y, z)) mpw = 0;
+        return !(mpw > 0);
+    } else {
+        // ch2/Species.cpp:32-36
+        if (x < m.x0[0]) { x = 2 * m.x0[0] - x; vx *= -1.0; } else if (x >= m.xm[0]) { x = 2 * m.xm[0] - x; vx *= -1.0; }
+        if (y < m.x0[1]) { y = 2 * m.x0[1] - y; vy *= -1.0; } else if (y >= m.xm[1]) { y = 2 * m.xm[1] - y; vy *= -1.0; }
+        if (z < m.x0[2]) { z = 2 * m.x0[2] - z; vz *= -1.0; } else if (z >= m.xm[2]) { z = 2 * m.xm[2] - z; vz *= -1.0; }
+        return false;
+    }
+}
+
 template <int WALL, bool FUSE, int MODE>
-__global__ void __launch_bounds__(256) k_push(MeshC m, const double *__restrict__ ef,
+__global__ void __launch_bounds__(256) k_push(MeshC m, const double *__restrict__ ef4,
                                               double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                                               double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
                                               double *__restrict__ pmpw, long long n, double s, double dt,
                                               uint32_t *__restrict__ dead_words, double *acc, double scale)
 {
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
-    const bool valid = idx < n;
-    bool dead = false;
-    if (valid) {
-        double x = px[idx], y = py[idx], z = pz[idx];
-        double vx = pvx[idx], vy = pvy[idx], vz = pvz[idx];
-        double mpw = pmpw[idx];
-        int i, j, k; double di, dj, dk;
-        cell_frac(x, m.x0[0], m.dh[0], m.ni, i, di);
-        cell_frac(y, m.x0[1], m.dh[1], m.nj, j, dj);
-        cell_frac(z, m.x0[2], m.dh[2], m.nk, k, dk);
-        if (i < 0) i = 0;
-        if (j < 0) j = 0;
-        if (k < 0) k = 0;
-        double e[3];
-        gather_ef(m, ef, i, j, k, di, dj, dk, e);
-        // part.vel += ef_part*(dt*charge/mass);  part.pos += part.vel*dt;   (Species.cpp:22-25)
-        vx = vx + e[0] * s; vy = vy + e[1] * s; vz = vz + e[2] * s;
-        x = x + vx * dt; y = y + vy * dt; z = z + vz * dt;
-        if (WALL == ESPIC_WALL_ABSORB) {
-            // Species.cpp:28-32
-            if (in_sphere(m, x, y, z) || !in_bounds(m, x, y, z)) { mpw = 0; pmpw[idx] = 0; }
-            dead = !(mpw > 0);       // removal test of Species.cpp:39
-        } else {
-            // ch2/Species.cpp:32-36
-            if (x < m.x0[0]) { x = 2 * m.x0[0] - x; vx *= -1.0; } else if (x >= m.xm[0]) { x = 2 * m.xm[0] - x; vx *= -1.0; }
-            if (y < m.x0[1]) { y = 2 * m.x0[1] - y; vy *= -1.0; } else if (y >= m.xm[1]) { y = 2 * m.xm[1] - y; vy *= -1.0; }
-            if (z < m.x0[2]) { z = 2 * m.x0[2] - z; vz *= -1.0; } else if (z >= m.xm[2]) { z = 2 * m.xm[2] - z; vz *= -1.0; }
-        }
-        px[idx] = x; py[idx] = y; pz[idx] = z;
-        pvx[idx] = vx; pvy[idx] = vy; pvz[idx] = vz;
-        if (FUSE && !dead) scatter_particle<MODE>(m, acc, x, y, z, mpw, scale);
+    const int lane = threadIdx.x & 31;
+    const long long i0 = 2 * (blockIdx.x * 256ll + threadIdx.x);
+    const long long wbase = i0 - 2 * lane;                   // first particle of this warp (multiple of 64)
+    if (wbase >= n) return;
+    const bool v0 = i0 < n, v1 = i0 + 1 < n;
+    double2 X = make_double2(m.x0[0], m.x0[0]), Y = make_double2(m.x0[1], m.x0[1]), Z = make_double2(m.x0[2], m.x0[2]);
+    double2 VX = make_double2(0, 0), VY = VX, VZ = VX, W = VX;
+    if (v0) {      // capacity is a multiple of 1024: slot i0+1 is always allocated
+        X = ld2(px + i0); Y = ld2(py + i0); Z = ld2(pz + i0);
+        VX = ld2(pvx + i0); VY = ld2(pvy + i0); VZ = ld2(pvz + i0); W = ld2(pmpw + i0);
+    }
+    if (!v1) { X.y = m.x0[0]; Y.y = m.x0[1]; Z.y = m.x0[2]; VX.y = 0; VY.y = 0; VZ.y = 0; W.y = 0; }   // unowned slot: keep the arithmetic tame
+    const double w0_in = W.x, w1_in = W.y;
+    bool dead0 = push_one<WALL>(m, ef4, s, dt, X.x, Y.x, Z.x, VX.x, VY.x, VZ.x, W.x);
+    bool dead1 = push_one<WALL>(m, ef4, s, dt, X.y, Y.y, Z.y, VX.y, VY.y, VZ.y, W.y);
+    dead0 = dead0 && v0;
+    dead1 = dead1 && v1;
+    if (v1) {
+        st2(px + i0, X.x, X.y); st2(py + i0, Y.x, Y.y); st2(pz + i0, Z.x, Z.y);
+        st2(pvx + i0, VX.x, VX.y); st2(pvy + i0, VY.x, VY.y); st2(pvz + i0, VZ.x, VZ.y);
+    } else if (v0) {
+        px[i0] = X.x; py[i0] = Y.x; pz[i0] = Z.x; pvx[i0] = VX.x; pvy[i0] = VY.x; pvz[i0] = VZ.x;
     }
     if (WALL == ESPIC_WALL_ABSORB) {
-        unsigned w = __ballot_sync(0xffffffffu, valid && dead);
-        if ((threadIdx.x & 31) == 0 && (idx - (threadIdx.x & 31)) < n) dead_words[idx >> 5] = w;
+        if (dead0 && w0_in != 0) pmpw[i0] = 0;               // part.mpw = 0 (Species.cpp:31)
+        if (dead1 && w1_in != 0) pmpw[i0 + 1] = 0;
+        // kill bit of particle wbase + b is bit (b & 31) of word (wbase + b) >> 5: interleave the two ballots
+        const uint32_t b0 = __ballot_sync(0xffffffffu, dead0), b1 = __ballot_sync(0xffffffffu, dead1);
+        if (lane == 0) {
+            const uint32_t lo = spread16(b0) | (spread16(b1) << 1);
+            const uint32_t hi = spread16(b0 >> 16) | (spread16(b1 >> 16) << 1);
+            dead_words[wbase >> 5] = lo;
+            if (wbase + 32 < n) dead_words[(wbase >> 5) + 1] = hi;
+        }
     }
+    if (FUSE) deposit_pair<MODE>(m, acc, scale, v0 && !dead0, X.x, Y.x, Z.x, W.x, v1 && !dead1, X.y, Y.y, Z.y, W.y);
 }
 
 // ---- removal in the reference's swap-with-last order (Species.cpp:36-46) ------------------------------
@@ -287,8 +419,8 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     const long long nw = (n + 31) / 32;
     int r;
     if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw, c->stream))) return r; }
-    const unsigned grid = nblk(n, 256);
-#define PUSH_ARGS c->m, c->ef, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale
+    const unsigned grid = nblk((n + 1) / 2, 256);
+#define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale
     if (wall_mode == ESPIC_WALL_ABSORB) {
         if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
@@ -338,9 +470,9 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
         if (s.np > 0) {
             const double scale = ldexp(1.0, s.acc_shift);
             if (mode == ESPIC_DEPOSIT_FP64)
-                k_deposit<ESPIC_DEPOSIT_FP64><<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
+                k_deposit<ESPIC_DEPOSIT_FP64><<<nblk((s.np + 1) / 2, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
             else
-                k_deposit<ESPIC_DEPOSIT_FIXED><<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
+                k_deposit<ESPIC_DEPOSIT_FIXED><<<nblk((s.np + 1) / 2, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
             LAUNCH_CHECK(c);
         }
     }
@@ -362,10 +494,8 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
 
 __device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y, double z)
 {
-    int i, j, k; double d;
-    cell_frac(x, m.x0[0], m.dh[0], m.ni, i, d);
-    cell_frac(y, m.x0[1], m.dh[1], m.nj, j, d);
-    cell_frac(z, m.x0[2], m.dh[2], m.nk, k, d);
+    int i, j, k; double d0, d1, d2;
+    cell3(m, x, y, z, i, j, k, d0, d1, d2);
     if (i < 0) i = 0;
     if (j < 0) j = 0;
     if (k < 0) k = 0;
@@ -496,7 +626,7 @@ __global__ void __launch_bounds__(256) k_add_flags(MeshC m, AddSrc a, long long 
     flags[i] = in_bounds(m, q[0], q[1], q[2]) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_add_write(MeshC m, AddSrc a, long long n, const double *__restrict__ ef,
+__global__ void __launch_bounds__(256) k_add_write(MeshC m, AddSrc a, long long n, const double *__restrict__ ef4,
                                                    const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pre,
                                                    const uint32_t *__restrict__ coff, long long base, double qm, double hdt,
                                                    double *p0, double *p1, double *p2, double *p3, double *p4, double *p5, double *p6)
@@ -506,11 +636,9 @@ __global__ void __launch_bounds__(256) k_add_write(MeshC m, AddSrc a, long long 
     double q[7];
     add_candidate(m, a, i, q);
     int ci, cj, ck; double di, dj, dk;
-    cell_frac(q[0], m.x0[0], m.dh[0], m.ni, ci, di);
-    cell_frac(q[1], m.x0[1], m.dh[1], m.nj, cj, dj);
-    cell_frac(q[2], m.x0[2], m.dh[2], m.nk, ck, dk);
+    cell3(m, q[0], q[1], q[2], ci, cj, ck, di, dj, dk);
     double e[3];
-    gather_ef(m, ef, ci, cj, ck, di, dj, dk, e);
+    gather_ef(m, ef4, ci, cj, ck, di, dj, dk, e);
     // vel -= charge/mass*ef_part*(0.5*dt)   (Species.cpp:77)
     long long dst = base + (long long)scan_at(pre, coff, i);
     p0[dst] = q[0]; p1[dst] = q[1]; p2[dst] = q[2];
@@ -532,7 +660,7 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, n, c->dscal + 2))) return r;
     const double qm = s.charge / s.mass, hdt = 0.5 * dt;
-    k_add_write<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->ef, c->cell_cnt, c->scan_pre, c->scan_coff, s.np, qm, hdt,
+    k_add_write<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->ef4, c->cell_cnt, c->scan_pre, c->scan_coff, s.np, qm, hdt,
                                                      s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
     LAUNCH_CHECK(c);
     unsigned long long *h = (unsigned long long *)c->hpin;
