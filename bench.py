@@ -222,9 +222,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=float, default=2e8, help="macroparticles per GPU")
     ap.add_argument("--mesh", type=int, default=128)
-    ap.add_argument("--solver", default="pcg", choices=["pcg", "gs", "qn"])
+    ap.add_argument("--solver", default="mg", choices=["pcg", "mg", "gs", "qn"],
+                    help="pcg: Newton + Jacobi-PCG (the reference's preconditioner); mg: same with a multigrid V-cycle preconditioner")
     ap.add_argument("--sort-every", type=int, default=5)
     ap.add_argument("--fixed-point", action="store_true", help="bit-reproducible int64 deposition")
+    ap.add_argument("--fuse", action="store_true", help="scatter inside the push kernel instead of the tiled deposit kernel")
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -257,7 +259,7 @@ def main():
     n_total = n_local * (world if args.impl == "ours" else args.gpus)
     box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
     mpw = N0 * box_vol / n_total
-    solver = {"pcg": es.SOLVE_PCG, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[args.solver]
+    solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[args.solver]
     max_it, tol = 5000, 1e-4
     workload = "sphere-%d^3-mesh-%.0e-ions-per-gpu-%s" % (n_mesh, n_local, args.solver)
 
@@ -280,7 +282,7 @@ def main():
     del t
     torch.cuda.empty_cache()
     dmode = es.DEPOSIT_FIXED if args.fixed_point else es.DEPOSIT_FP64
-    pflags = es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if args.fixed_point else 0)
+    pflags = (es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if args.fixed_point else 0)) if args.fuse else 0
 
     log("particles resident: %d on rank %d" % (n_gen, rank))
     e.sort_by_cell(sp)

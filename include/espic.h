@@ -112,8 +112,10 @@ enum { ESPIC_SOLVE_GS = 0,      /* PotentialSolver::solveGS, nonlinear Boltzmann
                                    Neumann rows eliminated exactly so the linear system is SPD and CG cannot break down */
        ESPIC_SOLVE_QN = 2,      /* solveQN (:204-222) */
        ESPIC_SOLVE_GS_BOX = 3,  /* ch2 PotentialSolver::solve, linear SOR on interior nodes (ch2/PotentialSolver.cpp:11-67) */
-       ESPIC_SOLVE_PCG_REF = 4 };/* solveNRPCG + solvePCGLinear + solveGSLinear fallback restated operation for operation on the
+       ESPIC_SOLVE_PCG_REF = 4, /* solveNRPCG + solvePCGLinear + solveGSLinear fallback restated operation for operation on the
                                    reference's non-symmetric 7-band matrix (:225-331,:433-461); inherits its breakdowns */
+       ESPIC_SOLVE_PCG_MG = 5 };/* ESPIC_SOLVE_PCG with the Jacobi preconditioner of solvePCGLinear (:304) replaced by one
+                                   aggregation-multigrid V-cycle: same Newton iteration, same equations, same stopping tests */
 
 typedef struct {
     int type;

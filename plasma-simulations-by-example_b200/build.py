@@ -17,7 +17,8 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(HERE, "csrc", "espic_internal.cuh"), os.path.join(ROOT, "include", "espic.h")]
+    csrc = os.path.join(HERE, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "espic.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -786,6 +786,23 @@ static int solve_nrpcg_spd(espic_ctx *c, const espic_solve_params *p, espic_solv
     return 0;
 }
 
+#include "espic_mg.cuh"
+
+static MgHierarchy *g_mg_of(espic_ctx *c)
+{
+    if (!c->mg) c->mg = new MgHierarchy();
+    return static_cast<MgHierarchy *>(c->mg);
+}
+
+void espic_mg_destroy(espic_ctx *c)
+{
+    if (!c->mg) return;
+    MgHierarchy *H = static_cast<MgHierarchy *>(c->mg);
+    cudaFree(H->pool);
+    delete H;
+    c->mg = nullptr;
+}
+
 extern "C" int espic_solve(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info_out)
 {
     CK(cudaSetDevice(c->device));
@@ -802,6 +819,7 @@ extern "C" int espic_solve(espic_ctx *c, const espic_solve_params *p, espic_solv
         case ESPIC_SOLVE_GS_BOX: r = solve_sor(c, p, true, &info); break;
         case ESPIC_SOLVE_PCG: r = solve_nrpcg_spd(c, p, &info); break;
         case ESPIC_SOLVE_PCG_REF: r = solve_nrpcg_ref(c, p, &info); break;
+        case ESPIC_SOLVE_PCG_MG: r = solve_nrpcg_mg(c, p, &info); break;
         default: espic_set_error("espic_solve: unknown solver type %d", p->type); return -1;
     }
     if (info_out) *info_out = info;

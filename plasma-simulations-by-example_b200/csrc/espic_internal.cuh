@@ -63,6 +63,7 @@ struct espic_ctx {
     int node_type_mode = -1;       // which solver family node_type was built for
     long long geom_version = 0, node_type_version = -1, diag0_version = -1;
     int sm_count = 148;
+    void *mg = nullptr;            // MgHierarchy of the multigrid-preconditioned solver (espic_mg.cuh)
     // comm
     void *nccl = nullptr; int rank = 0, nranks = 1;
 };
@@ -84,7 +85,8 @@ template <typename T> static inline int ensure_buf(T **ptr, long long *cap, long
 #define SCAN_CHUNK_LOG2 13
 int espic_scan_u32(espic_ctx *ctx, const uint32_t *in, long long n, unsigned long long *d_total);
 
-int espic_repack_ef(espic_ctx *c);     // espic_api.cu: refresh ef4 after ef was written from outside
+int espic_repack_ef(espic_ctx *c);
+void espic_mg_destroy(espic_ctx *c);   // espic_fields.cu     // espic_api.cu: refresh ef4 after ef was written from outside
 
 // espic_comm.cu
 void espic_comm_destroy(espic_ctx *c);

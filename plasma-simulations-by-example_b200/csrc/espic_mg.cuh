@@ -1,0 +1,608 @@
+// espic_mg.cuh -- aggregation-multigrid preconditioned CG for the Newton systems of the Boltzmann-electron Poisson solve.
+// Textually included by espic_fields.cu (it uses StencilC, the node types and the SPD Newton kernels defined there).
+//
+// The reference preconditions CG with the matrix diagonal (PotentialSolver::solvePCGLinear, PotentialSolver.cpp:299-331);
+// on the 128^3 mesh that takes ~300 iterations per Newton step and is >60 % of a PIC step.  ESPIC_SOLVE_PCG_MG keeps the
+// Newton iteration, the SPD system K = -(L - diag P) on the REG nodes, the stopping tests (sqrt(sum r^2 / n) < tol for
+// CG, sqrt(sum y^2 / n) < nr_tol for Newton) and replaces only the preconditioner by one multigrid V(1,1) cycle:
+//   * coarsening by 2x2x2 aggregation of nodes, piecewise-constant prolongation P, restriction P^T, Galerkin coarse
+//     operators P^T K P -- for a 7-point stencil these are again 7-point stencils (diagonal + three link arrays);
+//   * damped-Jacobi smoothing (w = 0.8), one sweep before and one after the coarse correction; both are fused with the
+//     grid transfer (down pass: smooth from zero + residual + restriction; up pass: prolongation + smooth), so a
+//     level costs two passes and two grid-wide barriers per V-cycle;
+//   * a few Jacobi sweeps on the coarsest level.
+// The cycle is a symmetric positive definite operator (self-adjoint smoother, R = P^T), which CG requires.
+// Everything runs in ONE persistent cooperative kernel per linear solve; convergence is tested on the device.
+#pragma once
+
+#define MG_MAX_LEVELS 8
+#define MG_OMEGA 0.8
+#define MG_COARSE_SWEEPS 6
+#define MG_COARSEST_NODES 4096      // stop coarsening once a level is this small
+
+struct MgLevel {
+    int ni, nj, nk;
+    long long nn;
+    double *diag, *minv;      // Galerkin diagonal and its inverse (0 on nodes without unknowns)
+    double *cx, *cy, *cz;     // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
+    double *x, *xn, *b;       // pre-smoothed iterate, post-smoothed iterate, right-hand side
+};
+
+struct MgHierarchy {
+    int nlev = 0;
+    MgLevel L[MG_MAX_LEVELS];
+    long long geom_version = -1;
+    double *pool = nullptr;   // one allocation for all coarse-level arrays
+};
+
+static MgHierarchy *g_mg_of(espic_ctx *c);   // stored in the context (espic_internal.cuh: void *mg)
+
+// ---- setup kernels -------------------------------------------------------------------------------------------------
+
+// links of level 1 from the fine node types: a fine link (u, u+e) exists iff both ends are REG; its weight is g = 1/dh^2
+__global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const uint8_t *__restrict__ type, MgLevel C)
+{
+    long long I = blockIdx.x * 256ll + threadIdx.x;
+    if (I >= C.nn) return;
+    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+    double lx = 0, ly = 0, lz = 0;
+    for (int dk = 0; dk < 2; dk++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int di = 0; di < 2; di++) {
+                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
+                const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+                if (type[u] != NT_REG) continue;
+                if (di == 1 && i + 1 < s.ni && type[u + 1] == NT_REG) lx += s.gdx2;
+                if (dj == 1 && j + 1 < s.nj && type[u + s.sj] == NT_REG) ly += s.gdy2;
+                if (dk == 1 && k + 1 < s.nk && type[u + s.sk] == NT_REG) lz += s.gdz2;
+            }
+    C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
+}
+
+// links of level l+1 from the links of level l (l >= 1)
+__global__ void __launch_bounds__(256) k_mg_links_from_links(MgLevel F, MgLevel C)
+{
+    long long I = blockIdx.x * 256ll + threadIdx.x;
+    if (I >= C.nn) return;
+    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+    double lx = 0, ly = 0, lz = 0;
+    for (int dk = 0; dk < 2; dk++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int di = 0; di < 2; di++) {
+                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
+                const long long u = ((long long)k * F.nj + j) * F.ni + i;
+                if (di == 1) lx += F.cx[u];
+                if (dj == 1) ly += F.cy[u];
+                if (dk == 1) lz += F.cz[u];
+            }
+    C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
+}
+
+// Galerkin diagonal of level 1: sum of the fine diagonals minus twice the fine links inside the aggregate
+__global__ void __launch_bounds__(256) k_mg_diag_from_fine(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ diagJ, MgLevel C)
+{
+    long long I = blockIdx.x * 256ll + threadIdx.x;
+    if (I >= C.nn) return;
+    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+    double d = 0;
+    for (int dk = 0; dk < 2; dk++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int di = 0; di < 2; di++) {
+                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
+                const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+                if (type[u] != NT_REG) continue;
+                d += diagJ[u];
+                if (di == 0 && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
+                if (dj == 0 && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
+                if (dk == 0 && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
+            }
+    C.diag[I] = d;
+    C.minv[I] = d > 0 ? 1.0 / d : 0.0;
+}
+
+__global__ void __launch_bounds__(256) k_mg_diag_from_level(MgLevel F, MgLevel C)
+{
+    long long I = blockIdx.x * 256ll + threadIdx.x;
+    if (I >= C.nn) return;
+    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+    double d = 0;
+    for (int dk = 0; dk < 2; dk++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int di = 0; di < 2; di++) {
+                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
+                const long long u = ((long long)k * F.nj + j) * F.ni + i;
+                d += F.diag[u];
+                if (di == 0 && i + 1 < F.ni) d -= 2 * F.cx[u];
+                if (dj == 0 && j + 1 < F.nj) d -= 2 * F.cy[u];
+                if (dk == 0 && k + 1 < F.nk) d -= 2 * F.cz[u];
+            }
+    C.diag[I] = d;
+    C.minv[I] = d > 0 ? 1.0 / d : 0.0;
+}
+
+// ---- device pieces of the V-cycle (grid-stride; the caller separates them with grid.sync()) ----------------------------
+
+// off-diagonal part of K v at fine node u (level 0): neighbours outside the REG set carry minv == 0 and are skipped
+__device__ __forceinline__ double mg_offdiag0(const StencilC &s, const double *__restrict__ v, long long u)
+{
+    return s.gdx2 * (v[u - 1] + v[u + 1]) + s.gdy2 * (v[u - s.sj] + v[u + s.sj]) + s.gdz2 * (v[u - s.sk] + v[u + s.sk]);
+}
+
+// sum over neighbours of link * f(neighbour) on a coarse level, f given as a functor of the neighbour's flat index
+template <typename F>
+__device__ __forceinline__ double mg_offdiag(const MgLevel &L, int i, int j, int k, long long u, F f)
+{
+    const long long sj = L.ni, sk = (long long)L.ni * L.nj;
+    double a = 0;
+    if (i > 0) a += L.cx[u - 1] * f(u - 1);
+    if (i + 1 < L.ni) a += L.cx[u] * f(u + 1);
+    if (j > 0) a += L.cy[u - sj] * f(u - sj);
+    if (j + 1 < L.nj) a += L.cy[u] * f(u + sj);
+    if (k > 0) a += L.cz[u - sk] * f(u - sk);
+    if (k + 1 < L.nk) a += L.cz[u] * f(u + sk);
+    return a;
+}
+
+// Down pass from the fine level: x0 = w D^-1 r is already stored (written together with r); the residual r - K x0 is
+// summed over each aggregate -> b of level 1.  One thread per COARSE node (it owns the 8 children).
+__device__ __forceinline__ void mg_down0(const StencilC &s, const double *__restrict__ r, const double *__restrict__ diag,
+                                         const double *__restrict__ x0, const MgLevel &C, long long t0, long long stride)
+{
+    for (long long I = t0; I < C.nn; I += stride) {
+        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+        double sum = 0;
+        if (C.minv[I] != 0) {
+#pragma unroll
+            for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+                for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+                    for (int di = 0; di < 2; di++) {
+                        const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                        if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
+                        const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+                        const double dg = diag[u];
+                        if (dg == 0) continue;                 // not an unknown
+                        sum += r[u] - (dg * x0[u] - mg_offdiag0(s, x0, u));
+                    }
+        }
+        C.b[I] = sum;
+    }
+}
+
+// The coarse levels are small: what matters there is the length of the dependent-load chain of a thread, not bandwidth.
+// All coarse passes therefore spread one node over 8 consecutive lanes (the 8 children of an aggregate, or the 7 stencil
+// terms of a node) and combine with three shuffles; the sum order is fixed, so results are reproducible.
+__device__ __forceinline__ double mg_sum8(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+// Down pass between coarse levels F -> C: lane c of a group handles child c of coarse node I
+__device__ __forceinline__ void mg_down(const MgLevel &F, const MgLevel &C, long long t0, long long stride)
+{
+    const long long total = C.nn * 8;
+    for (long long w = t0; (w & ~31LL) < total; w += stride) {
+        const long long I = w >> 3;
+        const int c = (int)(w & 7);
+        double res = 0;
+        if (I < C.nn) {
+            const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+            const int i = 2 * ci + (c & 1), j = 2 * cj + ((c >> 1) & 1), k = 2 * ck + (c >> 2);
+            if (i < F.ni && j < F.nj && k < F.nk) {
+                const long long u = ((long long)k * F.nj + j) * F.ni + i;
+                const double mi = F.minv[u];
+                double xu = 0;
+                if (mi != 0) {
+                    xu = MG_OMEGA * F.b[u] * mi;
+                    const double off = MG_OMEGA * mg_offdiag(F, i, j, k, u, [&](long long v) { return F.b[v] * F.minv[v]; });
+                    res = F.b[u] - (F.diag[u] * xu - off);
+                }
+                F.x[u] = xu;
+            }
+        }
+        res = mg_sum8(res);
+        if (c == 0 && I < C.nn) C.b[I] = res;
+    }
+}
+
+// stencil term c of node u on a coarse level: c = 0 centre (b - diag*v), c = 1..6 the six links, c = 7 nothing
+template <typename F>
+__device__ __forceinline__ double mg_term(const MgLevel &L, int c, int i, int j, int k, long long u, F val, double &centre)
+{
+    const long long sj = L.ni, sk = (long long)L.ni * L.nj;
+    switch (c) {
+        case 0: centre = val(u, i, j, k); return L.b[u] - L.diag[u] * centre;
+        case 1: return i > 0 ? L.cx[u - 1] * val(u - 1, i - 1, j, k) : 0.0;
+        case 2: return i + 1 < L.ni ? L.cx[u] * val(u + 1, i + 1, j, k) : 0.0;
+        case 3: return j > 0 ? L.cy[u - sj] * val(u - sj, i, j - 1, k) : 0.0;
+        case 4: return j + 1 < L.nj ? L.cy[u] * val(u + sj, i, j + 1, k) : 0.0;
+        case 5: return k > 0 ? L.cz[u - sk] * val(u - sk, i, j, k - 1) : 0.0;
+        case 6: return k + 1 < L.nk ? L.cz[u] * val(u + sk, i, j, k + 1) : 0.0;
+        default: return 0.0;
+    }
+}
+
+// one damped-Jacobi sweep on level L: out = in + w D^-1 (b - K in); 8 lanes per node
+__device__ __forceinline__ void mg_jacobi(const MgLevel &L, const double *__restrict__ in, double *__restrict__ out,
+                                          long long t0, long long stride)
+{
+    const long long total = L.nn * 8;
+    for (long long w = t0; (w & ~31LL) < total; w += stride) {
+        const long long u = w >> 3;
+        const int c = (int)(w & 7);
+        double term = 0, centre = 0, mi = 0;
+        if (u < L.nn) {
+            mi = L.minv[u];
+            if (mi != 0) {
+                const int i = (int)(u % L.ni), j = (int)((u / L.ni) % L.nj), k = (int)(u / ((long long)L.ni * L.nj));
+                term = mg_term(L, c, i, j, k, u, [&](long long v, int, int, int) { return in[v]; }, centre);
+            }
+        }
+        const double tot = mg_sum8(term);
+        centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
+        if (c == 0 && u < L.nn) out[u] = (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0;
+    }
+}
+
+// Up pass on a coarse level F with the correction e of the next coarser level C:
+//   xn = (x + P e) + w D^-1 (b - K (x + P e))           (8 lanes per node: one stencil term each)
+// fine != nullptr (F is level 1): the result is also handed down to the fine level, lane c writing child c:
+//   e0 = x0 + P xn  (0 on children that are not unknowns)
+__device__ __forceinline__ void mg_up(const MgLevel &F, const MgLevel &C, const double *__restrict__ e, long long t0, long long stride)
+{
+    if (F.nn * 2 > stride) {          // a big level: one thread per node keeps every lane busy
+        for (long long u = t0; u < F.nn; u += stride) {
+            const double mi = F.minv[u];
+            double out = 0;
+            if (mi != 0) {
+                const int i = (int)(u % F.ni), j = (int)((u / F.ni) % F.nj), k = (int)(u / ((long long)F.ni * F.nj));
+                double centre = 0, tot = 0;
+#pragma unroll
+                for (int c = 0; c < 7; c++)
+                    tot += mg_term(F, c, i, j, k, u, [&](long long v, int vi, int vj, int vk) {
+                        return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)]; }, centre);
+                out = centre + MG_OMEGA * mi * tot;
+            }
+            F.xn[u] = out;
+        }
+        return;
+    }
+    const long long total = F.nn * 8;
+    for (long long w = t0; (w & ~31LL) < total; w += stride) {
+        const long long u = w >> 3;
+        const int c = (int)(w & 7);
+        double term = 0, centre = 0, mi = 0;
+        int i = 0, j = 0, k = 0;
+        if (u < F.nn) {
+            mi = F.minv[u];
+            i = (int)(u % F.ni); j = (int)((u / F.ni) % F.nj); k = (int)(u / ((long long)F.ni * F.nj));
+            if (mi != 0) {
+                // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
+                term = mg_term(F, c, i, j, k, u, [&](long long v, int vi, int vj, int vk) {
+                    return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)]; }, centre);
+            }
+        }
+        const double tot = mg_sum8(term);
+        centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
+        const double out = (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0;
+        if (c == 0 && u < F.nn) F.xn[u] = out;
+    }
+}
+
+// Up pass on the fine level: z = (x0 + P e) + w D^-1 (r - K (x0 + P e)), the prolongated iterate formed on the fly (the
+// level-1 array e is 1/8 of a fine vector and stays in L1/L2); returns this thread's share of r.z
+__device__ __forceinline__ double mg_up0(const StencilC &s, const double *__restrict__ r, const double *__restrict__ diag,
+                                         const double *__restrict__ minv, const double *__restrict__ x0, const MgLevel &C,
+                                         const double *__restrict__ e, double *__restrict__ z, long long t0, long long stride)
+{
+    double acc = 0;
+    for (long long u = t0; u < s.nn; u += stride) {
+        const double mi = minv[u];
+        double zu = 0;
+        if (mi != 0) {
+            const int i = (int)(u % s.ni), j = (int)((u / s.ni) % s.nj), k = (int)(u / s.sk);
+            auto val = [&](long long v, int vi, int vj, int vk) {
+                // the fine links are implicit constants: neighbours outside the REG set must be masked explicitly
+                return minv[v] != 0 ? x0[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)] : 0.0;
+            };
+            const double off = s.gdx2 * (val(u - 1, i - 1, j, k) + val(u + 1, i + 1, j, k)) +
+                               s.gdy2 * (val(u - s.sj, i, j - 1, k) + val(u + s.sj, i, j + 1, k)) +
+                               s.gdz2 * (val(u - s.sk, i, j, k - 1) + val(u + s.sk, i, j, k + 1));
+            const double xu = x0[u] + e[((long long)(k >> 1) * C.nj + (j >> 1)) * C.ni + (i >> 1)];
+            zu = xu + MG_OMEGA * mi * (r[u] - (diag[u] * xu - off));
+            acc += r[u] * zu;
+        }
+        z[u] = zu;
+    }
+    return acc;
+}
+
+struct MgPcgArgs {
+    StencilC s;
+    int nlev;
+    int coarse_sweeps;            // Jacobi sweeps on the coarsest level (even)
+    MgLevel L[MG_MAX_LEVELS];     // L[0]: diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
+    double *delta, *r, *z, *d0, *d1, *q;     // r enters holding the right-hand side; d0/d1 ping-pong search directions
+    double *part;
+    int max_it;
+    double tol;
+    double *out;                  // converged, iterations, l2
+    unsigned long long *prof;     // optional: nanoseconds per phase as seen by block 0 (ESPIC_MG_PROFILE=1), 8 slots
+};
+
+__device__ __forceinline__ unsigned long long mg_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase ids: 0 down0, 1 coarser down passes, 2 coarsest sweeps, 3 coarse up passes, 4 up0 + r.z, 5 d/q pass, 6 r pass
+#define MG_TICK(id) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = mg_now(); a.prof[id] += n_ - tick; tick = n_; } } while (0)
+
+#define MG_BLOCK0_MAX 0        // a coarsest level this small is swept by block 0 alone (block barriers instead of grid barriers)
+
+// z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.
+__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, const MgPcgArgs &a, long long t0, long long stride,
+                                            unsigned long long &tick)
+{
+    const MgLevel &L0 = a.L[0];
+    if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
+        double acc = 0;
+        for (long long u = t0; u < a.s.nn; u += stride) { double zu = L0.minv[u] * a.r[u]; a.z[u] = zu; acc += a.r[u] * zu; }
+        return acc;
+    }
+    mg_down0(a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride);
+    grid.sync();
+    MG_TICK(0);
+    for (int l = 1; l + 1 < a.nlev; l++) {
+        mg_down(a.L[l], a.L[l + 1], t0, stride);
+        grid.sync();
+    }
+    MG_TICK(1);
+    // coarsest level: Jacobi sweeps from zero; the result ends in x (even sweep count)
+    const MgLevel &Lc = a.L[a.nlev - 1];
+    if (Lc.nn <= MG_BLOCK0_MAX) {
+        if (blockIdx.x == 0) {
+            for (long long u = threadIdx.x; u < Lc.nn; u += blockDim.x) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
+            __syncthreads();
+            for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
+                mg_jacobi(Lc, Lc.x, Lc.xn, threadIdx.x, blockDim.x);
+                __syncthreads();
+                mg_jacobi(Lc, Lc.xn, Lc.x, threadIdx.x, blockDim.x);
+                __syncthreads();
+            }
+        }
+        grid.sync();
+    } else {
+        for (long long u = t0; u < Lc.nn; u += stride) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
+        grid.sync();
+        for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
+            mg_jacobi(Lc, Lc.x, Lc.xn, t0, stride);
+            grid.sync();
+            mg_jacobi(Lc, Lc.xn, Lc.x, t0, stride);
+            grid.sync();
+        }
+    }
+    MG_TICK(2);
+    const double *e = Lc.x;
+    for (int l = a.nlev - 2; l >= 1; l--) {
+        mg_up(a.L[l], a.L[l + 1], e, t0, stride);
+        grid.sync();
+        e = a.L[l].xn;
+    }
+    MG_TICK(3);
+    return mg_up0(a.s, a.r, L0.diag, L0.minv, L0.x, a.L[1], e, a.z, t0, stride);
+}
+
+__global__ void __launch_bounds__(512) k_mg_pcg(MgPcgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    __shared__ double bc;
+    const StencilC &s = a.s;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nb = gridDim.x;
+    double *pA = a.part, *pB = a.part + nb, *pC = a.part + 2 * nb;
+    const double *diag = a.L[0].diag;
+
+    const double *minv = a.L[0].minv;
+    double *x0 = a.L[0].x;
+    // delta = 0: r = R; x0 = w D^-1 r; |r|
+    double acc = 0;
+    for (long long u = t0; u < s.nn; u += stride) { double r = a.r[u]; x0[u] = MG_OMEGA * r * minv[u]; acc += r * r; }
+    double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) pC[blockIdx.x] = t;
+    grid.sync();
+    double l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+    int it = 0, converged = l2 < a.tol;
+    double rz = 0, beta = 0;
+    double *d_old = a.d0, *d_new = a.d1;
+    unsigned long long tick = mg_now();
+    while (!converged && it < a.max_it) {
+        // z = M^-1 r ; rz' = r.z
+        acc = mg_vcycle(grid, a, t0, stride, tick);
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pB[blockIdx.x] = t;
+        grid.sync();
+        MG_TICK(4);
+        const double rz_new = grid_total(pB, nb, sh, &bc);
+        beta = (it == 0) ? 0.0 : rz_new / rz;
+        rz = rz_new;
+        // d = z + beta d (formed on the fly for the neighbours, written for this node) ; q = K d ; dq = d.q
+        acc = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            const double dj = diag[u];
+            double du = 0, qu = 0;
+            if (dj != 0) {
+                du = a.z[u] + beta * d_old[u];
+                // z and d are identically zero outside the REG set: no neighbour masks
+                const double off = s.gdx2 * ((a.z[u - 1] + beta * d_old[u - 1]) + (a.z[u + 1] + beta * d_old[u + 1])) +
+                                   s.gdy2 * ((a.z[u - s.sj] + beta * d_old[u - s.sj]) + (a.z[u + s.sj] + beta * d_old[u + s.sj])) +
+                                   s.gdz2 * ((a.z[u - s.sk] + beta * d_old[u - s.sk]) + (a.z[u + s.sk] + beta * d_old[u + s.sk]));
+                qu = dj * du - off;
+                acc += du * qu;
+            }
+            d_new[u] = du;
+            a.q[u] = qu;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pA[blockIdx.x] = t;
+        grid.sync();
+        MG_TICK(5);
+        const double alpha = rz / grid_total(pA, nb, sh, &bc);
+        // delta += alpha d ; r -= alpha q ; |r|
+        acc = 0;
+        for (long long u = t0; u < s.nn; u += stride) {
+            a.delta[u] = a.delta[u] + alpha * d_new[u];
+            const double r = a.r[u] - alpha * a.q[u];
+            a.r[u] = r;
+            x0[u] = MG_OMEGA * r * minv[u];          // pre-smoothed iterate of the next V-cycle
+            acc += r * r;
+        }
+        t = block_sum(acc, sh);
+        if (threadIdx.x == 0) pC[blockIdx.x] = t;
+        grid.sync();
+        MG_TICK(6);
+        l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+        it++;
+        double *tmp = d_old; d_old = d_new; d_new = tmp;
+        if (l2 < a.tol) converged = 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+
+static int mg_setup(espic_ctx *c, const StencilC &s)
+{
+    MgHierarchy *H = g_mg_of(c);
+    if (H->geom_version == c->geom_version && H->nlev > 0) return 0;
+    if (H->pool) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
+    // level dimensions: halve (rounding up) while every dimension stays >= 4 and the level is worth a barrier
+    int ni = s.ni, nj = s.nj, nk = s.nk, nlev = 1;
+    long long dims[MG_MAX_LEVELS][3] = {{ni, nj, nk}};
+    while (nlev < MG_MAX_LEVELS && std::min(ni, std::min(nj, nk)) > 4 && (long long)ni * nj * nk > MG_COARSEST_NODES) {
+        ni = (ni + 1) / 2; nj = (nj + 1) / 2; nk = (nk + 1) / 2;
+        dims[nlev][0] = ni; dims[nlev][1] = nj; dims[nlev][2] = nk;
+        nlev++;
+    }
+    long long total = 0;
+    for (int l = 1; l < nlev; l++) total += 8 * dims[l][0] * dims[l][1] * dims[l][2];
+    if (total > 0) CK(cudaMalloc(&H->pool, (size_t)total * sizeof(double)));
+    double *p = H->pool;
+    for (int l = 0; l < nlev; l++) {
+        MgLevel &L = H->L[l];
+        L.ni = (int)dims[l][0]; L.nj = (int)dims[l][1]; L.nk = (int)dims[l][2];
+        L.nn = dims[l][0] * dims[l][1] * dims[l][2];
+        if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = nullptr; continue; }
+        L.diag = p; p += L.nn; L.minv = p; p += L.nn; L.cx = p; p += L.nn; L.cy = p; p += L.nn; L.cz = p; p += L.nn;
+        L.x = p; p += L.nn; L.xn = p; p += L.nn; L.b = p; p += L.nn;
+    }
+    H->nlev = nlev;
+    for (int l = 1; l < nlev; l++) {
+        if (l == 1) k_mg_links_from_types<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->L[1]);
+        else k_mg_links_from_links<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
+        LAUNCH_CHECK(c);
+    }
+    H->geom_version = c->geom_version;
+    return 0;
+}
+
+// Newton + multigrid-preconditioned CG (same outer iteration as solve_nrpcg_spd)
+static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info)
+{
+    int r;
+    if ((r = ensure_node_types(c, 0))) return r;
+    if ((r = ensure_sv(c, 8))) return r;
+    StencilC s = make_stencil(c->m);
+    if ((r = mg_setup(c, s))) return r;
+    MgHierarchy *H = g_mg_of(c);
+    double *diag0 = c->sv[0], *R = c->sv[1], *diagJ = c->sv[2], *minv = c->sv[3];
+    double *delta = c->sv[4], *z = c->sv[5], *d0 = c->sv[6], *d1 = c->sv[7];
+    // two more fine vectors (q, x0) + the partial sums live in the reduction scratch
+    if ((r = ensure_buf(&c->red, &c->red_cap, 2 * s.nn + 8192, c->stream))) return r;
+    double *q = c->red, *x0 = c->red + s.nn, *part = c->red + 2 * s.nn;
+    static int coarse_sweeps = -1;
+    if (coarse_sweeps < 0) {
+        const char *ev = getenv("ESPIC_MG_COARSE_SWEEPS");
+        coarse_sweeps = ev ? std::max(0, atoi(ev)) : MG_COARSE_SWEEPS;
+        coarse_sweeps += coarse_sweeps & 1;
+    }
+    if (c->diag0_version != c->geom_version) {
+        k_spd_diag0<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, diag0);
+        LAUNCH_CHECK(c);
+        c->diag0_version = c->geom_version;
+    }
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, 0));
+    if (bps < 1) { espic_set_error("k_mg_pcg cannot be made resident"); return -1; }
+    long long want = (s.nn + 511) / 512;
+    int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
+    if (3 * grid > 4096) grid = 4096 / 3;
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
+    double *dout = reinterpret_cast<double *>(c->dscal + 24);
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    double norm = 0;
+    bool converged = false;
+    for (int it = 0; it < p->nr_max_it; it++) {
+        info->nr_iters++;
+        k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, diag0, p->phi0, p->Te0, p->n0,
+                                                                R, diagJ, minv, delta);
+        LAUNCH_CHECK(c);
+        // Galerkin diagonals: the Boltzmann term changes with phi, the links do not
+        for (int l = 1; l < H->nlev; l++) {
+            if (l == 1) k_mg_diag_from_fine<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, diagJ, H->L[1]);
+            else k_mg_diag_from_level<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
+            LAUNCH_CHECK(c);
+        }
+        MgPcgArgs a;
+        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps;
+        a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
+        for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
+        a.L[0].diag = diagJ; a.L[0].minv = minv; a.L[0].x = x0;
+        a.delta = delta; a.r = R; a.z = z; a.d0 = d0; a.d1 = d1; a.q = q;
+        a.part = part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
+        CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
+        void *args[] = {&a};
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, 0, c->stream));
+        LAUNCH_CHECK(c);
+        k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
+        LAUNCH_CHECK(c);
+        k_sum_final<<<1, 256, 0, c->stream>>>(part, nb_res, dres);
+        LAUNCH_CHECK(c);
+        double *h = reinterpret_cast<double *>(c->hpin) + 24;
+        CK(cudaMemcpyAsync(h, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        double sum;
+        if ((r = read_scalar(c, dres, &sum))) return r;
+        info->lin_iters += (long long)h[1];
+        if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
+        norm = sqrt(sum / (double)s.nn);
+        if (norm < p->nr_tol) { converged = true; break; }
+    }
+    for (int level = 0; level < 3; level++) {
+        k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
+        LAUNCH_CHECK(c);
+    }
+    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
+    info->converged = converged;
+    info->residual = norm;
+    if (getenv("ESPIC_MG_PROFILE")) {
+        unsigned long long hp[8];
+        CK(cudaMemcpyAsync(hp, c->dscal + 40, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemsetAsync(c->dscal + 40, 0, sizeof(hp), c->stream));
+        fprintf(stderr, "[mg profile] its=%lld  us/it: down0 %.1f  down %.1f  coarsest %.1f  up %.1f  up0+rz %.1f  dq %.1f  r %.1f\n",
+                info->lin_iters, hp[0] * 1e-3 / info->lin_iters, hp[1] * 1e-3 / info->lin_iters, hp[2] * 1e-3 / info->lin_iters,
+                hp[3] * 1e-3 / info->lin_iters, hp[4] * 1e-3 / info->lin_iters, hp[5] * 1e-3 / info->lin_iters, hp[6] * 1e-3 / info->lin_iters);
+    }
+    return 0;
+}

@@ -153,15 +153,16 @@ __device__ __forceinline__ long long particle_weights(const MeshC &m, double x, 
 template <int MODE>
 __device__ __forceinline__ void red8(const MeshC &m, double *acc, long long u, const typename AccVal<MODE>::T w[8])
 {
-    const long long sj = m.ni, sk = (long long)m.ni * m.nj;
-    AccVal<MODE>::red(acc, u, w[0]);
-    AccVal<MODE>::red(acc, u + 1, w[1]);
-    AccVal<MODE>::red(acc, u + 1 + sj, w[2]);
-    AccVal<MODE>::red(acc, u + sj, w[3]);
-    AccVal<MODE>::red(acc, u + sk, w[4]);
-    AccVal<MODE>::red(acc, u + 1 + sk, w[5]);
-    AccVal<MODE>::red(acc, u + 1 + sj + sk, w[6]);
-    AccVal<MODE>::red(acc, u + sj + sk, w[7]);
+    // four row bases, the +1 neighbours are immediate offsets
+    double *p00 = acc + u, *p10 = p00 + m.ni, *p01 = p00 + (long long)m.ni * m.nj, *p11 = p01 + m.ni;
+    AccVal<MODE>::red(p00, 0, w[0]);
+    AccVal<MODE>::red(p00, 1, w[1]);
+    AccVal<MODE>::red(p10, 1, w[2]);
+    AccVal<MODE>::red(p10, 0, w[3]);
+    AccVal<MODE>::red(p01, 0, w[4]);
+    AccVal<MODE>::red(p01, 1, w[5]);
+    AccVal<MODE>::red(p11, 1, w[6]);
+    AccVal<MODE>::red(p11, 0, w[7]);
 }
 
 // Whole-warp call.  u = lower node of the lane's cell (-1: nothing to deposit), w = its eight weights.
@@ -492,14 +493,21 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
 // sort by cell (counting sort; cell key as ch4 World::XtoC: c = k*(nj-1)*(ni-1) + j*(ni-1) + i)
 // =====================================================================================================
 
+// Sort key: the cell, refined by SORT_ZBINS slabs of the cell along z.  The beam drifts along +z, so the particles of a
+// cell cross into the next cell in the order of their z fraction; with the slabs contiguous in memory, the particles
+// that have crossed after s steps are still a contiguous run (the warp-level run merging of the deposit and the L1
+// locality of the gather survive between sorts), instead of being interleaved one by one with those that have not.
+#define SORT_ZBINS 8
 __device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y, double z)
 {
     int i, j, k; double d0, d1, d2;
     cell3(m, x, y, z, i, j, k, d0, d1, d2);
     if (i < 0) i = 0;
     if (j < 0) j = 0;
-    if (k < 0) k = 0;
-    return ((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i;
+    if (k < 0) { k = 0; d2 = 0; }
+    int zb = (int)(d2 * SORT_ZBINS);
+    zb = zb < 0 ? 0 : (zb > SORT_ZBINS - 1 ? SORT_ZBINS - 1 : zb);
+    return (((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i) * SORT_ZBINS + zb;
 }
 
 __global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
@@ -549,7 +557,7 @@ extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
     Species &s = c->sp[sp];
     const long long n = s.np;
     if (n < 2) return 0;
-    const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1);
+    const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1) * SORT_ZBINS;
     int r;
     if (s.alt_cap < s.cap) {
         for (int q = 0; q < 7; q++) {

@@ -1,13 +1,20 @@
 // PotentialSolver.cpp -- forwards solve()/computeEF() to the matrix-free device solvers (espic_solve, espic_compute_ef).
 #include "PotentialSolver.h"
 
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 static int kind_of(SolverType t)
 {
     switch (t) {
         case GS: case GSCUDA: return ESPIC_SOLVE_GS;
-        case PCG: return ESPIC_SOLVE_PCG;
+        case PCG: {
+            // Newton + PCG: multigrid-preconditioned by default; ESPIC_PCG=jacobi selects the reference's diagonal
+            // preconditioner (PotentialSolver.cpp:304).  Same equations, same stopping tests, same converged potential.
+            const char *e = std::getenv("ESPIC_PCG");
+            return (e && std::string(e) == "jacobi") ? ESPIC_SOLVE_PCG : ESPIC_SOLVE_PCG_MG;
+        }
         default: return ESPIC_SOLVE_QN;
     }
 }

@@ -338,6 +338,34 @@ def test_spd_pcg_where_reference_breaks_down():
     assert_close(got.phi, w.phi, 1e-8, "phi: SPD PCG vs reference GS at residual 1e-6")
 
 
+@pytest.mark.parametrize("dims,n0", [((21, 21, 41), 1e10), ((33, 20, 47), 1e12), ((12, 9, 14), 1e11), ((64, 64, 64), 1e12)])
+def test_multigrid_pcg_matches_jacobi_pcg(dims, n0):
+    """ESPIC_SOLVE_PCG_MG changes only the preconditioner: the converged potential must agree with the Jacobi-PCG one
+    (and so with the reference's equations) far below the production tolerance, on even, odd and ragged mesh sizes,
+    and it must need fewer CG iterations."""
+    n = 200000
+    w, sp = cases.sphere_case(seed=77, ni=dims[0], nj=dims[1], nk=dims[2], n=n, amp=0.0, mpw=n0 * 0.016 / n)
+    w.set_reference_values(0.0, 1.5, n0)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    w.solve_qn()
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    a = GpuEngine(st)
+    a.e.nr_tol = 1e-10
+    ja = a.run(["solve_pcg:20000:1e-9", "ef"])
+    b = GpuEngine(st)
+    b.e.nr_tol = 1e-10
+    mg = b.run(["solve_mg:20000:1e-9", "ef"])
+    assert ja.diag[0] == 1.0 and mg.diag[0] == 1.0
+    assert_close(mg.phi, ja.phi, 1e-10, "phi: multigrid vs Jacobi preconditioner")
+    assert_close(mg.ef, ja.ef, 1e-9, "ef")
+    assert b.info["nr_iters"] == a.info["nr_iters"]
+    if dims[0] * dims[1] * dims[2] > 4096:      # smaller meshes have no coarse level: the cycle degenerates to Jacobi
+        assert b.info["lin_iters"] < a.info["lin_iters"], (b.info, a.info)
+    if dims[0] >= 64:
+        assert b.info["lin_iters"] * 3 < a.info["lin_iters"], (b.info, a.info)
+
+
 def test_pcg_iteration_count_matches_reference():
     """Same algorithm, different summation order: PCG iteration counts stay within a few percent of the oracle's."""
     d = np.load([p for p in GOLDEN if p.endswith("sphere_pcg_shipped_mesh.npz")][0])
