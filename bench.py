@@ -68,30 +68,59 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md).  In-process NVML queries (pynvml): a
+    polling `nvidia-smi -lms` child was measured to stall this process's cudaStreamSynchronize calls for milliseconds."""
 
-    def __init__(self, index):
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def __init__(self, index, period=0.1):
         super().__init__(daemon=True)
-        self.index = index
+        self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.stop_flag = False
-        self.proc = None
+        self.source = None
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for n, bit in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                time.sleep(self.period)
+        except Exception:
+            self._run_smi()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            return
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            if self.stop_flag:
-                break
-            f = [x.strip() for x in line.split(",")]
+        self.source = "nvidia-smi"
+        while not self.stop_flag:
             try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
                 self.samples.append(float(f[0]))
                 self.max_mhz = float(f[1])
                 for n, v in zip(names, f[2:6]):
@@ -99,17 +128,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
+            time.sleep(1.0)
 
     def stop(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0, "source": self.source}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def make_particles_device(torch, n, seed, mpw, dev):
@@ -230,6 +258,7 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -320,12 +349,14 @@ def main():
         pic_step(i, wc)
         log("warm-up step %d: n=%d %s" % (i, wc[0][0], wc[0][1]))
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    if not args.no_clocks:
+        sampler.start()
+        time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     push_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
     counts = []
+    kernel_ms = []
     launches0 = e.kernel_launches()
     if world > 1:
         dist.barrier()
@@ -342,6 +373,7 @@ def main():
         n_before = e.count(sp)
         e.push(sp, DT, es.WALL_ABSORB, pflags)
         pe[2].record()
+        kernel_ms.append(e.last_push_ms())       # CUDA events around the k_push launch itself, on the launching stream
         n_live = e.count(sp)
         e.deposit(sp, dmode)
         e.compute_charge_density()
@@ -376,11 +408,13 @@ def main():
     ph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in phase_ev])     # sort, push, dep+rho, solve, ef
     phase_ms = ph.mean(axis=0)
 
-    # dominant kernel: the fused push+deposit.  push phase = kernel + removal bookkeeping; the kernel alone is timed by
-    # the library's own events when available
+    # dominant kernel: k_push (Species::advance).  Its duration is the mean over the timed steps of the CUDA-event time of
+    # the kernel launch alone (events recorded by the library on the launching stream); the push PHASE additionally holds
+    # the removal bookkeeping (popcount, scan, hole filling, one D2H count)
     push_ms = float(phase_ms[1])
+    k_ms = float(np.mean(kernel_ms))
     peak, peak_src = measured_peak_gbs()
-    achieved = PUSH_BYTES * (pushed_local / args.steps) / (push_ms * 1e-3) / 1e9
+    achieved = PUSH_BYTES * (pushed_local / args.steps) / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "push_traffic.json")
     if os.path.exists(tpath):
@@ -446,12 +480,14 @@ def main():
                        "parallelism": "particle-index sharding x%d, NCCL density all-reduce, replicated field solve" % world,
                        "l2": "inputs (%.1f GB of particles per GPU) are larger than L2" % (56 * n_local / 1e9),
                        "pcg_iters_per_step": float(np.mean(lin)), "newton_iters_per_step": float(np.mean([c[2]["nr_iters"] for c in counts]))},
-            "phases_ms": {"sort(amortised)": float(phase_ms[0]), "push+deposit": push_ms, "density+rho": float(phase_ms[2]),
+            "phases_ms": {"sort(amortised)": float(phase_ms[0]), "push+removal": push_ms, "deposit+rho": float(phase_ms[2]),
                           "poisson": float(phase_ms[3]), "ef": float(phase_ms[4])},
-            "roofline": {"bound": "hbm", "kernel": "k_push<ABSORB,FUSE> (push + trilinear gather + kill + fused deposit)",
+            "roofline": {"bound": "hbm", "kernel": "k_push<ABSORB%s> (Species::advance: gather + leapfrog + kill flags%s)" % (
+                             (",FUSE", " + fused deposit") if args.fuse else ("", "")),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_particle": PUSH_BYTES,
-                         "note": "duration = CUDA-event time of the push phase (kernel + removal bookkeeping)"},
+                         "peak_source": peak_src, "bytes_per_particle": PUSH_BYTES, "kernel_ms": k_ms,
+                         "particles_per_launch": pushed_local / args.steps,
+                         "note": "duration = CUDA events around the kernel launch on its stream, mean over the timed steps"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

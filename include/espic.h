@@ -84,6 +84,9 @@ enum { ESPIC_PUSH_FUSE_DEPOSIT = 1,   /* also scatter the survivors: the next es
        ESPIC_PUSH_NO_COMPACT = 2,     /* leave dead particles in place with mpw=0 (kill-mask tests) */
        ESPIC_PUSH_FIXED_POINT = 256 };/* with FUSE_DEPOSIT: accumulate in int64 fixed point */
 int espic_push(espic_ctx *ctx, int sp, double dt, int wall_mode, int flags);
+/* device time (ms) of the push kernel of the most recent espic_push alone -- CUDA events on the launching stream,
+ * without the removal bookkeeping that follows it (bench.py's roofline numerator) */
+int espic_last_push_ms(espic_ctx *ctx, double *ms);
 
 /* Species::computeNumberDensity (Species.cpp:51-62): den = scatter(mpw) / node_vol. */
 enum { ESPIC_DEPOSIT_FP64 = 0,     /* FP64 atomics (order-dependent rounding) */

@@ -24,7 +24,9 @@ extern "C" const char *espic_last_error(void) { return g_err; }
 int espic_ensure(void **ptr, long long *cap, long long need, size_t elem, cudaStream_t s)
 {
     if (need <= *cap && *ptr) return 0;
-    long long ncap = std::max<long long>(need, 16);
+    // grow geometrically: sizes such as "number of particles removed this step" drift from call to call, and a
+    // cudaFree/cudaMalloc pair synchronises the whole device (measured: up to 250 ms with tens of GB resident)
+    long long ncap = std::max<long long>(2 * need, 1024);
     if (*ptr) { CK(cudaStreamSynchronize(s)); CK(cudaFree(*ptr)); *ptr = nullptr; }
     CK(cudaMalloc(ptr, (size_t)ncap * elem));
     *cap = ncap;
@@ -155,6 +157,7 @@ extern "C" void espic_destroy(espic_ctx *c)
     cudaFree(c->dead_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
     cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
     for (int q = 0; q < 8; q++) cudaFree(c->sv[q]);
+    if (c->push_ev0) { cudaEventDestroy(c->push_ev0); cudaEventDestroy(c->push_ev1); }
     cudaFreeHost(c->hpin);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -48,6 +48,9 @@ struct espic_ctx {
     int nsp = 0;
     Species sp[ESPIC_MAX_SPECIES];
     long long launches = 0;
+    // CUDA events around the most recent k_push launch on `stream` (bench.py's roofline numerator uses the kernel alone)
+    cudaEvent_t push_ev0 = nullptr, push_ev1 = nullptr;
+    bool push_timed = false;
     // scratch
     uint32_t *dead_words = nullptr; long long dead_words_cap = 0;
     uint32_t *scan_pre = nullptr;  long long scan_cap = 0;

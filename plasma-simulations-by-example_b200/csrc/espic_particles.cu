@@ -2,6 +2,8 @@
 // diagnostics as sm_100a kernels over SoA particle arrays (include/espic.h).
 #include "espic_internal.cuh"
 #include <algorithm>
+#include <chrono>
+#include <stdlib.h>
 #include <math.h>
 
 #define SP_CHECK(c, sp) do { if ((sp) < 0 || (sp) >= (c)->nsp) { espic_set_error("bad species id %d", (sp)); return -1; } } while (0)
@@ -295,7 +297,7 @@ __device__ __forceinline__ bool push_one(const MeshC &m, const double *__restric
 }
 
 template <int WALL, bool FUSE, int MODE>
-__global__ void __launch_bounds__(256) k_push(MeshC m, const double *__restrict__ ef4,
+__global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const double *__restrict__ ef4,
                                               double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                                               double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
                                               double *__restrict__ pmpw, long long n, double s, double dt,
@@ -421,6 +423,8 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     int r;
     if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw, c->stream))) return r; }
     const unsigned grid = nblk((n + 1) / 2, 256);
+    if (!c->push_ev0) { CK(cudaEventCreate(&c->push_ev0)); CK(cudaEventCreate(&c->push_ev1)); }
+    CK(cudaEventRecord(c->push_ev0, c->stream));
 #define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale
     if (wall_mode == ESPIC_WALL_ABSORB) {
         if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
@@ -433,21 +437,28 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     } else { espic_set_error("espic_push: bad wall mode %d", wall_mode); return -1; }
 #undef PUSH_ARGS
     LAUNCH_CHECK(c);
+    CK(cudaEventRecord(c->push_ev1, c->stream));
+    c->push_timed = true;
     if (fuse) s.acc_fresh = true;
     if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) return 0;
 
     // count the dead, then remove them in the reference's order
+    static const bool trace = getenv("ESPIC_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_a = trace ? now() : 0;
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
     k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, c->cell_cnt);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
     unsigned long long *h = (unsigned long long *)c->hpin;
     CK(cudaMemcpyAsync(h, c->dscal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    const double t_b = trace ? now() : 0;
     CK(cudaStreamSynchronize(c->stream));
+    const double t_c = trace ? now() : 0;
     const long long D = (long long)h[0];
     if (D == 0) return 0;
     if (D < n) {
-        if ((r = ensure_buf(&c->lists, &c->lists_cap, 2 * D, c->stream))) return r;
+        if ((r = ensure_buf(&c->lists, &c->lists_cap, std::max(2 * D, n / 64), c->stream))) return r;
         CK(cudaMemsetAsync(c->lists, 0xff, (size_t)D * sizeof(long long), c->stream));
         k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
                                                            c->lists, c->lists + D);
@@ -456,6 +467,21 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
         LAUNCH_CHECK(c);
     }
     s.np = n - D;
+    if (trace) fprintf(stderr, "[espic_push] n=%lld D=%lld host ms: enqueue %.3f  wait-for-count %.3f  removal-enqueue %.3f\n",
+                       n, D, t_b - t_a, t_c - t_b, now() - t_c);
+    return 0;
+}
+
+// device time of the most recent k_push launch alone (no removal bookkeeping), from events on the launching stream
+extern "C" int espic_last_push_ms(espic_ctx *c, double *ms)
+{
+    *ms = 0;
+    if (!c->push_timed) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->push_ev1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->push_ev0, c->push_ev1));
+    *ms = f;
     return 0;
 }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "espic_create", "espic_destroy", "espic_last_error", "espic_set_stream", "espic_sync", "espic_kernel_launches",
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
-    "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_deposit",
+    "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
     "espic_sort_by_cell", "espic_inject_cold_beam", "espic_species_diag", "espic_update_average",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
@@ -82,6 +82,7 @@ def load():
     L.espic_species_download.restype = C.c_longlong
     L.espic_species_add.argtypes = [vp, C.c_int, comp, C.c_longlong, C.c_double, C.POINTER(C.c_longlong)]
     L.espic_push.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
+    L.espic_last_push_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.espic_deposit.argtypes = [vp, C.c_int, C.c_int]
     L.espic_sort_by_cell.argtypes = [vp, C.c_int]
     L.espic_inject_cold_beam.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
@@ -241,6 +242,11 @@ class Engine:
 
     def push(self, sp, dt, wall=WALL_ABSORB, flags=0):
         self._ck(self.L.espic_push(self.h, sp, dt, wall, flags))
+
+    def last_push_ms(self):
+        ms = C.c_double(0)
+        self._ck(self.L.espic_last_push_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def deposit(self, sp, mode=DEPOSIT_FP64):
         self._ck(self.L.espic_deposit(self.h, sp, mode))
