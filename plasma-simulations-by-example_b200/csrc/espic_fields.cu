@@ -799,6 +799,7 @@ void espic_mg_destroy(espic_ctx *c)
     if (!c->mg) return;
     MgHierarchy *H = static_cast<MgHierarchy *>(c->mg);
     cudaFree(H->pool);
+    cudaFree(H->nbmask);
     delete H;
     c->mg = nullptr;
 }

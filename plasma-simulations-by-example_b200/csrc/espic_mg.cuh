@@ -33,11 +33,29 @@ struct MgHierarchy {
     MgLevel L[MG_MAX_LEVELS];
     long long geom_version = -1;
     double *pool = nullptr;   // one allocation for all coarse-level arrays
+    uint8_t *nbmask = nullptr; // per fine node: bit b set iff neighbour b (-x,+x,-y,+y,-z,+z) is an unknown (REG)
+    // |R after the first Newton update| / |R before it| seen in the previous solve: the first linear solve of the next
+    // solve is stopped a decade below the nonlinear residual it cannot remove anyway (inexact Newton forcing term)
+    double newton_ratio = 0;
 };
 
 static MgHierarchy *g_mg_of(espic_ctx *c);   // stored in the context (espic_internal.cuh: void *mg)
 
 // ---- setup kernels -------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_mg_nbmask(StencilC s, const uint8_t *__restrict__ type, uint8_t *__restrict__ nbmask)
+{
+    long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= s.nn) return;
+    unsigned m = 0;
+    if (type[u] == NT_REG) {         // REG nodes are interior: all six neighbours exist
+        m |= (type[u - 1] == NT_REG) << 0;    m |= (type[u + 1] == NT_REG) << 1;
+        m |= (type[u - s.sj] == NT_REG) << 2; m |= (type[u + s.sj] == NT_REG) << 3;
+        m |= (type[u - s.sk] == NT_REG) << 4; m |= (type[u + s.sk] == NT_REG) << 5;
+        m |= 64;                              // bit 6: the node itself is an unknown
+    }
+    nbmask[u] = (uint8_t)m;
+}
 
 // links of level 1 from the fine node types: a fine link (u, u+e) exists iff both ends are REG; its weight is g = 1/dh^2
 __global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const uint8_t *__restrict__ type, MgLevel C)
@@ -297,30 +315,49 @@ __device__ __forceinline__ void mg_up(const MgLevel &F, const MgLevel &C, const 
     }
 }
 
-// Up pass on the fine level: z = (x0 + P e) + w D^-1 (r - K (x0 + P e)), the prolongated iterate formed on the fly (the
-// level-1 array e is 1/8 of a fine vector and stays in L1/L2); returns this thread's share of r.z
+// Up pass on the fine level: z = (x0 + P e) + w D^-1 (r - K (x0 + P e)).  One thread per level-1 node: it holds the
+// correction of its own aggregate and of the six neighbouring aggregates in registers and walks its 8 children, so the
+// prolongated iterate never touches memory; nbmask replaces six mask loads per node.  Returns the thread's share of r.z
 __device__ __forceinline__ double mg_up0(const StencilC &s, const double *__restrict__ r, const double *__restrict__ diag,
-                                         const double *__restrict__ minv, const double *__restrict__ x0, const MgLevel &C,
+                                         const double *__restrict__ minv, const double *__restrict__ x0,
+                                         const uint8_t *__restrict__ nbmask, const MgLevel &C,
                                          const double *__restrict__ e, double *__restrict__ z, long long t0, long long stride)
 {
     double acc = 0;
-    for (long long u = t0; u < s.nn; u += stride) {
-        const double mi = minv[u];
-        double zu = 0;
-        if (mi != 0) {
-            const int i = (int)(u % s.ni), j = (int)((u / s.ni) % s.nj), k = (int)(u / s.sk);
-            auto val = [&](long long v, int vi, int vj, int vk) {
-                // the fine links are implicit constants: neighbours outside the REG set must be masked explicitly
-                return minv[v] != 0 ? x0[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)] : 0.0;
-            };
-            const double off = s.gdx2 * (val(u - 1, i - 1, j, k) + val(u + 1, i + 1, j, k)) +
-                               s.gdy2 * (val(u - s.sj, i, j - 1, k) + val(u + s.sj, i, j + 1, k)) +
-                               s.gdz2 * (val(u - s.sk, i, j, k - 1) + val(u + s.sk, i, j, k + 1));
-            const double xu = x0[u] + e[((long long)(k >> 1) * C.nj + (j >> 1)) * C.ni + (i >> 1)];
-            zu = xu + MG_OMEGA * mi * (r[u] - (diag[u] * xu - off));
-            acc += r[u] * zu;
-        }
-        z[u] = zu;
+    const long long csj = C.ni, csk = (long long)C.ni * C.nj;
+    for (long long I = t0; I < C.nn; I += stride) {
+        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / csk);
+        const double e0 = e[I];
+        // corrections of the neighbouring aggregates: [axis][side]
+        const double exm = ci > 0 ? e[I - 1] : 0.0, exp_ = ci + 1 < C.ni ? e[I + 1] : 0.0;
+        const double eym = cj > 0 ? e[I - csj] : 0.0, eyp = cj + 1 < C.nj ? e[I + csj] : 0.0;
+        const double ezm = ck > 0 ? e[I - csk] : 0.0, ezp = ck + 1 < C.nk ? e[I + csk] : 0.0;
+#pragma unroll
+        for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+            for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+                for (int di = 0; di < 2; di++) {
+                    const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                    if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
+                    const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
+                    const unsigned m = nbmask[u];
+                    double zu = 0;
+                    if (m & 64u) {
+                        // the neighbour on the inner side of the aggregate shares e0, the outer one takes the next aggregate's
+                        const double vxm = (m & 1u) ? x0[u - 1] + (di ? e0 : exm) : 0.0;
+                        const double vxp = (m & 2u) ? x0[u + 1] + (di ? exp_ : e0) : 0.0;
+                        const double vym = (m & 4u) ? x0[u - s.sj] + (dj ? e0 : eym) : 0.0;
+                        const double vyp = (m & 8u) ? x0[u + s.sj] + (dj ? eyp : e0) : 0.0;
+                        const double vzm = (m & 16u) ? x0[u - s.sk] + (dk ? e0 : ezm) : 0.0;
+                        const double vzp = (m & 32u) ? x0[u + s.sk] + (dk ? ezp : e0) : 0.0;
+                        const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
+                        const double xu = x0[u] + e0;
+                        zu = xu + MG_OMEGA * minv[u] * (r[u] - (diag[u] * xu - off));
+                        acc += r[u] * zu;
+                    }
+                    z[u] = zu;
+                }
     }
     return acc;
 }
@@ -330,11 +367,13 @@ struct MgPcgArgs {
     int nlev;
     int coarse_sweeps;            // Jacobi sweeps on the coarsest level (even)
     MgLevel L[MG_MAX_LEVELS];     // L[0]: diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
+    const uint8_t *nbmask;
     double *delta, *r, *z, *d0, *d1, *q;     // r enters holding the right-hand side; d0/d1 ping-pong search directions
     double *part;
     int max_it;
     double tol;
-    double *out;                  // converged, iterations, l2
+    double rel_tol;               // stop at l2 < max(tol, rel_tol * l2_start)
+    double *out;                  // converged, iterations, l2, l2 at the start
     unsigned long long *prof;     // optional: nanoseconds per phase as seen by block 0 (ESPIC_MG_PROFILE=1), 8 slots
 };
 
@@ -399,10 +438,10 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, const MgPcgArg
         e = a.L[l].xn;
     }
     MG_TICK(3);
-    return mg_up0(a.s, a.r, L0.diag, L0.minv, L0.x, a.L[1], e, a.z, t0, stride);
+    return mg_up0(a.s, a.r, L0.diag, L0.minv, L0.x, a.nbmask, a.L[1], e, a.z, t0, stride);
 }
 
-__global__ void __launch_bounds__(512) k_mg_pcg(MgPcgArgs a)
+__global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
@@ -423,7 +462,9 @@ __global__ void __launch_bounds__(512) k_mg_pcg(MgPcgArgs a)
     if (threadIdx.x == 0) pC[blockIdx.x] = t;
     grid.sync();
     double l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
-    int it = 0, converged = l2 < a.tol;
+    const double l2_start = l2;
+    const double stop = fmax(a.tol, a.rel_tol * l2_start);
+    int it = 0, converged = l2 < stop;
     double rz = 0, beta = 0;
     double *d_old = a.d0, *d_new = a.d1;
     unsigned long long tick = mg_now();
@@ -475,9 +516,9 @@ __global__ void __launch_bounds__(512) k_mg_pcg(MgPcgArgs a)
         l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
         it++;
         double *tmp = d_old; d_old = d_new; d_new = tmp;
-        if (l2 < a.tol) converged = 1;
+        if (l2 < stop) converged = 1;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; a.out[3] = l2_start; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -487,6 +528,9 @@ static int mg_setup(espic_ctx *c, const StencilC &s)
     MgHierarchy *H = g_mg_of(c);
     if (H->geom_version == c->geom_version && H->nlev > 0) return 0;
     if (H->pool) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
+    if (!H->nbmask) CK(cudaMalloc(&H->nbmask, (size_t)s.nn));
+    k_mg_nbmask<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->nbmask);
+    LAUNCH_CHECK(c);
     // level dimensions: halve (rounding up) while every dimension stays >= 4 and the level is worth a barrier
     int ni = s.ni, nj = s.nj, nk = s.nk, nlev = 1;
     long long dims[MG_MAX_LEVELS][3] = {{ni, nj, nk}};
@@ -551,8 +595,9 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
     const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
     double *dout = reinterpret_cast<double *>(c->dscal + 24);
     double *dres = reinterpret_cast<double *>(c->dscal + 16);
-    double norm = 0;
+    double norm = 0, r0_norm = 0, lin_stop = 0;
     bool converged = false;
+    static const bool inexact = getenv("ESPIC_MG_EXACT_NEWTON") == nullptr;
     for (int it = 0; it < p->nr_max_it; it++) {
         info->nr_iters++;
         k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, diag0, p->phi0, p->Te0, p->n0,
@@ -565,12 +610,15 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
             LAUNCH_CHECK(c);
         }
         MgPcgArgs a;
-        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps;
+        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps; a.nbmask = H->nbmask;
         a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = diagJ; a.L[0].minv = minv; a.L[0].x = x0;
         a.delta = delta; a.r = R; a.z = z; a.d0 = d0; a.d1 = d1; a.q = q;
         a.part = part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
+        // Newton step 0 leaves a nonlinear residual of about newton_ratio * |R0| whatever the accuracy of its linear solve:
+        // solve it to a tenth of that; every later step (and a first step without history) is solved to tol.
+        a.rel_tol = (it == 0 && inexact) ? 0.1 * std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
         void *args[] = {&a};
         CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, 0, c->stream));
@@ -580,13 +628,19 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         k_sum_final<<<1, 256, 0, c->stream>>>(part, nb_res, dres);
         LAUNCH_CHECK(c);
         double *h = reinterpret_cast<double *>(c->hpin) + 24;
-        CK(cudaMemcpyAsync(h, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(h, dout, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         double sum;
         if ((r = read_scalar(c, dres, &sum))) return r;
         info->lin_iters += (long long)h[1];
         if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
         norm = sqrt(sum / (double)s.nn);
-        if (norm < p->nr_tol) { converged = true; break; }
+        if (it == 0) r0_norm = h[3];
+        if (it == 1 && r0_norm > 0) H->newton_ratio = h[3] / r0_norm;
+        lin_stop = (a.rel_tol > 0) ? std::max(p->tol, a.rel_tol * h[3]) : p->tol;
+        if (getenv("ESPIC_MG_PROFILE"))
+            fprintf(stderr, "[mg newton %d] |R| %.3e -> %.3e in %d its, |y| = %.3e\n", it, h[3], h[2], (int)h[1], norm);
+        // converged as the reference defines it (update below nr_tol) -- but only after a linear solve that went to tol
+        if (norm < p->nr_tol && lin_stop <= p->tol) { converged = true; break; }
     }
     for (int level = 0; level < 3; level++) {
         k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
