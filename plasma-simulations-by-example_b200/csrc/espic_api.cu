@@ -325,6 +325,7 @@ extern "C" int espic_species_upload(espic_ctx *c, int sp, const double *const co
     for (long long i = 0; i < n; i++) if (comp[6][i] > s.mpw_max) s.mpw_max = comp[6][i];
     s.np = base + n;
     s.acc_fresh = false;
+    s.pushes_since_sort = 1 << 20;       // arbitrary order
     return 0;
 }
 
@@ -341,6 +342,7 @@ extern "C" int espic_species_upload_device(espic_ctx *c, int sp, const double *c
     if (mpw_max > s.mpw_max) s.mpw_max = mpw_max;
     s.np = base + n;
     s.acc_fresh = false;
+    s.pushes_since_sort = 1 << 20;       // arbitrary order
     return 0;
 }
 

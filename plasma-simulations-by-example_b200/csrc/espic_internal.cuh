@@ -34,6 +34,7 @@ struct Species {
     int acc_mode = ESPIC_DEPOSIT_FP64;
     int acc_shift = 0;                 // fixed point: value * 2^shift
     double mpw_max = 0;                // upper bound of any mpw seen (fixed-point scale)
+    int pushes_since_sort = 1 << 20;   // how scrambled the cell order is: chooses the deposit kernel
 };
 
 struct espic_ctx {

@@ -7,7 +7,7 @@
 // CG, sqrt(sum y^2 / n) < nr_tol for Newton) and replaces only the preconditioner by one multigrid V(1,1) cycle:
 //   * coarsening by 2x2x2 aggregation of nodes, piecewise-constant prolongation P, restriction P^T, Galerkin coarse
 //     operators P^T K P -- for a 7-point stencil these are again 7-point stencils (diagonal + three link arrays);
-//   * damped-Jacobi smoothing (w = 0.8), one sweep before and one after the coarse correction; both are fused with the
+//   * damped-Jacobi smoothing (w = 0.9), one sweep before and one after the coarse correction; both are fused with the
 //     grid transfer (down pass: smooth from zero + residual + restriction; up pass: prolongation + smooth), so a
 //     level costs two passes and two grid-wide barriers per V-cycle;
 //   * a few Jacobi sweeps on the coarsest level.
@@ -16,7 +16,7 @@
 #pragma once
 
 #define MG_MAX_LEVELS 8
-#define MG_OMEGA 0.8
+#define MG_OMEGA 0.9
 #define MG_COARSE_SWEEPS 6
 #define MG_COARSEST_NODES 4096      // stop coarsening once a level is this small
 
