@@ -252,12 +252,13 @@ def main():
     ap.add_argument("--mesh", type=int, default=128)
     ap.add_argument("--solver", default="mg", choices=["pcg", "mg", "gs", "qn"],
                     help="pcg: Newton + Jacobi-PCG (the reference's preconditioner); mg: same with a multigrid V-cycle preconditioner")
-    ap.add_argument("--sort-every", type=int, default=5)
+    ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--fixed-point", action="store_true", help="bit-reproducible int64 deposition")
     ap.add_argument("--fuse", action="store_true", help="scatter inside the push kernel instead of the tiled deposit kernel")
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra QN-solver measurement")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
@@ -460,6 +461,38 @@ def main():
         e2e = {"value": pushed_e2e / (ms_e * 1e-3), "unit": "particle-pushes/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / args.steps}
 
+    # ---------------------------------------------------------------- the same step with ch9's own default field solver (QN)
+    variants = None
+    if not args.no_variants and args.solver != "qn":
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nq = max(3, min(args.steps, 5))
+        pushed_q = 0
+        v0.record()
+        for i in range(nq):
+            if args.sort_every > 0 and i % args.sort_every == 0:
+                e.sort_by_cell(sp)
+            pushed_q += e.count(sp)
+            e.push(sp, DT, es.WALL_ABSORB, pflags)
+            e.deposit(sp, dmode)
+            e.compute_charge_density()
+            e.solve(es.SOLVE_QN, 1, 1.0)
+            e.compute_ef()
+        v1.record()
+        torch.cuda.synchronize()
+        ms_q = v0.elapsed_time(v1)
+        if world > 1:
+            tq = torch.tensor([ms_q, pushed_q], dtype=torch.float64, device=dev)
+            mq = tq.clone()
+            dist.all_reduce(mq, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tq, op=dist.ReduceOp.SUM)
+            ms_q, pushed_q = float(mq[0].item()), float(tq[1].item())
+        variants = {"qn": {"value": pushed_q / (ms_q * 1e-3), "unit": "particle-pushes/s", "ms_per_step": ms_q / nq, "steps": nq,
+                           "note": "same workload with SolverType::QN, the solver ch9/Main.cpp ships with (ch9/Main.cpp:40); "
+                                   "run after the timed region, not part of `value`"}}
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -489,6 +522,7 @@ def main():
                          "particles_per_launch": pushed_local / args.steps,
                          "note": "duration = CUDA events around the kernel launch on its stream, mean over the timed steps"},
             "cpu_baseline": cpu,
+            "solver_variants": variants,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

@@ -388,6 +388,8 @@ __device__ __forceinline__ unsigned long long mg_now()
 
 #define MG_BLOCK0_MAX 0        // a coarsest level this small is swept by block 0 alone (block barriers instead of grid barriers)
 
+#define MG_SMEM (2 * MG_BLOCK0_MAX * (int)sizeof(double))   // 0: the single-block variant measured slower (49 vs 32 us) than grid-wide sweeps
+
 // z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.
 __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, const MgPcgArgs &a, long long t0, long long stride,
                                             unsigned long long &tick)
@@ -409,15 +411,39 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, const MgPcgArg
     // coarsest level: Jacobi sweeps from zero; the result ends in x (even sweep count)
     const MgLevel &Lc = a.L[a.nlev - 1];
     if (Lc.nn <= MG_BLOCK0_MAX) {
+        // a coarsest level this small is swept by block 0 alone, the iterate living in shared memory: block barriers
+        // (tens of cycles) instead of one grid-wide barrier (~4.5 us) per sweep; everybody else waits once
         if (blockIdx.x == 0) {
-            for (long long u = threadIdx.x; u < Lc.nn; u += blockDim.x) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
+            extern __shared__ double mg_sm[];
+            double *xa = mg_sm, *xb = mg_sm + MG_BLOCK0_MAX;
+            const int nn = (int)Lc.nn;
+            const int sj = Lc.ni, sk = Lc.ni * Lc.nj;
+            for (int u = threadIdx.x; u < nn; u += blockDim.x) xa[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
             __syncthreads();
-            for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
-                mg_jacobi(Lc, Lc.x, Lc.xn, threadIdx.x, blockDim.x);
-                __syncthreads();
-                mg_jacobi(Lc, Lc.xn, Lc.x, threadIdx.x, blockDim.x);
+            for (int sweep = 0; sweep < a.coarse_sweeps; sweep++) {
+                const double *in = (sweep & 1) ? xb : xa;
+                double *out = (sweep & 1) ? xa : xb;
+                for (int u = threadIdx.x; u < nn; u += blockDim.x) {
+                    const double mi = Lc.minv[u];
+                    double o = 0;
+                    if (mi != 0) {
+                        const int i = u % Lc.ni, j = (u / Lc.ni) % Lc.nj, k = u / sk;
+                        double off = 0;
+                        if (i > 0) off += Lc.cx[u - 1] * in[u - 1];
+                        if (i + 1 < Lc.ni) off += Lc.cx[u] * in[u + 1];
+                        if (j > 0) off += Lc.cy[u - sj] * in[u - sj];
+                        if (j + 1 < Lc.nj) off += Lc.cy[u] * in[u + sj];
+                        if (k > 0) off += Lc.cz[u - sk] * in[u - sk];
+                        if (k + 1 < Lc.nk) off += Lc.cz[u] * in[u + sk];
+                        const double xu = in[u];
+                        o = xu + MG_OMEGA * mi * (Lc.b[u] - (Lc.diag[u] * xu - off));
+                    }
+                    out[u] = o;
+                }
                 __syncthreads();
             }
+            const double *res = (a.coarse_sweeps & 1) ? xb : xa;
+            for (int u = threadIdx.x; u < nn; u += blockDim.x) Lc.x[u] = res[u];
         }
         grid.sync();
     } else {
@@ -587,7 +613,12 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         c->diag0_version = c->geom_version;
     }
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, 0));
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        CK(cudaFuncSetAttribute(k_mg_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+        smem_opt_in = true;
+    }
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, MG_SMEM));
     if (bps < 1) { espic_set_error("k_mg_pcg cannot be made resident"); return -1; }
     long long want = (s.nn + 511) / 512;
     int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
@@ -621,7 +652,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         a.rel_tol = (it == 0 && inexact) ? 0.1 * std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
         void *args[] = {&a};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, 0, c->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, MG_SMEM, c->stream));
         LAUNCH_CHECK(c);
         k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
         LAUNCH_CHECK(c);
