@@ -329,10 +329,10 @@ def main():
     e.compute_ef()
 
     def pic_step(i, count):
-        if args.sort_every > 0 and i % args.sort_every == 0:
-            e.sort_by_cell(sp)
         e.push(sp, DT, es.WALL_ABSORB, pflags)
         n_live = e.count(sp)
+        if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
+            e.sort_by_cell(sp)       # between push and deposit: the scatter sees perfectly ordered particles
         e.deposit(sp, dmode)
         e.compute_charge_density()
         inf = e.solve(solver, max_it, tol)
@@ -368,14 +368,14 @@ def main():
     for i in range(args.steps):
         pe = phase_ev[i]
         pe[0].record()
-        if args.sort_every > 0 and (i + args.warmup) % args.sort_every == 0:
-            e.sort_by_cell(sp)
-        pe[1].record()
         n_before = e.count(sp)
         e.push(sp, DT, es.WALL_ABSORB, pflags)
-        pe[2].record()
+        pe[1].record()
         kernel_ms.append(e.last_push_ms())       # CUDA events around the k_push launch itself, on the launching stream
         n_live = e.count(sp)
+        if args.sort_every > 0 and (i + args.warmup) % args.sort_every == 0 and not args.fuse:
+            e.sort_by_cell(sp)
+        pe[2].record()
         e.deposit(sp, dmode)
         e.compute_charge_density()
         pe[3].record()
@@ -406,7 +406,8 @@ def main():
         pushed = float(pushed_local)
     value = pushed / (ms * 1e-3)
     log("timed region done: %.2f ms/step" % (ms / args.steps))
-    ph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in phase_ev])     # sort, push, dep+rho, solve, ef
+    ph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in phase_ev])     # push, sort, dep+rho, solve, ef
+    ph = ph[:, [1, 0, 2, 3, 4]]
     phase_ms = ph.mean(axis=0)
 
     # dominant kernel: k_push (Species::advance).  Its duration is the mean over the timed steps of the CUDA-event time of
@@ -435,6 +436,7 @@ def main():
         pb = [p.numpy() for p in pinned]
         h2d = 7 * 8 * n_inj
         d2h = 0
+        phi_pinned = torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy()    # where Output::fields would read phi
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -446,7 +448,7 @@ def main():
             pushed_e2e += e.count(sp)
             pic_step(i + 1, None)
             dg = e.diag(sp)                                    # device -> host: the step's diagnostics ...
-            phi_host = e.field(es.PHI)                         # ... and the potential (what Output::fields reads)
+            phi_host = e.field(es.PHI, out=phi_pinned)         # ... and the potential (what Output::fields reads)
             d2h = dg.nbytes + phi_host.nbytes + 8
         e1.record()
         torch.cuda.synchronize()
@@ -472,10 +474,10 @@ def main():
         pushed_q = 0
         v0.record()
         for i in range(nq):
-            if args.sort_every > 0 and i % args.sort_every == 0:
-                e.sort_by_cell(sp)
             pushed_q += e.count(sp)
             e.push(sp, DT, es.WALL_ABSORB, pflags)
+            if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
+                e.sort_by_cell(sp)
             e.deposit(sp, dmode)
             e.compute_charge_density()
             e.solve(es.SOLVE_QN, 1, 1.0)

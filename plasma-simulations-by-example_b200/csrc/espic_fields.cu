@@ -152,17 +152,17 @@ __global__ void k_qn(long long nn, const int32_t *__restrict__ object_id, const 
 
 // ---- nonlinear / linear SOR, red-black ordering ------------------------------------------------------------
 
-// One colour of PotentialSolver::solveGS (PotentialSolver.cpp:352-384) / ch2 solve (ch2/PotentialSolver.cpp:27-41).
-// Same node update as the reference; the sweep visits nodes in red-black instead of lexicographic order.
+// grid_total (defined below) sums per-block partials identically in every block
+__device__ __forceinline__ double grid_total(const double *part, int n, double *sh, double *bcast);
+
+// One node update of PotentialSolver::solveGS (PotentialSolver.cpp:352-384) / ch2 solve (ch2/PotentialSolver.cpp:27-41).
+// Same formula as the reference; the sweep visits nodes in red-black instead of lexicographic order.
 template <bool BOLTZ>
-__global__ void __launch_bounds__(256) k_sor_color(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
-                                                   double *__restrict__ phi, int color, double phi0, double Te0, double n0)
+__device__ __forceinline__ void sor_node(const StencilC &s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                                         double *__restrict__ phi, long long t, int color, double phi0, double Te0, double n0)
 {
-    // thread -> (pair index along i, j, k): only nodes with (i+j+k)&1 == color
+    // t -> (pair index along i, j, k): only nodes with (i+j+k)&1 == color
     const int hi = (s.ni + 1) >> 1;
-    long long t = blockIdx.x * 256ll + threadIdx.x;
-    long long total = (long long)hi * s.nj * s.nk;
-    if (t >= total) return;
     int ih = (int)(t % hi), j = (int)((t / hi) % s.nj), k = (int)(t / ((long long)hi * s.nj));
     int i = 2 * ih + ((j + k + color) & 1);
     if (i >= s.ni) return;
@@ -183,33 +183,72 @@ __global__ void __launch_bounds__(256) k_sor_color(StencilC s, const uint8_t *__
     phi[u] = p + 1.4 * (phi_new - p);
 }
 
-// residual of PotentialSolver.cpp:389-421 (ch2: ch2/PotentialSolver.cpp:46-58), per-block partial sums of R^2
+// squared residual of PotentialSolver.cpp:389-421 (ch2: ch2/PotentialSolver.cpp:46-58) at node u
 template <bool BOLTZ>
-__global__ void __launch_bounds__(256) k_sor_residual(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
-                                                      const double *__restrict__ phi, double phi0, double Te0, double n0,
-                                                      double *__restrict__ part)
+__device__ __forceinline__ double sor_residual2(const StencilC &s, const uint8_t *__restrict__ type, const double *__restrict__ rho,
+                                                const double *__restrict__ phi, long long u, double phi0, double Te0, double n0)
 {
-    __shared__ double sh[32];
-    double sum = 0;
-    for (long long u = blockIdx.x * 256ll + threadIdx.x; u < s.nn; u += (long long)gridDim.x * 256) {
-        int ty = type[u];
-        if (ty == NT_DIRICHLET) continue;
-        double R;
-        double p = phi[u];
-        if (ty != NT_REG) R = p - phi[nbr_of(s, u, ty)];
-        else {
-            double src;
-            if (BOLTZ) {
-                double ne = n0 * exp((p - phi0) / Te0);
-                src = (rho[u] - C_QE * ne) / C_EPS_0;
-            } else src = rho[u] / C_EPS_0;
-            R = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (phi[u - 1] + phi[u + 1]) +
-                s.gdy2 * (phi[u - s.sj] + phi[u + s.sj]) + s.gdz2 * (phi[u - s.sk] + phi[u + s.sk]);
-        }
-        sum += R * R;
+    int ty = type[u];
+    if (ty == NT_DIRICHLET) return 0.0;
+    double R;
+    double p = phi[u];
+    if (ty != NT_REG) R = p - phi[nbr_of(s, u, ty)];
+    else {
+        double src;
+        if (BOLTZ) {
+            double ne = n0 * exp((p - phi0) / Te0);
+            src = (rho[u] - C_QE * ne) / C_EPS_0;
+        } else src = rho[u] / C_EPS_0;
+        R = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (phi[u - 1] + phi[u + 1]) +
+            s.gdy2 * (phi[u - s.sj] + phi[u + s.sj]) + s.gdz2 * (phi[u - s.sk] + phi[u + s.sk]);
     }
-    double t = block_sum(sum, sh);
-    if (threadIdx.x == 0) part[blockIdx.x] = t;
+    return R * R;
+}
+
+struct SorArgs {
+    StencilC s;
+    const uint8_t *type;
+    const double *rho;
+    double *phi;
+    double phi0, Te0, n0;
+    int max_it;
+    double tol;
+    double *part;       // gridDim partial sums
+    double *out;        // converged, sweeps, L2
+};
+
+// The whole SOR solve as ONE persistent cooperative kernel: two colour passes per sweep separated by grid barriers, the
+// residual every 25 sweeps (including sweep 0, like the reference) reduced and tested on the device.  The shipped
+// 21x21x41 mesh needs thousands of sweeps of ~18 k nodes per solve: kernel-launch latency, not bandwidth, is the cost.
+template <bool BOLTZ>
+__global__ void __launch_bounds__(256) k_sor(SorArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    __shared__ double bc;
+    const StencilC &s = a.s;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long half = (long long)((s.ni + 1) >> 1) * s.nj * s.nk;
+    double L2 = 0;
+    int it = 0, converged = 0;
+    for (it = 0; it < a.max_it; it++) {
+        for (int color = 0; color < 2; color++) {
+            for (long long t = t0; t < half; t += stride) sor_node<BOLTZ>(s, a.type, a.rho, a.phi, t, color, a.phi0, a.Te0, a.n0);
+            grid.sync();
+        }
+        if (it % 25 == 0) {
+            double sum = 0;
+            for (long long u = t0; u < s.nn; u += stride) sum += sor_residual2<BOLTZ>(s, a.type, a.rho, a.phi, u, a.phi0, a.Te0, a.n0);
+            double t = block_sum(sum, sh);
+            if (threadIdx.x == 0) a.part[blockIdx.x] = t;
+            grid.sync();
+            L2 = sqrt(grid_total(a.part, gridDim.x, sh, &bc) / ((double)s.ni * s.nj * s.nk));
+            if (L2 < a.tol) { converged = 1; it++; break; }      // identical in every block: grid_total is deterministic
+            grid.sync();                                         // the partials may be overwritten only after everyone has read them
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = L2; }
 }
 
 static int solve_sor(espic_ctx *c, const espic_solve_params *p, bool box, espic_solve_info *info)
@@ -217,33 +256,29 @@ static int solve_sor(espic_ctx *c, const espic_solve_params *p, bool box, espic_
     int r;
     if ((r = ensure_node_types(c, box ? 1 : 0))) return r;
     StencilC s = make_stencil(c->m);
-    const int nb_res = std::min<long long>(nblk(s.nn, 256), 4 * c->sm_count);
-    if ((r = ensure_buf(&c->red, &c->red_cap, nb_res, c->stream))) return r;
     const long long half = (long long)((s.ni + 1) >> 1) * s.nj * s.nk;
-    double *dres = reinterpret_cast<double *>(c->dscal + 16);
-    double L2 = 0;
-    bool converged = false;
-    long long it = 0;
-    for (it = 0; it < p->max_it; it++) {
-        for (int color = 0; color < 2; color++) {
-            if (box) k_sor_color<false><<<nblk(half, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, color, 0, 1, 0);
-            else k_sor_color<true><<<nblk(half, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, color, p->phi0, p->Te0, p->n0);
-            LAUNCH_CHECK(c);
-        }
-        if (it % 25 == 0) {
-            if (box) k_sor_residual<false><<<nb_res, 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, 0, 1, 0, c->red);
-            else k_sor_residual<true><<<nb_res, 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, p->phi0, p->Te0, p->n0, c->red);
-            LAUNCH_CHECK(c);
-            k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb_res, dres);
-            LAUNCH_CHECK(c);
-            double sum;
-            if ((r = read_scalar(c, dres, &sum))) return r;
-            L2 = sqrt(sum / ((double)s.ni * s.nj * s.nk));
-            if (L2 < p->tol) { converged = true; it++; break; }
-        }
-    }
-    if (!converged) fprintf(stderr, "GS failed to converge, L2=%g\n", L2);
-    if (info) { info->converged = converged; info->gs_iters = it; info->residual = L2; }
+    int bps = 0;
+    if (box) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sor<false>, 256, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sor<true>, 256, 0));
+    if (bps < 1) { espic_set_error("k_sor cannot be made resident"); return -1; }
+    int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>((half + 255) / 256, 1));
+    if (grid > 4096) grid = 4096;
+    if ((r = ensure_buf(&c->red, &c->red_cap, 8192, c->stream))) return r;
+    double *dout = reinterpret_cast<double *>(c->dscal + 24);
+    SorArgs a;
+    a.s = s; a.type = c->node_type; a.rho = c->rho; a.phi = c->phi;
+    a.phi0 = box ? 0 : p->phi0; a.Te0 = box ? 1 : p->Te0; a.n0 = box ? 0 : p->n0;
+    a.max_it = p->max_it; a.tol = p->tol; a.part = c->red; a.out = dout;
+    void *args[] = {&a};
+    if (box) CK(cudaLaunchCooperativeKernel((void *)k_sor<false>, dim3(grid), dim3(256), args, 0, c->stream));
+    else CK(cudaLaunchCooperativeKernel((void *)k_sor<true>, dim3(grid), dim3(256), args, 0, c->stream));
+    LAUNCH_CHECK(c);
+    double *h = reinterpret_cast<double *>(c->hpin) + 24;
+    CK(cudaMemcpyAsync(h, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const bool converged = h[0] != 0.0;
+    if (!converged) fprintf(stderr, "GS failed to converge, L2=%g\n", h[2]);
+    if (info) { info->converged = converged; info->gs_iters = (long long)h[1]; info->residual = h[2]; }
     return 0;
 }
 

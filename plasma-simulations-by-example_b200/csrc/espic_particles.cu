@@ -629,9 +629,9 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
         if (r) return r;
         if (s.np > 0) {
             const double scale = ldexp(1.0, s.acc_shift);
-            // right after a cell sort runs of equal cells are long and the plain warp merge is the cheaper kernel
-            // (2.0 vs 3.6 ms at 2e8 particles); once the order has decayed the tile-grouping kernel wins (3.8 vs 5-7 ms)
-            const bool ordered = s.pushes_since_sort <= 1;
+            // directly after a cell sort (no push in between) runs of equal cells are long and the plain warp merge is the
+            // cheaper kernel (2.0 vs 3.6 ms at 2e8 particles); once the order has decayed the tile-grouping kernel wins (3.8 vs 4-7 ms)
+            const bool ordered = s.pushes_since_sort == 0;
             if (mode == ESPIC_DEPOSIT_FP64) {
                 if (ordered) k_deposit<ESPIC_DEPOSIT_FP64><<<nblk((s.np + 1) / 2, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
                 else k_deposit_tile<ESPIC_DEPOSIT_FP64><<<nblk(s.np, DT_TILE), DT_THREADS, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);

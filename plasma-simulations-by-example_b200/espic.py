@@ -167,11 +167,12 @@ class Engine:
     def add_inlet(self):
         self._ck(self.L.espic_add_inlet(self.h))
 
-    def field(self, which, sp=0):
-        if which == OBJECT_ID:
-            out = np.zeros(self.nn, dtype=np.int32)
-        else:
-            out = np.zeros(self.nn * (3 if which == EF else 1))
+    def field(self, which, sp=0, out=None):
+        """Download a node field.  `out`: optional preallocated (e.g. pinned) array to receive it."""
+        n, dt = self.nn * (3 if which == EF else 1), (np.int32 if which == OBJECT_ID else np.float64)
+        if out is None:
+            out = np.zeros(n, dtype=dt)
+        assert out.size == n and out.dtype == dt and out.flags["C_CONTIGUOUS"]
         self._ck(self.L.espic_field_download(self.h, which, sp, out.ctypes.data_as(C.c_void_p)))
         return out
 

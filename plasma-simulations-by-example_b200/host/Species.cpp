@@ -85,11 +85,14 @@ void Species::advance()
 {
     flush();
     world.fields_to_device();
-    if (sort_every > 0 && n_advance % sort_every == 0) sortByCell();
+    // with the periodic cell sort enabled the sort goes between push and scatter (the deposit then sees perfectly
+    // ordered particles); otherwise the scatter is fused into the push kernel
+    const bool sort_now = sort_every > 0 && n_advance % sort_every == 0;
     n_advance++;
     espic_host::check(espic_push(world.engine(), sp_id, world.getDt(), reflect ? ESPIC_WALL_REFLECT : ESPIC_WALL_ABSORB,
-                                 ESPIC_PUSH_FUSE_DEPOSIT),
+                                 sort_every > 0 ? 0 : ESPIC_PUSH_FUSE_DEPOSIT),
                       "espic_push");
+    if (sort_now) sortByCell();
     particles_changed();
 }
 
