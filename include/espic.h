@@ -117,8 +117,13 @@ enum { ESPIC_SOLVE_GS = 0,      /* PotentialSolver::solveGS, nonlinear Boltzmann
        ESPIC_SOLVE_GS_BOX = 3,  /* ch2 PotentialSolver::solve, linear SOR on interior nodes (ch2/PotentialSolver.cpp:11-67) */
        ESPIC_SOLVE_PCG_REF = 4, /* solveNRPCG + solvePCGLinear + solveGSLinear fallback restated operation for operation on the
                                    reference's non-symmetric 7-band matrix (:225-331,:433-461); inherits its breakdowns */
-       ESPIC_SOLVE_PCG_MG = 5 };/* ESPIC_SOLVE_PCG with the Jacobi preconditioner of solvePCGLinear (:304) replaced by one
+       ESPIC_SOLVE_PCG_MG = 5,  /* ESPIC_SOLVE_PCG with the Jacobi preconditioner of solvePCGLinear (:304) replaced by one
                                    aggregation-multigrid V-cycle: same Newton iteration, same equations, same stopping tests */
+       ESPIC_SOLVE_PCG_MG_SLAB = 6 };/* ESPIC_SOLVE_PCG_MG decomposed into one k-slab per rank (needs espic_comm_init; nk must be a
+                                   multiple of nranks * 2^(levels-1)): every rank computes its slab, boundary planes are stored
+                                   straight into the neighbours' memory (CUDA IPC over NVLink), dot products and barriers go
+                                   through peer memory too; replaces ch9/MPI updateGhosts + MPI_Allreduce
+                                   (ch9/MPI/src/PotentialSolver.cpp:137,189,425-479).  Every rank ends with the full phi. */
 
 typedef struct {
     int type;

@@ -15,6 +15,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -29,6 +30,7 @@ static int nccl_load()
     g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { espic_set_error("libnccl lacks required symbols"); return -1; }
     g_nccl.h = h;
@@ -88,6 +90,24 @@ int espic_comm_allreduce_acc(espic_ctx *c, Species &s)
     if (c->nranks <= 1 || !c->nccl) return 0;
     int dt = (s.acc_mode == ESPIC_DEPOSIT_FIXED) ? ncclInt64 : ncclFloat64;
     NCK(g_nccl.AllReduce(s.acc, s.acc, (size_t)c->m.nn, dt, ncclSum, (ncclComm_t)c->nccl, c->stream));
+    return 0;
+}
+
+// in-place all-gather of `count` doubles per rank: rank r's block sits at buf + r*count
+int espic_comm_allgather_doubles(espic_ctx *c, double *buf, size_t count)
+{
+    if (c->nranks <= 1 || !c->nccl) return 0;
+    if (!g_nccl.AllGather) { espic_set_error("libnccl lacks ncclAllGather"); return -1; }
+    NCK(g_nccl.AllGather(buf + (size_t)c->rank * count, buf, count, ncclFloat64, (ncclComm_t)c->nccl, c->stream));
+    return 0;
+}
+
+// in-place all-gather of `bytes` bytes per rank (device buffer)
+int espic_comm_allgather_bytes(espic_ctx *c, void *buf, size_t bytes)
+{
+    if (c->nranks <= 1 || !c->nccl) return 0;
+    if (!g_nccl.AllGather) { espic_set_error("libnccl lacks ncclAllGather"); return -1; }
+    NCK(g_nccl.AllGather((char *)buf + (size_t)c->rank * bytes, buf, bytes, 0 /* ncclInt8 */, (ncclComm_t)c->nccl, c->stream));
     return 0;
 }
 

@@ -831,6 +831,7 @@ static MgHierarchy *g_mg_of(espic_ctx *c)
 
 void espic_mg_destroy(espic_ctx *c)
 {
+    slab_destroy(c);
     if (!c->mg) return;
     MgHierarchy *H = static_cast<MgHierarchy *>(c->mg);
     cudaFree(H->pool);
@@ -856,6 +857,7 @@ extern "C" int espic_solve(espic_ctx *c, const espic_solve_params *p, espic_solv
         case ESPIC_SOLVE_PCG: r = solve_nrpcg_spd(c, p, &info); break;
         case ESPIC_SOLVE_PCG_REF: r = solve_nrpcg_ref(c, p, &info); break;
         case ESPIC_SOLVE_PCG_MG: r = solve_nrpcg_mg(c, p, &info); break;
+        case ESPIC_SOLVE_PCG_MG_SLAB: r = solve_nrpcg_mg_slab(c, p, &info); break;
         default: espic_set_error("espic_solve: unknown solver type %d", p->type); return -1;
     }
     if (info_out) *info_out = info;

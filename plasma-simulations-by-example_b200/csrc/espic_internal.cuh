@@ -68,6 +68,7 @@ struct espic_ctx {
     long long geom_version = 0, node_type_version = -1, diag0_version = -1;
     int sm_count = 148;
     void *mg = nullptr;            // MgHierarchy of the multigrid-preconditioned solver (espic_mg.cuh)
+    void *slab = nullptr;          // SlabState of the slab-decomposed multi-GPU variant (espic_mg.cuh)
     // comm
     void *nccl = nullptr; int rank = 0, nranks = 1;
 };
@@ -96,6 +97,8 @@ void espic_mg_destroy(espic_ctx *c);   // espic_fields.cu     // espic_api.cu: r
 void espic_comm_destroy(espic_ctx *c);
 int  espic_comm_max_double(espic_ctx *c, double *v);
 int  espic_comm_allreduce_acc(espic_ctx *c, Species &s);
+int  espic_comm_allgather_doubles(espic_ctx *c, double *buf, size_t count);
+int  espic_comm_allgather_bytes(espic_ctx *c, void *buf, size_t bytes);
 
 // ---- device helpers ---------------------------------------------------------------------------
 

@@ -142,9 +142,70 @@ __global__ void __launch_bounds__(256) k_mg_diag_from_level(MgLevel F, MgLevel C
     C.minv[I] = d > 0 ? 1.0 / d : 0.0;
 }
 
-// ---- device pieces of the V-cycle (grid-stride; the caller separates them with grid.sync()) ----------------------------
+// ---- who owns what: single GPU, or one k-slab per rank with peer-mapped pools -----------------------------------------
+// Every pass below is written once and instantiated twice.  `Own` tells a pass which flat index range of a level this
+// rank computes and what a store has to do besides writing locally:
+//   OwnAll   one GPU: the whole level, plain stores, grid-wide barrier.
+//   OwnSlab  rank r of R owns planes [k0,k1) of every level (boundaries are multiples of 2^(levels-1) fine planes, so an
+//            aggregate never straddles two ranks).  All solver vectors live at the same offset of a pool that every rank
+//            maps from every other rank (CUDA IPC over NVLink).  A value written on the first / last plane of the slab is
+//            ALSO stored straight into the lower / upper neighbour's copy (peer store fused into the producing pass: the
+//            halo exchange costs no extra pass and no NCCL call); dot-product partials are stored to every rank so all
+//            ranks add the same numbers in the same order; the barrier is a grid barrier plus one flag per peer.
+struct OwnAll {
+    static constexpr bool slab = false;
+    __device__ __forceinline__ long long lo(const MgLevel &L, int) const { return 0; }
+    __device__ __forceinline__ long long hi(const MgLevel &L, int) const { return L.nn; }
+    __device__ __forceinline__ void st(double *A, long long u, const MgLevel &, int, double v) const { A[u] = v; }
+    __device__ __forceinline__ int nparts(int nb) const { return nb; }
+    __device__ __forceinline__ void put_partial(double *base, int nb, double v) const { base[blockIdx.x] = v; }
+    __device__ __forceinline__ void barrier(cg::grid_group &grid) { grid.sync(); }
+};
 
-// off-diagonal part of K v at fine node u (level 0): neighbours outside the REG set carry minv == 0 and are skipped
+#define MG_MAX_RANKS 8
+struct OwnSlab {
+    static constexpr bool slab = true;
+    int rank, nranks;
+    int k0[MG_MAX_LEVELS], k1[MG_MAX_LEVELS];
+    long long peer[MG_MAX_RANKS];        // byte distance from an address in this rank's pool to the same address in rank p's pool
+    unsigned long long *flags;           // in the pool: flags[p] = last barrier epoch rank p has reached (written by rank p)
+    unsigned long long epoch;            // barriers passed so far (identical on every rank)
+    __device__ __forceinline__ long long lo(const MgLevel &L, int l) const { return (long long)k0[l] * L.ni * L.nj; }
+    __device__ __forceinline__ long long hi(const MgLevel &L, int l) const { return (long long)k1[l] * L.ni * L.nj; }
+    __device__ __forceinline__ void st(double *A, long long u, const MgLevel &L, int l, double v) const
+    {
+        A[u] = v;
+        const long long plane = (long long)L.ni * L.nj;
+        if (rank > 0 && u < lo(L, l) + plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank - 1]) = v;
+        if (rank + 1 < nranks && u >= hi(L, l) - plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank + 1]) = v;
+    }
+    __device__ __forceinline__ int nparts(int nb) const { return nb * nranks; }
+    __device__ __forceinline__ void put_partial(double *base, int nb, double v) const
+    {
+        for (int p = 0; p < nranks; p++)
+            *reinterpret_cast<double *>(reinterpret_cast<char *>(base + rank * nb + blockIdx.x) + peer[p]) = v;
+    }
+    __device__ __forceinline__ void barrier(cg::grid_group &grid)
+    {
+        __threadfence_system();          // this thread's peer stores are visible system-wide before anybody signals
+        grid.sync();
+        epoch++;
+        if (blockIdx.x == 0 && threadIdx.x < nranks) {
+            const int p = threadIdx.x;
+            volatile unsigned long long *theirs = reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[p]);
+            *theirs = epoch;             // tell rank p (and ourselves) that this rank has arrived
+            __threadfence_system();
+            volatile unsigned long long *mine = flags + p;
+            while (*mine < epoch) { }    // wait until rank p has arrived
+            __threadfence_system();
+        }
+        grid.sync();
+    }
+};
+
+// ---- device pieces of the V-cycle (grid-stride; the caller separates them with barriers) ---------------------------------
+
+// off-diagonal part of K v at fine node u (level 0): neighbours outside the REG set carry v == 0
 __device__ __forceinline__ double mg_offdiag0(const StencilC &s, const double *__restrict__ v, long long u)
 {
     return s.gdx2 * (v[u - 1] + v[u + 1]) + s.gdy2 * (v[u - s.sj] + v[u + s.sj]) + s.gdz2 * (v[u - s.sk] + v[u + s.sk]);
@@ -167,10 +228,12 @@ __device__ __forceinline__ double mg_offdiag(const MgLevel &L, int i, int j, int
 
 // Down pass from the fine level: x0 = w D^-1 r is already stored (written together with r); the residual r - K x0 is
 // summed over each aggregate -> b of level 1.  One thread per COARSE node (it owns the 8 children).
-__device__ __forceinline__ void mg_down0(const StencilC &s, const double *__restrict__ r, const double *__restrict__ diag,
-                                         const double *__restrict__ x0, const MgLevel &C, long long t0, long long stride)
+template <class Own>
+__device__ __forceinline__ void mg_down0(const Own &own, const StencilC &s, const double *__restrict__ r,
+                                         const double *__restrict__ diag, const double *__restrict__ x0, const MgLevel &C,
+                                         long long t0, long long stride)
 {
-    for (long long I = t0; I < C.nn; I += stride) {
+    for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
         const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
         double sum = 0;
         if (C.minv[I] != 0) {
@@ -188,7 +251,7 @@ __device__ __forceinline__ void mg_down0(const StencilC &s, const double *__rest
                         sum += r[u] - (dg * x0[u] - mg_offdiag0(s, x0, u));
                     }
         }
-        C.b[I] = sum;
+        own.st(C.b, I, C, 1, sum);
     }
 }
 
@@ -203,15 +266,17 @@ __device__ __forceinline__ double mg_sum8(double v)
     return v;
 }
 
-// Down pass between coarse levels F -> C: lane c of a group handles child c of coarse node I
-__device__ __forceinline__ void mg_down(const MgLevel &F, const MgLevel &C, long long t0, long long stride)
+// Down pass between coarse levels F (level lf) -> C: lane c of a group handles child c of coarse node I
+template <class Own>
+__device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf, const MgLevel &C, long long t0, long long stride)
 {
-    const long long total = C.nn * 8;
+    const long long first = own.lo(C, lf + 1), total = (own.hi(C, lf + 1) - first) * 8;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long I = w >> 3;
+        const long long I = first + (w >> 3);
         const int c = (int)(w & 7);
+        const bool live = w < total;
         double res = 0;
-        if (I < C.nn) {
+        if (live) {
             const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
             const int i = 2 * ci + (c & 1), j = 2 * cj + ((c >> 1) & 1), k = 2 * ck + (c >> 2);
             if (i < F.ni && j < F.nj && k < F.nk) {
@@ -223,11 +288,11 @@ __device__ __forceinline__ void mg_down(const MgLevel &F, const MgLevel &C, long
                     const double off = MG_OMEGA * mg_offdiag(F, i, j, k, u, [&](long long v) { return F.b[v] * F.minv[v]; });
                     res = F.b[u] - (F.diag[u] * xu - off);
                 }
-                F.x[u] = xu;
+                own.st(F.x, u, F, lf, xu);
             }
         }
         res = mg_sum8(res);
-        if (c == 0 && I < C.nn) C.b[I] = res;
+        if (c == 0 && live) own.st(C.b, I, C, lf + 1, res);
     }
 }
 
@@ -248,16 +313,18 @@ __device__ __forceinline__ double mg_term(const MgLevel &L, int c, int i, int j,
     }
 }
 
-// one damped-Jacobi sweep on level L: out = in + w D^-1 (b - K in); 8 lanes per node
-__device__ __forceinline__ void mg_jacobi(const MgLevel &L, const double *__restrict__ in, double *__restrict__ out,
-                                          long long t0, long long stride)
+// one damped-Jacobi sweep on level L (index l): out = in + w D^-1 (b - K in); 8 lanes per node
+template <class Own>
+__device__ __forceinline__ void mg_jacobi(const Own &own, const MgLevel &L, int l, const double *__restrict__ in,
+                                          double *__restrict__ out, long long t0, long long stride)
 {
-    const long long total = L.nn * 8;
+    const long long first = own.lo(L, l), total = (own.hi(L, l) - first) * 8;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long u = w >> 3;
+        const long long u = first + (w >> 3);
         const int c = (int)(w & 7);
+        const bool live = w < total;
         double term = 0, centre = 0, mi = 0;
-        if (u < L.nn) {
+        if (live) {
             mi = L.minv[u];
             if (mi != 0) {
                 const int i = (int)(u % L.ni), j = (int)((u / L.ni) % L.nj), k = (int)(u / ((long long)L.ni * L.nj));
@@ -266,69 +333,69 @@ __device__ __forceinline__ void mg_jacobi(const MgLevel &L, const double *__rest
         }
         const double tot = mg_sum8(term);
         centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        if (c == 0 && u < L.nn) out[u] = (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0;
+        if (c == 0 && live) own.st(out, u, L, l, (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0);
     }
 }
 
-// Up pass on a coarse level F with the correction e of the next coarser level C:
-//   xn = (x + P e) + w D^-1 (b - K (x + P e))           (8 lanes per node: one stencil term each)
-// fine != nullptr (F is level 1): the result is also handed down to the fine level, lane c writing child c:
-//   e0 = x0 + P xn  (0 on children that are not unknowns)
-__device__ __forceinline__ void mg_up(const MgLevel &F, const MgLevel &C, const double *__restrict__ e, long long t0, long long stride)
+// Up pass on a coarse level F (index lf) with the correction e of the next coarser level C:
+//   xn = (x + P e) + w D^-1 (b - K (x + P e))
+template <class Own>
+__device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, const MgLevel &C, const double *__restrict__ e,
+                                      long long t0, long long stride)
 {
-    if (F.nn * 2 > stride) {          // a big level: one thread per node keeps every lane busy
-        for (long long u = t0; u < F.nn; u += stride) {
+    const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
+    auto val = [&](long long v, int vi, int vj, int vk) {
+        // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
+        return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)];
+    };
+    if (count * 2 > stride) {          // a big level: one thread per node keeps every lane busy
+        for (long long u = first + t0; u < first + count; u += stride) {
             const double mi = F.minv[u];
             double out = 0;
             if (mi != 0) {
                 const int i = (int)(u % F.ni), j = (int)((u / F.ni) % F.nj), k = (int)(u / ((long long)F.ni * F.nj));
                 double centre = 0, tot = 0;
 #pragma unroll
-                for (int c = 0; c < 7; c++)
-                    tot += mg_term(F, c, i, j, k, u, [&](long long v, int vi, int vj, int vk) {
-                        return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)]; }, centre);
+                for (int c = 0; c < 7; c++) tot += mg_term(F, c, i, j, k, u, val, centre);
                 out = centre + MG_OMEGA * mi * tot;
             }
-            F.xn[u] = out;
+            own.st(F.xn, u, F, lf, out);
         }
         return;
     }
-    const long long total = F.nn * 8;
+    const long long total = count * 8;          // a small level: 8 lanes per node, one stencil term each
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long u = w >> 3;
+        const long long u = first + (w >> 3);
         const int c = (int)(w & 7);
+        const bool live = w < total;
         double term = 0, centre = 0, mi = 0;
-        int i = 0, j = 0, k = 0;
-        if (u < F.nn) {
+        if (live) {
             mi = F.minv[u];
-            i = (int)(u % F.ni); j = (int)((u / F.ni) % F.nj); k = (int)(u / ((long long)F.ni * F.nj));
             if (mi != 0) {
-                // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
-                term = mg_term(F, c, i, j, k, u, [&](long long v, int vi, int vj, int vk) {
-                    return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)]; }, centre);
+                const int i = (int)(u % F.ni), j = (int)((u / F.ni) % F.nj), k = (int)(u / ((long long)F.ni * F.nj));
+                term = mg_term(F, c, i, j, k, u, val, centre);
             }
         }
         const double tot = mg_sum8(term);
         centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        const double out = (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0;
-        if (c == 0 && u < F.nn) F.xn[u] = out;
+        if (c == 0 && live) own.st(F.xn, u, F, lf, (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0);
     }
 }
 
 // Up pass on the fine level: z = (x0 + P e) + w D^-1 (r - K (x0 + P e)).  One thread per level-1 node: it holds the
 // correction of its own aggregate and of the six neighbouring aggregates in registers and walks its 8 children, so the
 // prolongated iterate never touches memory; nbmask replaces six mask loads per node.  Returns the thread's share of r.z
-__device__ __forceinline__ double mg_up0(const StencilC &s, const double *__restrict__ r, const double *__restrict__ diag,
-                                         const double *__restrict__ minv, const double *__restrict__ x0,
-                                         const uint8_t *__restrict__ nbmask, const MgLevel &C,
+template <class Own>
+__device__ __forceinline__ double mg_up0(const Own &own, const StencilC &s, const MgLevel &L0, const double *__restrict__ r,
+                                         const double *__restrict__ diag, const double *__restrict__ minv,
+                                         const double *__restrict__ x0, const uint8_t *__restrict__ nbmask, const MgLevel &C,
                                          const double *__restrict__ e, double *__restrict__ z, long long t0, long long stride)
 {
     double acc = 0;
     const long long csj = C.ni, csk = (long long)C.ni * C.nj;
-    for (long long I = t0; I < C.nn; I += stride) {
+    for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
         const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / csk);
         const double e0 = e[I];
-        // corrections of the neighbouring aggregates: [axis][side]
         const double exm = ci > 0 ? e[I - 1] : 0.0, exp_ = ci + 1 < C.ni ? e[I + 1] : 0.0;
         const double eym = cj > 0 ? e[I - csj] : 0.0, eyp = cj + 1 < C.nj ? e[I + csj] : 0.0;
         const double ezm = ck > 0 ? e[I - csk] : 0.0, ezp = ck + 1 < C.nk ? e[I + csk] : 0.0;
@@ -356,7 +423,7 @@ __device__ __forceinline__ double mg_up0(const StencilC &s, const double *__rest
                         zu = xu + MG_OMEGA * minv[u] * (r[u] - (diag[u] * xu - off));
                         acc += r[u] * zu;
                     }
-                    z[u] = zu;
+                    own.st(z, u, L0, 0, zu);
                 }
     }
     return acc;
@@ -366,7 +433,7 @@ struct MgPcgArgs {
     StencilC s;
     int nlev;
     int coarse_sweeps;            // Jacobi sweeps on the coarsest level (even)
-    MgLevel L[MG_MAX_LEVELS];     // L[0]: diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
+    MgLevel L[MG_MAX_LEVELS];     // L[0]: dims, diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
     const uint8_t *nbmask;
     double *delta, *r, *z, *d0, *d1, *q;     // r enters holding the right-hand side; d0/d1 ping-pong search directions
     double *part;
@@ -386,108 +453,87 @@ __device__ __forceinline__ unsigned long long mg_now()
 // phase ids: 0 down0, 1 coarser down passes, 2 coarsest sweeps, 3 coarse up passes, 4 up0 + r.z, 5 d/q pass, 6 r pass
 #define MG_TICK(id) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = mg_now(); a.prof[id] += n_ - tick; tick = n_; } } while (0)
 
-#define MG_BLOCK0_MAX 0        // a coarsest level this small is swept by block 0 alone (block barriers instead of grid barriers)
-
-#define MG_SMEM (2 * MG_BLOCK0_MAX * (int)sizeof(double))   // 0: the single-block variant measured slower (49 vs 32 us) than grid-wide sweeps
-
 // z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.
-__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, const MgPcgArgs &a, long long t0, long long stride,
+template <class Own>
+__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, const MgPcgArgs &a, long long t0, long long stride,
                                             unsigned long long &tick)
 {
     const MgLevel &L0 = a.L[0];
     if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
         double acc = 0;
-        for (long long u = t0; u < a.s.nn; u += stride) { double zu = L0.minv[u] * a.r[u]; a.z[u] = zu; acc += a.r[u] * zu; }
+        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
+            double zu = L0.minv[u] * a.r[u];
+            own.st(a.z, u, L0, 0, zu);
+            acc += a.r[u] * zu;
+        }
         return acc;
     }
-    mg_down0(a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride);
-    grid.sync();
+    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride);
+    own.barrier(grid);
     MG_TICK(0);
     for (int l = 1; l + 1 < a.nlev; l++) {
-        mg_down(a.L[l], a.L[l + 1], t0, stride);
-        grid.sync();
+        mg_down(own, a.L[l], l, a.L[l + 1], t0, stride);
+        own.barrier(grid);
     }
     MG_TICK(1);
     // coarsest level: Jacobi sweeps from zero; the result ends in x (even sweep count)
-    const MgLevel &Lc = a.L[a.nlev - 1];
-    if (Lc.nn <= MG_BLOCK0_MAX) {
-        // a coarsest level this small is swept by block 0 alone, the iterate living in shared memory: block barriers
-        // (tens of cycles) instead of one grid-wide barrier (~4.5 us) per sweep; everybody else waits once
-        if (blockIdx.x == 0) {
-            extern __shared__ double mg_sm[];
-            double *xa = mg_sm, *xb = mg_sm + MG_BLOCK0_MAX;
-            const int nn = (int)Lc.nn;
-            const int sj = Lc.ni, sk = Lc.ni * Lc.nj;
-            for (int u = threadIdx.x; u < nn; u += blockDim.x) xa[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
-            __syncthreads();
-            for (int sweep = 0; sweep < a.coarse_sweeps; sweep++) {
-                const double *in = (sweep & 1) ? xb : xa;
-                double *out = (sweep & 1) ? xa : xb;
-                for (int u = threadIdx.x; u < nn; u += blockDim.x) {
-                    const double mi = Lc.minv[u];
-                    double o = 0;
-                    if (mi != 0) {
-                        const int i = u % Lc.ni, j = (u / Lc.ni) % Lc.nj, k = u / sk;
-                        double off = 0;
-                        if (i > 0) off += Lc.cx[u - 1] * in[u - 1];
-                        if (i + 1 < Lc.ni) off += Lc.cx[u] * in[u + 1];
-                        if (j > 0) off += Lc.cy[u - sj] * in[u - sj];
-                        if (j + 1 < Lc.nj) off += Lc.cy[u] * in[u + sj];
-                        if (k > 0) off += Lc.cz[u - sk] * in[u - sk];
-                        if (k + 1 < Lc.nk) off += Lc.cz[u] * in[u + sk];
-                        const double xu = in[u];
-                        o = xu + MG_OMEGA * mi * (Lc.b[u] - (Lc.diag[u] * xu - off));
-                    }
-                    out[u] = o;
-                }
-                __syncthreads();
-            }
-            const double *res = (a.coarse_sweeps & 1) ? xb : xa;
-            for (int u = threadIdx.x; u < nn; u += blockDim.x) Lc.x[u] = res[u];
-        }
-        grid.sync();
-    } else {
-        for (long long u = t0; u < Lc.nn; u += stride) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
-        grid.sync();
-        for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
-            mg_jacobi(Lc, Lc.x, Lc.xn, t0, stride);
-            grid.sync();
-            mg_jacobi(Lc, Lc.xn, Lc.x, t0, stride);
-            grid.sync();
-        }
+    const int lc = a.nlev - 1;
+    const MgLevel &Lc = a.L[lc];
+    for (long long u = own.lo(Lc, lc) + t0; u < own.hi(Lc, lc); u += stride) own.st(Lc.x, u, Lc, lc, MG_OMEGA * Lc.b[u] * Lc.minv[u]);
+    own.barrier(grid);
+    for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
+        mg_jacobi(own, Lc, lc, Lc.x, Lc.xn, t0, stride);
+        own.barrier(grid);
+        mg_jacobi(own, Lc, lc, Lc.xn, Lc.x, t0, stride);
+        own.barrier(grid);
     }
     MG_TICK(2);
     const double *e = Lc.x;
     for (int l = a.nlev - 2; l >= 1; l--) {
-        mg_up(a.L[l], a.L[l + 1], e, t0, stride);
-        grid.sync();
+        mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
+        own.barrier(grid);
         e = a.L[l].xn;
     }
     MG_TICK(3);
-    return mg_up0(a.s, a.r, L0.diag, L0.minv, L0.x, a.nbmask, a.L[1], e, a.z, t0, stride);
+    return mg_up0(own, a.s, L0, a.r, L0.diag, L0.minv, L0.x, a.nbmask, a.L[1], e, a.z, t0, stride);
 }
 
-__global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
+// Sum of per-block partials (of every rank in slab mode), computed redundantly by every block in the same fixed order
+template <class Own>
+__device__ __forceinline__ double mg_total(const Own &own, const double *part, int nb, double *sh, double *bcast)
+{
+    return grid_total(part, own.nparts(nb), sh, bcast);
+}
+
+template <class Own>
+__device__ __forceinline__ void mg_pcg_body(MgPcgArgs &a, Own &own)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     __shared__ double bc;
     const StencilC &s = a.s;
+    const MgLevel &L0 = a.L[0];
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int nb = gridDim.x;
-    double *pA = a.part, *pB = a.part + nb, *pC = a.part + 2 * nb;
-    const double *diag = a.L[0].diag;
+    const int np = own.nparts(nb);
+    double *pA = a.part, *pB = a.part + np, *pC = a.part + 2 * np;
+    const double *diag = L0.diag;
+    const double *minv = L0.minv;
+    double *x0 = L0.x;
+    const long long ulo = own.lo(L0, 0), uhi = own.hi(L0, 0);
 
-    const double *minv = a.L[0].minv;
-    double *x0 = a.L[0].x;
     // delta = 0: r = R; x0 = w D^-1 r; |r|
     double acc = 0;
-    for (long long u = t0; u < s.nn; u += stride) { double r = a.r[u]; x0[u] = MG_OMEGA * r * minv[u]; acc += r * r; }
+    for (long long u = ulo + t0; u < uhi; u += stride) {
+        const double r = a.r[u];
+        own.st(x0, u, L0, 0, MG_OMEGA * r * minv[u]);
+        acc += r * r;
+    }
     double t = block_sum(acc, sh);
-    if (threadIdx.x == 0) pC[blockIdx.x] = t;
-    grid.sync();
-    double l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+    if (threadIdx.x == 0) own.put_partial(pC, nb, t);
+    own.barrier(grid);
+    double l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / (double)s.nn);
     const double l2_start = l2;
     const double stop = fmax(a.tol, a.rel_tol * l2_start);
     int it = 0, converged = l2 < stop;
@@ -496,17 +542,17 @@ __global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
     unsigned long long tick = mg_now();
     while (!converged && it < a.max_it) {
         // z = M^-1 r ; rz' = r.z
-        acc = mg_vcycle(grid, a, t0, stride, tick);
+        acc = mg_vcycle(grid, own, a, t0, stride, tick);
         t = block_sum(acc, sh);
-        if (threadIdx.x == 0) pB[blockIdx.x] = t;
-        grid.sync();
+        if (threadIdx.x == 0) own.put_partial(pB, nb, t);
+        own.barrier(grid);
         MG_TICK(4);
-        const double rz_new = grid_total(pB, nb, sh, &bc);
+        const double rz_new = mg_total(own, pB, nb, sh, &bc);
         beta = (it == 0) ? 0.0 : rz_new / rz;
         rz = rz_new;
         // d = z + beta d (formed on the fly for the neighbours, written for this node) ; q = K d ; dq = d.q
         acc = 0;
-        for (long long u = t0; u < s.nn; u += stride) {
+        for (long long u = ulo + t0; u < uhi; u += stride) {
             const double dj = diag[u];
             double du = 0, qu = 0;
             if (dj != 0) {
@@ -518,28 +564,28 @@ __global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
                 qu = dj * du - off;
                 acc += du * qu;
             }
-            d_new[u] = du;
+            own.st(d_new, u, L0, 0, du);
             a.q[u] = qu;
         }
         t = block_sum(acc, sh);
-        if (threadIdx.x == 0) pA[blockIdx.x] = t;
-        grid.sync();
+        if (threadIdx.x == 0) own.put_partial(pA, nb, t);
+        own.barrier(grid);
         MG_TICK(5);
-        const double alpha = rz / grid_total(pA, nb, sh, &bc);
+        const double alpha = rz / mg_total(own, pA, nb, sh, &bc);
         // delta += alpha d ; r -= alpha q ; |r|
         acc = 0;
-        for (long long u = t0; u < s.nn; u += stride) {
+        for (long long u = ulo + t0; u < uhi; u += stride) {
             a.delta[u] = a.delta[u] + alpha * d_new[u];
             const double r = a.r[u] - alpha * a.q[u];
             a.r[u] = r;
-            x0[u] = MG_OMEGA * r * minv[u];          // pre-smoothed iterate of the next V-cycle
+            own.st(x0, u, L0, 0, MG_OMEGA * r * minv[u]);          // pre-smoothed iterate of the next V-cycle
             acc += r * r;
         }
         t = block_sum(acc, sh);
-        if (threadIdx.x == 0) pC[blockIdx.x] = t;
-        grid.sync();
+        if (threadIdx.x == 0) own.put_partial(pC, nb, t);
+        own.barrier(grid);
         MG_TICK(6);
-        l2 = sqrt(grid_total(pC, nb, sh, &bc) / (double)s.nn);
+        l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / (double)s.nn);
         it++;
         double *tmp = d_old; d_old = d_new; d_new = tmp;
         if (l2 < stop) converged = 1;
@@ -547,27 +593,59 @@ __global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
     if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; a.out[3] = l2_start; }
 }
 
+__global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
+{
+    OwnAll own;
+    mg_pcg_body(a, own);
+}
+
+// slab-decomposed variant: one of these kernels per rank, running concurrently, talking through peer memory only
+__global__ void __launch_bounds__(512, 2) k_mg_pcg_slab(MgPcgArgs a, OwnSlab own, unsigned long long *epoch_io)
+{
+    own.epoch = *epoch_io;
+    mg_pcg_body(a, own);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *epoch_io = own.epoch;
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 
-static int mg_setup(espic_ctx *c, const StencilC &s)
+// number of levels and their dimensions for an (ni,nj,nk) mesh
+static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3])
 {
-    MgHierarchy *H = g_mg_of(c);
-    if (H->geom_version == c->geom_version && H->nlev > 0) return 0;
-    if (H->pool) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
-    if (!H->nbmask) CK(cudaMalloc(&H->nbmask, (size_t)s.nn));
-    k_mg_nbmask<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->nbmask);
-    LAUNCH_CHECK(c);
-    // level dimensions: halve (rounding up) while every dimension stays >= 4 and the level is worth a barrier
     int ni = s.ni, nj = s.nj, nk = s.nk, nlev = 1;
-    long long dims[MG_MAX_LEVELS][3] = {{ni, nj, nk}};
+    dims[0][0] = ni; dims[0][1] = nj; dims[0][2] = nk;
+    // halve (rounding up) while every dimension stays > 4 and the level is worth a barrier
     while (nlev < MG_MAX_LEVELS && std::min(ni, std::min(nj, nk)) > 4 && (long long)ni * nj * nk > MG_COARSEST_NODES) {
         ni = (ni + 1) / 2; nj = (nj + 1) / 2; nk = (nk + 1) / 2;
         dims[nlev][0] = ni; dims[nlev][1] = nj; dims[nlev][2] = nk;
         nlev++;
     }
+    return nlev;
+}
+
+static long long mg_coarse_doubles(const StencilC &s)
+{
+    long long dims[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims);
     long long total = 0;
     for (int l = 1; l < nlev; l++) total += 8 * dims[l][0] * dims[l][1] * dims[l][2];
-    if (total > 0) CK(cudaMalloc(&H->pool, (size_t)total * sizeof(double)));
+    return total;
+}
+
+// (re)build the hierarchy H for the current geometry; coarse-level arrays go to `external` if given (slab mode: a pool
+// that the other ranks map), else to an allocation owned by H
+static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *external)
+{
+    if (H->geom_version == c->geom_version && H->nlev > 0) return 0;
+    if (H->pool && !external) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
+    if (!H->nbmask) CK(cudaMalloc(&H->nbmask, (size_t)s.nn));
+    k_mg_nbmask<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->nbmask);
+    LAUNCH_CHECK(c);
+    long long dims[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims);
+    const long long total = mg_coarse_doubles(s);
+    if (external) H->pool = external;
+    else if (total > 0) CK(cudaMalloc(&H->pool, (size_t)total * sizeof(double)));
     double *p = H->pool;
     for (int l = 0; l < nlev; l++) {
         MgLevel &L = H->L[l];
@@ -594,8 +672,8 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
     if ((r = ensure_node_types(c, 0))) return r;
     if ((r = ensure_sv(c, 8))) return r;
     StencilC s = make_stencil(c->m);
-    if ((r = mg_setup(c, s))) return r;
     MgHierarchy *H = g_mg_of(c);
+    if ((r = mg_setup(c, s, H, nullptr))) return r;
     double *diag0 = c->sv[0], *R = c->sv[1], *diagJ = c->sv[2], *minv = c->sv[3];
     double *delta = c->sv[4], *z = c->sv[5], *d0 = c->sv[6], *d1 = c->sv[7];
     // two more fine vectors (q, x0) + the partial sums live in the reduction scratch
@@ -613,12 +691,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         c->diag0_version = c->geom_version;
     }
     int bps = 0;
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
-        CK(cudaFuncSetAttribute(k_mg_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
-        smem_opt_in = true;
-    }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, MG_SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, 0));
     if (bps < 1) { espic_set_error("k_mg_pcg cannot be made resident"); return -1; }
     long long want = (s.nn + 511) / 512;
     int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
@@ -655,7 +728,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         a.rel_tol = (it == 0 && inexact) ? forcing * std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
         void *args[] = {&a};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, MG_SMEM, c->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, 0, c->stream));
         LAUNCH_CHECK(c);
         k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
         LAUNCH_CHECK(c);
@@ -692,5 +765,174 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
                 info->lin_iters, hp[0] * 1e-3 / info->lin_iters, hp[1] * 1e-3 / info->lin_iters, hp[2] * 1e-3 / info->lin_iters,
                 hp[3] * 1e-3 / info->lin_iters, hp[4] * 1e-3 / info->lin_iters, hp[5] * 1e-3 / info->lin_iters, hp[6] * 1e-3 / info->lin_iters);
     }
+    return 0;
+}
+
+
+// ====================================================================================================================
+// Slab-decomposed variant (ESPIC_SOLVE_PCG_MG_SLAB): one k-slab per rank, all traffic through peer-mapped memory
+// ====================================================================================================================
+
+struct SlabState {
+    bool ready = false, diag0_done = false;
+    long long geom_version = -1;
+    double *pool = nullptr;            // this rank's pool; every rank carves it identically
+    size_t pool_doubles = 0;
+    void *peer_base[MG_MAX_RANKS] = {nullptr};
+    // carved arrays (fine vectors), the coarse-level arrays, partial sums, flags
+    double *diag0, *R, *diagJ, *minv, *delta, *z, *d0, *d1, *q, *x0, *coarse, *part;
+    unsigned long long *flags, *epoch;
+    MgHierarchy H;
+    OwnSlab own;
+};
+
+static void slab_destroy(espic_ctx *c)
+{
+    if (!c->slab) return;
+    SlabState *S = static_cast<SlabState *>(c->slab);
+    for (int p = 0; p < MG_MAX_RANKS; p++)
+        if (S->peer_base[p] && p != c->rank) cudaIpcCloseMemHandle(S->peer_base[p]);
+    cudaFree(S->pool);
+    cudaFree(S->H.nbmask);
+    delete S;
+    c->slab = nullptr;
+}
+
+static int slab_setup(espic_ctx *c, const StencilC &s)
+{
+    if (c->nranks < 2 || !c->nccl) { espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB needs espic_comm_init with at least 2 ranks"); return -1; }
+    if (c->nranks > MG_MAX_RANKS) { espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB supports at most %d ranks", MG_MAX_RANKS); return -1; }
+    if (!c->slab) c->slab = new SlabState();
+    SlabState *S = static_cast<SlabState *>(c->slab);
+    if (S->ready && S->geom_version == c->geom_version) return 0;
+    if (S->ready) { espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: the geometry changed after the slab solver was set up"); return -1; }
+    long long dims[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims);
+    const int unit = 1 << (nlev - 1);                 // fine planes per coarsest plane
+    if (s.nk % (c->nranks * unit) != 0) {
+        espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: nk=%d must be a multiple of nranks*2^(levels-1) = %d", s.nk, c->nranks * unit);
+        return -1;
+    }
+    const int planes = s.nk / c->nranks;
+    // ---- pool: identical carving on every rank
+    const long long coarse = mg_coarse_doubles(s);
+    const long long nparts = 3ll * c->nranks * 4096;
+    S->pool_doubles = (size_t)(10 * s.nn + coarse + nparts + 64);
+    CK(cudaMalloc(&S->pool, S->pool_doubles * sizeof(double)));
+    CK(cudaMemsetAsync(S->pool, 0, S->pool_doubles * sizeof(double), c->stream));
+    double *p = S->pool;
+    S->diag0 = p; p += s.nn; S->R = p; p += s.nn; S->diagJ = p; p += s.nn; S->minv = p; p += s.nn; S->delta = p; p += s.nn;
+    S->z = p; p += s.nn; S->d0 = p; p += s.nn; S->d1 = p; p += s.nn; S->q = p; p += s.nn; S->x0 = p; p += s.nn;
+    S->coarse = p; p += coarse; S->part = p; p += nparts;
+    S->flags = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->epoch = reinterpret_cast<unsigned long long *>(p); p += 16;
+    // ---- exchange IPC handles through the NCCL communicator and map the peers
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, S->pool));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char *dh = nullptr;
+    CK(cudaMalloc(&dh, 64 * MG_MAX_RANKS));
+    CK(cudaMemcpyAsync(dh + 64 * c->rank, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    int r;
+    if ((r = espic_comm_allgather_bytes(c, dh, 64))) return r;
+    cudaIpcMemHandle_t all[MG_MAX_RANKS];
+    CK(cudaMemcpyAsync(all, dh, 64 * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(dh));
+    OwnSlab &own = S->own;
+    own.rank = c->rank; own.nranks = c->nranks; own.flags = S->flags; own.epoch = 0;
+    for (int q = 0; q < MG_MAX_RANKS; q++) own.peer[q] = 0;
+    for (int q = 0; q < c->nranks; q++) {
+        if (q == c->rank) { S->peer_base[q] = S->pool; continue; }
+        CK(cudaIpcOpenMemHandle(&S->peer_base[q], all[q], cudaIpcMemLazyEnablePeerAccess));
+        own.peer[q] = (long long)((char *)S->peer_base[q] - (char *)S->pool);
+    }
+    for (int l = 0; l < MG_MAX_LEVELS; l++) { own.k0[l] = 0; own.k1[l] = 0; }
+    for (int l = 0; l < nlev; l++) {
+        own.k0[l] = (c->rank * planes) >> l;
+        own.k1[l] = (c->rank + 1 == c->nranks) ? (int)dims[l][2] : (((c->rank + 1) * planes) >> l);
+    }
+    // ---- hierarchy inside the pool
+    if ((r = mg_setup(c, s, &S->H, S->coarse))) return r;
+    // every rank's pool must be zeroed and mapped before anybody stores into it: a collective on the stream + sync
+    if ((r = espic_comm_allgather_doubles(c, S->part, 1))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    S->geom_version = c->geom_version;
+    S->ready = true;
+    return 0;
+}
+
+static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info)
+{
+    int r;
+    if ((r = ensure_node_types(c, 0))) return r;
+    StencilC s = make_stencil(c->m);
+    if ((r = slab_setup(c, s))) return r;
+    SlabState *S = static_cast<SlabState *>(c->slab);
+    MgHierarchy *H = &S->H;
+    const long long slab_nn = (long long)(s.nk / c->nranks) * s.sk;
+    if (!S->diag0_done) {
+        k_spd_diag0<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, S->diag0);
+        LAUNCH_CHECK(c);
+        S->diag0_done = true;
+    }
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg_slab, 512, 0));
+    if (bps < 1) { espic_set_error("k_mg_pcg_slab cannot be made resident"); return -1; }
+    // the same grid on every rank (the partial-sum layout depends on it): all blocks the device can hold
+    int grid = bps * c->sm_count;
+    if (grid > 4096) grid = 4096;
+    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
+    if ((r = ensure_buf(&c->red, &c->red_cap, 8192, c->stream))) return r;
+    double *dout = reinterpret_cast<double *>(c->dscal + 24);
+    double *dres = reinterpret_cast<double *>(c->dscal + 16);
+    double norm = 0;
+    bool converged = false;
+    for (int it = 0; it < p->nr_max_it; it++) {
+        info->nr_iters++;
+        // the Newton linearisation and the Galerkin diagonals are computed by every rank for the whole mesh (cheap, pointwise)
+        k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, S->diag0, p->phi0, p->Te0, p->n0,
+                                                                S->R, S->diagJ, S->minv, S->delta);
+        LAUNCH_CHECK(c);
+        for (int l = 1; l < H->nlev; l++) {
+            if (l == 1) k_mg_diag_from_fine<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, S->diagJ, H->L[1]);
+            else k_mg_diag_from_level<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
+            LAUNCH_CHECK(c);
+        }
+        CK(cudaMemsetAsync(S->d0, 0, (size_t)s.nn * sizeof(double), c->stream));
+        MgPcgArgs a;
+        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = MG_COARSE_SWEEPS; a.nbmask = H->nbmask;
+        for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
+        a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;
+        a.delta = S->delta; a.r = S->R; a.z = S->z; a.d0 = S->d0; a.d1 = S->d1; a.q = S->q;
+        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.rel_tol = 0.0; a.out = dout; a.prof = nullptr;
+        // nobody may store into a neighbour's pool before that neighbour has finished preparing this Newton step
+        if ((r = espic_comm_allgather_doubles(c, S->part, 1))) return r;
+        OwnSlab own = S->own;
+        void *args[] = {&a, &own, &S->epoch};
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg_slab, dim3(grid), dim3(512), args, 0, c->stream));
+        LAUNCH_CHECK(c);
+        // every rank needs the whole update: gather the slabs of delta
+        if ((r = espic_comm_allgather_doubles(c, S->delta, (size_t)slab_nn))) return r;
+        k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, S->delta, c->phi, c->red);
+        LAUNCH_CHECK(c);
+        k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb_res, dres);
+        LAUNCH_CHECK(c);
+        double *h = reinterpret_cast<double *>(c->hpin) + 24;
+        CK(cudaMemcpyAsync(h, dout, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        double sum;
+        if ((r = read_scalar(c, dres, &sum))) return r;
+        info->lin_iters += (long long)h[1];
+        if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
+        norm = sqrt(sum / (double)s.nn);
+        if (norm < p->nr_tol) { converged = true; break; }
+    }
+    for (int level = 0; level < 3; level++) {
+        k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
+        LAUNCH_CHECK(c);
+    }
+    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
+    info->converged = converged;
+    info->residual = norm;
     return 0;
 }

@@ -15,7 +15,7 @@ PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE = range(7)
 WALL_ABSORB, WALL_REFLECT = 0, 1
 PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_FIXED_POINT = 1, 2, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
-SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF, SOLVE_PCG_MG = 0, 1, 2, 3, 4, 5
+SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF, SOLVE_PCG_MG, SOLVE_PCG_MG_SLAB = 0, 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
     "espic_create", "espic_destroy", "espic_last_error", "espic_set_stream", "espic_sync", "espic_kernel_launches",

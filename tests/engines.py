@@ -155,8 +155,9 @@ class GpuEngine:
                 e.compute_charge_density()
             elif op == "ef":
                 e.compute_ef()
-            elif op in ("solve", "solve_gs", "solve_pcg", "solve_qn", "solve_mg"):
+            elif op in ("solve", "solve_gs", "solve_pcg", "solve_qn", "solve_mg", "solve_mgslab"):
                 kind = {"solve": es.SOLVE_GS_BOX, "solve_gs": es.SOLVE_GS, "solve_qn": es.SOLVE_QN, "solve_mg": es.SOLVE_PCG_MG,
+                        "solve_mgslab": es.SOLVE_PCG_MG_SLAB,
                         "solve_pcg": es.SOLVE_PCG_REF if self.pcg_ref else es.SOLVE_PCG}[op]
                 self.info = e.solve(kind, int(c[1]) if len(c) > 1 else 1, float(c[2]) if len(c) > 2 else 1.0)
                 self.converged = float(self.info["converged"])

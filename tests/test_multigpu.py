@@ -67,3 +67,52 @@ def test_two_rank_deposit_matches_single_gpu(tmp_path):
     # 2 x 25001 vs 1 x 50001 may pick a different power of two, so compare through the exact integer sums
     assert np.abs(out["fixed"] - one_fixed).max() <= 2.0 ** -40 * np.abs(one_fixed).max()
     assert np.abs(out["fp64"] - one).max() <= 1e-12 * np.abs(one).max()
+
+
+def _slab_worker(rank, world, port, path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = np.load(path)
+    st = sf.state_from_dict(d, "in_")
+    g = GpuEngine(st, device=rank)           # every rank holds the full rho and phi (the solve is what is decomposed)
+    uid = [g.e.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.e.comm_init(rank, world, uid[0])
+    g.e.nr_tol = 1e-10
+    out = g.run(["solve_mgslab:20000:1e-9", "ef"])
+    np.savez(path + ".rank%d.npz" % rank, phi=out.phi, ef=out.ef, conv=out.diag[0], lin=g.info["lin_iters"], nr=g.info["nr_iters"])
+    dist.barrier()
+    g.e.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("dims,n0", [((32, 32, 64), 1e12), ((40, 24, 48), 1e11)])
+def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0):
+    """ESPIC_SOLVE_PCG_MG_SLAB on two ranks (k-slabs, halo planes and dot products through peer memory) must give the
+    potential of the single-GPU multigrid solve: same iteration counts, phi within 1e-10 (summation order of the dot
+    products differs), and both ranks must end with identical fields."""
+    import torch.multiprocessing as mp
+    n = 200000
+    w, sp = cases.sphere_case(seed=91, ni=dims[0], nj=dims[1], nk=dims[2], n=n, amp=0.0, mpw=n0 * 0.016 / n)
+    w.set_reference_values(0.0, 1.5, n0)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    w.solve_qn()
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    path = str(tmp_path / "in.npz")
+    np.savez(path, **sf.state_to_dict(st, "in_"))
+    mp.spawn(_slab_worker, args=(2, 29700 + os.getpid() % 1000, path), nprocs=2, join=True)
+    r0, r1 = np.load(path + ".rank0.npz"), np.load(path + ".rank1.npz")
+    one = GpuEngine(st)
+    one.e.nr_tol = 1e-10
+    ref = one.run(["solve_mg:20000:1e-9", "ef"])
+    assert r0["conv"] == 1.0 and r1["conv"] == 1.0 and ref.diag[0] == 1.0
+    assert np.array_equal(r0["phi"], r1["phi"]), "both ranks must hold the same potential, bit for bit"
+    assert int(r0["nr"]) == one.info["nr_iters"]
+    assert abs(int(r0["lin"]) - one.info["lin_iters"]) <= 2
+    scale = np.abs(ref.phi).max()
+    assert np.abs(r0["phi"] - ref.phi).max() <= 1e-10 * scale
+    assert np.abs(r0["ef"] - ref.ef).max() <= 1e-9 * np.abs(ref.ef).max()
