@@ -250,8 +250,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=float, default=2e8, help="macroparticles per GPU")
     ap.add_argument("--mesh", type=int, default=128)
-    ap.add_argument("--solver", default="mg", choices=["pcg", "mg", "gs", "qn"],
-                    help="pcg: Newton + Jacobi-PCG (the reference's preconditioner); mg: same with a multigrid V-cycle preconditioner")
+    ap.add_argument("--solver", default="mg", choices=["pcg", "mg", "mgslab", "gs", "qn"],
+                    help="pcg: Newton + Jacobi-PCG (the reference's preconditioner); mg: same with a multigrid V-cycle "
+                         "preconditioner, solved by every rank; mgslab: the multigrid solve decomposed into one k-slab per rank")
     ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--fixed-point", action="store_true", help="bit-reproducible int64 deposition")
     ap.add_argument("--fuse", action="store_true", help="scatter inside the push kernel instead of the tiled deposit kernel")
@@ -289,7 +290,9 @@ def main():
     n_total = n_local * (world if args.impl == "ours" else args.gpus)
     box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
     mpw = N0 * box_vol / n_total
-    solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[args.solver]
+    solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "mgslab": es.SOLVE_PCG_MG_SLAB, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[args.solver]
+    if args.solver == "mgslab" and world == 1:
+        solver = es.SOLVE_PCG_MG
     max_it, tol = 5000, 1e-4
     workload = "sphere-%d^3-mesh-%.0e-ions-per-gpu-%s" % (n_mesh, n_local, args.solver)
 
@@ -512,7 +515,8 @@ def main():
             "config": {"workload": workload, "mesh": [n_mesh] * 3, "particles_per_gpu": n_local, "solver": args.solver,
                        "solver_tol": tol, "dt": DT, "sort_every": args.sort_every,
                        "deposit": "fixed-point int64" if args.fixed_point else "fp64 atomics",
-                       "parallelism": "particle-index sharding x%d, NCCL density all-reduce, replicated field solve" % world,
+                       "parallelism": "particle-index sharding x%d, NCCL density all-reduce, %s" % (
+                           world, "k-slab multigrid Poisson solve over peer memory" if (args.solver == "mgslab" and world > 1) else "replicated field solve"),
                        "l2": "inputs (%.1f GB of particles per GPU) are larger than L2" % (56 * n_local / 1e9),
                        "pcg_iters_per_step": float(np.mean(lin)), "newton_iters_per_step": float(np.mean([c[2]["nr_iters"] for c in counts]))},
             "phases_ms": {"sort(amortised)": float(phase_ms[0]), "push+removal": push_ms, "deposit+rho": float(phase_ms[2]),

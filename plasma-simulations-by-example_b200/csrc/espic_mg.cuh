@@ -185,21 +185,39 @@ struct OwnSlab {
         for (int p = 0; p < nranks; p++)
             *reinterpret_cast<double *>(reinterpret_cast<char *>(base + rank * nb + blockIdx.x) + peer[p]) = v;
     }
-    __device__ __forceinline__ void barrier(cg::grid_group &grid)
+    // All blocks of all ranks.  Local arrival (one atomic per block on a cumulative counter), then block 0 exchanges one
+    // flag with every peer over NVLink, then it releases the local blocks: one local round trip plus one remote one.
+    // Ordering: every block's thread 0 issues a system-scope fence after the block barrier and before arriving, block 0
+    // fences again (system scope) between seeing all arrivals and signalling the peers, so a peer that sees the flag also
+    // sees every halo value and partial sum stored before this barrier.
+    unsigned long long *arrive, *release;     // in the local pool
+    __device__ __forceinline__ void barrier(cg::grid_group &)
     {
-        __threadfence_system();          // this thread's peer stores are visible system-wide before anybody signals
-        grid.sync();
+        __syncthreads();
         epoch++;
-        if (blockIdx.x == 0 && threadIdx.x < nranks) {
-            const int p = threadIdx.x;
-            volatile unsigned long long *theirs = reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[p]);
-            *theirs = epoch;             // tell rank p (and ourselves) that this rank has arrived
+        if (threadIdx.x == 0) {
             __threadfence_system();
-            volatile unsigned long long *mine = flags + p;
-            while (*mine < epoch) { }    // wait until rank p has arrived
-            __threadfence_system();
+            volatile unsigned long long *rel = release;
+            if (blockIdx.x == 0) {
+                volatile unsigned long long *arr = arrive;
+                const unsigned long long want = (unsigned long long)(gridDim.x - 1) * epoch;
+                while (*arr < want) { }
+                __threadfence_system();
+                for (int p = 0; p < nranks; p++)
+                    *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[p]) = epoch;
+                for (int p = 0; p < nranks; p++) {
+                    volatile unsigned long long *mine = flags + p;
+                    while (*mine < epoch) { }
+                }
+                __threadfence_system();
+                *rel = epoch;
+            } else {
+                atomicAdd(arrive, 1ull);
+                while (*rel < epoch) { }
+            }
+            __threadfence();
         }
-        grid.sync();
+        __syncthreads();
     }
 };
 
@@ -781,7 +799,7 @@ struct SlabState {
     void *peer_base[MG_MAX_RANKS] = {nullptr};
     // carved arrays (fine vectors), the coarse-level arrays, partial sums, flags
     double *diag0, *R, *diagJ, *minv, *delta, *z, *d0, *d1, *q, *x0, *coarse, *part;
-    unsigned long long *flags, *epoch;
+    unsigned long long *flags, *epoch, *arrive, *release;
     MgHierarchy H;
     OwnSlab own;
 };
@@ -817,7 +835,7 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     // ---- pool: identical carving on every rank
     const long long coarse = mg_coarse_doubles(s);
     const long long nparts = 3ll * c->nranks * 4096;
-    S->pool_doubles = (size_t)(10 * s.nn + coarse + nparts + 64);
+    S->pool_doubles = (size_t)(10 * s.nn + coarse + nparts + 128);
     CK(cudaMalloc(&S->pool, S->pool_doubles * sizeof(double)));
     CK(cudaMemsetAsync(S->pool, 0, S->pool_doubles * sizeof(double), c->stream));
     double *p = S->pool;
@@ -826,6 +844,8 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     S->coarse = p; p += coarse; S->part = p; p += nparts;
     S->flags = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->epoch = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->arrive = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->release = reinterpret_cast<unsigned long long *>(p); p += 16;
     // ---- exchange IPC handles through the NCCL communicator and map the peers
     cudaIpcMemHandle_t mine;
     CK(cudaIpcGetMemHandle(&mine, S->pool));
@@ -841,6 +861,7 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     CK(cudaFree(dh));
     OwnSlab &own = S->own;
     own.rank = c->rank; own.nranks = c->nranks; own.flags = S->flags; own.epoch = 0;
+    own.arrive = S->arrive; own.release = S->release;
     for (int q = 0; q < MG_MAX_RANKS; q++) own.peer[q] = 0;
     for (int q = 0; q < c->nranks; q++) {
         if (q == c->rank) { S->peer_base[q] = S->pool; continue; }
@@ -886,7 +907,7 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
     if ((r = ensure_buf(&c->red, &c->red_cap, 8192, c->stream))) return r;
     double *dout = reinterpret_cast<double *>(c->dscal + 24);
     double *dres = reinterpret_cast<double *>(c->dscal + 16);
-    double norm = 0;
+    double norm = 0, r0_norm = 0;
     bool converged = false;
     for (int it = 0; it < p->nr_max_it; it++) {
         info->nr_iters++;
@@ -905,7 +926,9 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;
         a.delta = S->delta; a.r = S->R; a.z = S->z; a.d0 = S->d0; a.d1 = S->d1; a.q = S->q;
-        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.rel_tol = 0.0; a.out = dout; a.prof = nullptr;
+        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout; a.prof = nullptr;
+        // same inexact-Newton forcing as the single-GPU solver (identical on every rank: it derives from all-reduced norms)
+        a.rel_tol = (it == 0 && getenv("ESPIC_MG_EXACT_NEWTON") == nullptr) ? std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         // nobody may store into a neighbour's pool before that neighbour has finished preparing this Newton step
         if ((r = espic_comm_allgather_doubles(c, S->part, 1))) return r;
         OwnSlab own = S->own;
@@ -925,7 +948,10 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         info->lin_iters += (long long)h[1];
         if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
         norm = sqrt(sum / (double)s.nn);
-        if (norm < p->nr_tol) { converged = true; break; }
+        if (it == 0) r0_norm = h[3];
+        if (it == 1 && r0_norm > 0) H->newton_ratio = h[3] / r0_norm;
+        const double lin_stop = (a.rel_tol > 0) ? std::max(p->tol, a.rel_tol * h[3]) : p->tol;
+        if (norm < p->nr_tol && lin_stop <= p->tol) { converged = true; break; }
     }
     for (int level = 0; level < 3; level++) {
         k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
