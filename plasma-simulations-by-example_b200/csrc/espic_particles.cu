@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restri
 #define DT_THREADS 256
 #define DT_PER 4
 #define DT_TILE (DT_THREADS * DT_PER)
-#define DT_SLOTS 256                      // hash table entries; a tile that touches more cells spills to direct REDs
+#define DT_SLOTS 1024                     // hash table entries (a tile of 1024 particles cannot touch more cells)
+#define DT_SLOT_BITS 10
 #define DT_EMPTY 0xffffffffu
 
 template <int MODE>
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
 {
     typedef typename AccVal<MODE>::T T;
     __shared__ double sx[DT_TILE], sy[DT_TILE], sz[DT_TILE], sw[DT_TILE];
-    __shared__ uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS], hoff[DT_SLOTS];
+    __shared__ uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS];     // hcnt: slot counts, then (after the scan) slot offsets
     __shared__ uint16_t pslot[DT_TILE], order[DT_TILE];
     __shared__ uint32_t wsum[DT_THREADS / 32];
     __shared__ uint32_t n_sorted;
@@ -280,8 +281,8 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         const long long pf = base + (long long)ahead * DT_TILE;
         if (ahead > 0 && pf + DT_TILE <= n) l2_prefetch((tid == 0 ? x : tid == 1 ? y : tid == 2 ? z : mpw) + pf, DT_TILE * 8);
     }
-    hkey[tid] = DT_EMPTY;                 // DT_SLOTS == DT_THREADS
-    hcnt[tid] = 0;
+#pragma unroll
+    for (int t = tid; t < DT_SLOTS; t += DT_THREADS) { hkey[t] = DT_EMPTY; hcnt[t] = 0; }
     __syncthreads();
     // ---- 1. load, hash, count
 #pragma unroll
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
             const int leader = __ffs(peers) - 1;
             uint32_t slot = 0xffffu;
             if (key != DT_EMPTY && lane == leader) {
-                uint32_t h = (key * 2654435761u) >> 24;          // DT_SLOTS = 2^8
+                uint32_t h = (key * 2654435761u) >> (32 - DT_SLOT_BITS);
                 slot = 0xfffeu;
                 for (int probe = 0; probe < DT_SLOTS; probe++) {
                     const uint32_t old = atomicCAS(&hkey[h], DT_EMPTY, key);
@@ -322,10 +323,13 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         }
     }
     __syncthreads();
-    // ---- 2. exclusive scan of the slot counts (one entry per thread), then place the particle ids
+    // ---- 2. exclusive scan of the slot counts (DT_SLOTS / DT_THREADS consecutive entries per thread), then place the ids
     {
-        const uint32_t cnt = hcnt[tid];
-        uint32_t inc = cnt;
+        constexpr int PER = DT_SLOTS / DT_THREADS;
+        uint32_t cnt[PER], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) { cnt[q] = hcnt[tid * PER + q]; tsum += cnt[q]; }
+        uint32_t inc = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -333,10 +337,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         }
         if (lane == 31) wsum[tid >> 5] = inc;
         __syncthreads();
-        uint32_t woff = 0;
-        for (int w = 0; w < (tid >> 5); w++) woff += wsum[w];
-        hoff[tid] = woff + inc - cnt;
-        if (tid == DT_THREADS - 1) n_sorted = woff + inc;
+        uint32_t run = inc - tsum;
+        for (int w = 0; w < (tid >> 5); w++) run += wsum[w];
+#pragma unroll
+        for (int q = 0; q < PER; q++) { hcnt[tid * PER + q] = run; run += cnt[q]; }
+        if (tid == DT_THREADS - 1) n_sorted = run;
     }
     __syncthreads();
 #pragma unroll
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
         const int leader = __ffs(peers) - 1;
         uint32_t at = 0;
-        if (slot < DT_SLOTS && lane == leader) at = atomicAdd(&hoff[slot], (uint32_t)__popc(peers));
+        if (slot < DT_SLOTS && lane == leader) at = atomicAdd(&hcnt[slot], (uint32_t)__popc(peers));
         at = __shfl_sync(0xffffffffu, at, leader);
         if (slot < DT_SLOTS) order[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)p;
         else if (slot == 0xfffeu) {                        // table overflow: this particle deposits on its own
