@@ -674,8 +674,25 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
             LAUNCH_CHECK(c);
         }
     }
+    static const bool trace_ar = getenv("ESPIC_TRACE") != nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;
+    if (trace_ar && c->nranks > 1) {
+        cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+        cudaEventRecord(t0, c->stream);
+        double dummy = 0;
+        espic_comm_max_double(c, &dummy);              // a tiny collective first: absorbs the skew between the ranks
+        cudaEventRecord(t1, c->stream);
+    }
     int r = espic_comm_allreduce_acc(c, s);
     if (r) return r;
+    if (t0) {
+        cudaEventRecord(t2, c->stream);
+        cudaEventSynchronize(t2);
+        float skew = 0, ar = 0;
+        cudaEventElapsedTime(&skew, t0, t1); cudaEventElapsedTime(&ar, t1, t2);
+        fprintf(stderr, "[espic_deposit rank %d] wait for peers %.3f ms, all-reduce of %lld doubles %.3f ms\n", c->rank, skew, c->m.nn, ar);
+        cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    }
     const double inv_scale = ldexp(1.0, -s.acc_shift);
     if (mode == ESPIC_DEPOSIT_FP64)
         k_den_finalize<ESPIC_DEPOSIT_FP64><<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, s.acc, c->node_vol, s.den, inv_scale);
