@@ -157,6 +157,7 @@ struct OwnAll {
     __device__ __forceinline__ long long lo(const MgLevel &L, int) const { return 0; }
     __device__ __forceinline__ long long hi(const MgLevel &L, int) const { return L.nn; }
     __device__ __forceinline__ void st(double *A, long long u, const MgLevel &, int, double v) const { A[u] = v; }
+    __device__ __forceinline__ void st_all(double *A, long long u, double v) const { A[u] = v; }
     __device__ __forceinline__ int nparts(int nb) const { return nb; }
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const { base[blockIdx.x] = v; }
     __device__ __forceinline__ void barrier(cg::grid_group &grid) { grid.sync(); }
@@ -179,6 +180,11 @@ struct OwnSlab {
         if (rank > 0 && u < lo(L, l) + plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank - 1]) = v;
         if (rank + 1 < nranks && u >= hi(L, l) - plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank + 1]) = v;
     }
+    // store into every rank's copy (the right-hand side of the coarsest level: that level is solved by every rank in full)
+    __device__ __forceinline__ void st_all(double *A, long long u, double v) const
+    {
+        for (int p = 0; p < nranks; p++) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[p]) = v;
+    }
     __device__ __forceinline__ int nparts(int nb) const { return nb * nranks; }
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const
     {
@@ -195,26 +201,35 @@ struct OwnSlab {
     {
         __syncthreads();
         epoch++;
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            volatile unsigned long long *rel = release;
-            if (blockIdx.x == 0) {
-                volatile unsigned long long *arr = arrive;
-                const unsigned long long want = (unsigned long long)(gridDim.x - 1) * epoch;
-                while (*arr < want) { }
-                __threadfence_system();
-                for (int p = 0; p < nranks; p++)
-                    *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[p]) = epoch;
-                for (int p = 0; p < nranks; p++) {
-                    volatile unsigned long long *mine = flags + p;
-                    while (*mine < epoch) { }
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < 32) {          // first warp: lane 0 collects the local arrivals, lane p talks to peer p
+                const int lane = threadIdx.x;
+                if (lane == 0) {
+                    __threadfence_system();
+                    volatile unsigned long long *arr = arrive;
+                    const unsigned long long want = (unsigned long long)(gridDim.x - 1) * epoch;
+                    while (*arr < want) { }
+                    __threadfence_system();
                 }
-                __threadfence_system();
-                *rel = epoch;
-            } else {
-                atomicAdd(arrive, 1ull);
-                while (*rel < epoch) { }
+                __syncwarp();
+                if (lane < nranks) {
+                    *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[lane]) = epoch;
+                    volatile unsigned long long *mine = flags + lane;
+                    while (*mine < epoch) { }
+                    __threadfence_system();
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    volatile unsigned long long *rel = release;
+                    *rel = epoch;
+                    __threadfence();
+                }
             }
+        } else if (threadIdx.x == 0) {
+            __threadfence_system();
+            atomicAdd(arrive, 1ull);
+            volatile unsigned long long *rel = release;
+            while (*rel < epoch) { }
             __threadfence();
         }
         __syncthreads();
@@ -249,7 +264,7 @@ __device__ __forceinline__ double mg_offdiag(const MgLevel &L, int i, int j, int
 template <class Own>
 __device__ __forceinline__ void mg_down0(const Own &own, const StencilC &s, const double *__restrict__ r,
                                          const double *__restrict__ diag, const double *__restrict__ x0, const MgLevel &C,
-                                         long long t0, long long stride)
+                                         long long t0, long long stride, bool to_all)
 {
     for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
         const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
@@ -269,7 +284,8 @@ __device__ __forceinline__ void mg_down0(const Own &own, const StencilC &s, cons
                         sum += r[u] - (dg * x0[u] - mg_offdiag0(s, x0, u));
                     }
         }
-        own.st(C.b, I, C, 1, sum);
+        if (to_all) own.st_all(C.b, I, sum);
+        else own.st(C.b, I, C, 1, sum);
     }
 }
 
@@ -286,7 +302,8 @@ __device__ __forceinline__ double mg_sum8(double v)
 
 // Down pass between coarse levels F (level lf) -> C: lane c of a group handles child c of coarse node I
 template <class Own>
-__device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf, const MgLevel &C, long long t0, long long stride)
+__device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf, const MgLevel &C, long long t0, long long stride,
+                                        bool to_all)
 {
     const long long first = own.lo(C, lf + 1), total = (own.hi(C, lf + 1) - first) * 8;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
@@ -310,7 +327,10 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
             }
         }
         res = mg_sum8(res);
-        if (c == 0 && live) own.st(C.b, I, C, lf + 1, res);
+        if (c == 0 && live) {
+            if (to_all) own.st_all(C.b, I, res);
+            else own.st(C.b, I, C, lf + 1, res);
+        }
     }
 }
 
@@ -486,24 +506,29 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
         }
         return acc;
     }
-    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride);
+    // The coarsest level is tiny: in slab mode its right-hand side is stored to EVERY rank and every rank sweeps the whole
+    // level redundantly with grid-local barriers only (identical arithmetic -> identical result everywhere); that removes
+    // coarse_sweeps+1 inter-GPU barriers per V-cycle.
+    const int lc = a.nlev - 1;
+    const MgLevel &Lc = a.L[lc];
+    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride, lc == 1);
     own.barrier(grid);
     MG_TICK(0);
     for (int l = 1; l + 1 < a.nlev; l++) {
-        mg_down(own, a.L[l], l, a.L[l + 1], t0, stride);
+        mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lc);
         own.barrier(grid);
     }
     MG_TICK(1);
-    // coarsest level: Jacobi sweeps from zero; the result ends in x (even sweep count)
-    const int lc = a.nlev - 1;
-    const MgLevel &Lc = a.L[lc];
-    for (long long u = own.lo(Lc, lc) + t0; u < own.hi(Lc, lc); u += stride) own.st(Lc.x, u, Lc, lc, MG_OMEGA * Lc.b[u] * Lc.minv[u]);
-    own.barrier(grid);
-    for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
-        mg_jacobi(own, Lc, lc, Lc.x, Lc.xn, t0, stride);
-        own.barrier(grid);
-        mg_jacobi(own, Lc, lc, Lc.xn, Lc.x, t0, stride);
-        own.barrier(grid);
+    {
+        OwnAll whole;
+        for (long long u = t0; u < Lc.nn; u += stride) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
+        grid.sync();
+        for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
+            mg_jacobi(whole, Lc, lc, Lc.x, Lc.xn, t0, stride);
+            grid.sync();
+            mg_jacobi(whole, Lc, lc, Lc.xn, Lc.x, t0, stride);
+            grid.sync();
+        }
     }
     MG_TICK(2);
     const double *e = Lc.x;
@@ -926,7 +951,8 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;
         a.delta = S->delta; a.r = S->R; a.z = S->z; a.d0 = S->d0; a.d1 = S->d1; a.q = S->q;
-        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout; a.prof = nullptr;
+        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
+        a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
         // same inexact-Newton forcing as the single-GPU solver (identical on every rank: it derives from all-reduced norms)
         a.rel_tol = (it == 0 && getenv("ESPIC_MG_EXACT_NEWTON") == nullptr) ? std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         // nobody may store into a neighbour's pool before that neighbour has finished preparing this Newton step
@@ -960,5 +986,14 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
     if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
     info->converged = converged;
     info->residual = norm;
+    if (getenv("ESPIC_MG_PROFILE") && c->rank == 0) {
+        unsigned long long hp[8];
+        CK(cudaMemcpyAsync(hp, c->dscal + 40, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemsetAsync(c->dscal + 40, 0, sizeof(hp), c->stream));
+        fprintf(stderr, "[mg slab profile] its=%lld  us/it: down0 %.1f  down %.1f  coarsest %.1f  up %.1f  up0+rz %.1f  dq %.1f  r %.1f\n",
+                info->lin_iters, hp[0] * 1e-3 / info->lin_iters, hp[1] * 1e-3 / info->lin_iters, hp[2] * 1e-3 / info->lin_iters,
+                hp[3] * 1e-3 / info->lin_iters, hp[4] * 1e-3 / info->lin_iters, hp[5] * 1e-3 / info->lin_iters, hp[6] * 1e-3 / info->lin_iters);
+    }
     return 0;
 }
