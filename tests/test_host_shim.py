@@ -257,3 +257,43 @@ def test_reference_ch3_main_steady_state_statistics(tmp_path):
         assert np.abs(a - b).max() <= tol * b.max(), (key, np.abs(a - b).max() / b.max())
     a, b = np.array(got["phi_k_profile"]), np.array(ref["phi_k_profile"])
     assert np.abs(a - b).max() <= 0.02 * np.abs(b).max()
+
+
+def _run_main(exe_name, tmp_path, args=(), timeout=900):
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip("bin/%s is built only where the reference tree is present" % exe_name)
+    os.makedirs(str(tmp_path / "results"), exist_ok=True)
+    with open(str(tmp_path / "run.log"), "w") as log:
+        subprocess.run([exe] + list(args), cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=timeout, check=True,
+                       env=dict(os.environ, ESPIC_SEED="99"))
+    rows = [l.split(",") for l in open(str(tmp_path / "runtime_diags.csv")).read().splitlines()]
+    return rows[0], [[float(x) for x in r] for r in rows[1:]]
+
+
+@pytest.mark.gpu
+def test_reference_ch9_main_quasi_neutral(tmp_path):
+    """ch9/Main.cpp unchanged (SolverType::QN, mpw 1e4, n = 1e12): known answers of the reference build at ts = 400
+    (697 961 particles, KE 9.43056e-09, PE 8.89026e-08; run-to-run scatter ~0.1 %)."""
+    header, rows = _run_main("main_ch9", tmp_path)
+    last = [r for r in rows if int(r[0]) == 400][0]
+    assert abs(last[3] / 697961 - 1) < 0.01
+    assert abs(last[8] / 9.43056e-09 - 1) < 0.01
+    assert abs(last[9] / 8.89026e-08 - 1) < 0.02
+    first = rows[0]
+    assert first[3] in (2800.0, 2801.0), "first injection = 2800 (+ Bernoulli) particles"
+
+
+@pytest.mark.gpu
+def test_reference_ch9_mt_main_three_species(tmp_path):
+    """ch9/MT/Main.cpp unchanged: neutrals + O+ + O++ with three beam sources and setNumThreads(); the reference reaches
+    ~1.10e7 particles for ts >= 300.  Neutrals must not contribute to rho (World.cpp:46-54)."""
+    header, rows = _run_main("main_ch9mt", tmp_path, args=("4",))
+    assert header[3].startswith("mp_count.O") and len(header) == 3 + 6 * 3 + 2
+    last = [r for r in rows if int(r[0]) == 400][0]
+    counts = [last[3], last[9], last[15]]
+    assert abs(sum(counts) / 1.10e7 - 1) < 0.03, counts
+    # neutrals fly straight: momentum only along z, every real O atom still has v = 7000 m/s
+    assert abs(last[5]) < 1e-6 * abs(last[7]) and abs(last[6]) < 1e-6 * abs(last[7])
+    ke_per_real = last[8] / last[4]
+    assert abs(ke_per_real / (0.5 * 16 * AMU * 7000.0 ** 2) - 1) < 1e-9
