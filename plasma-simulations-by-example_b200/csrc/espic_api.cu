@@ -291,7 +291,10 @@ extern "C" int espic_species_reserve(espic_ctx *c, int sp, long long capacity)
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
     if (capacity <= s.cap) return 0;
-    // round up so 128-bit vector access of whole warps never leaves the allocation
+    // grow geometrically once particles exist (a source appends a few thousand particles every step; reallocating seven
+    // arrays per step costs ~40 ms of cudaMalloc/cudaFree), and round up so 128-bit vector access of whole warps never
+    // leaves the allocation
+    if (s.cap > 0 && s.np > 0) capacity = std::max(capacity, s.cap + s.cap / 2);
     long long ncap = (capacity + 1023) / 1024 * 1024;
     for (int q = 0; q < 7; q++) {
         double *np_ = nullptr;

@@ -296,4 +296,4 @@ def test_reference_ch9_mt_main_three_species(tmp_path):
     # neutrals fly straight: momentum only along z, every real O atom still has v = 7000 m/s
     assert abs(last[5]) < 1e-6 * abs(last[7]) and abs(last[6]) < 1e-6 * abs(last[7])
     ke_per_real = last[8] / last[4]
-    assert abs(ke_per_real / (0.5 * 16 * AMU * 7000.0 ** 2) - 1) < 1e-9
+    assert abs(ke_per_real / (0.5 * 16 * AMU * 7000.0 ** 2) - 1) < 1e-5      # the CSV carries 6 significant digits
