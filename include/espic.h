@@ -55,7 +55,9 @@ int espic_add_inlet(espic_ctx *ctx);
 /* ---- node fields: the public World/Species members Output.cpp and Main.cpp read -------------- */
 
 enum { ESPIC_PHI = 0, ESPIC_RHO = 1, ESPIC_EF = 2, ESPIC_NODE_VOL = 3, ESPIC_OBJECT_ID = 4,
-       ESPIC_DEN = 5, ESPIC_DEN_AVE = 6 };
+       ESPIC_DEN = 5, ESPIC_DEN_AVE = 6,
+       /* per-species velocity-moment fields of ch4 (Species.h:85-95); VEL and NV_SUM are interleaved [3*u+c] */
+       ESPIC_VEL = 7, ESPIC_T = 8, ESPIC_N_SUM = 9, ESPIC_NV_SUM = 10, ESPIC_NUU_SUM = 11, ESPIC_NVV_SUM = 12, ESPIC_NWW_SUM = 13 };
 int espic_field_download(espic_ctx *ctx, int which, int species, void *host);
 int espic_field_upload(espic_ctx *ctx, int which, int species, const void *host);
 /* device pointer of a field (zero-copy interop: NCCL, torch.from_blob, ...) */
@@ -104,6 +106,16 @@ int espic_inject_cold_beam(espic_ctx *ctx, int sp, double v_drift, double den, d
 int espic_species_diag(espic_ctx *ctx, int sp, double out[5]);
 /* Species::updateAverages -> Field::updateAverage (Field.h:214-221) */
 int espic_update_average(espic_ctx *ctx, int sp);
+
+/* ---- velocity moments (the "next" row 8f-1: mesh-averaged velocity and temperature) ----------- */
+
+/* Species::sampleMoments (ch4/Species.cpp:190-200): n_sum, nv_sum, nuu_sum, nvv_sum, nww_sum += trilinear scatter of
+ * mpw, mpw*vel, mpw*vx*vx, mpw*vy*vy, mpw*vz*vz */
+int espic_sample_moments(espic_ctx *ctx, int sp);
+/* Species::computeGasProperties (ch4/Species.cpp:203-226): vel = nv_sum/n_sum, T = m/(2K) * sum of velocity variances */
+int espic_compute_gas_properties(espic_ctx *ctx, int sp);
+/* Species::clearSamples (ch4/Species.cpp:239-241) */
+int espic_clear_samples(espic_ctx *ctx, int sp);
 
 /* ---- fields --------------------------------------------------------------------------------- */
 

@@ -331,6 +331,54 @@ void orc_number_density(const orc_mesh *m, const double *node_vol, const orc_par
     }
 }
 
+/* Species::sampleMoments, ch4/Species.cpp:190-200: n_sum, nv_sum (3 interleaved components), nuu_sum, nvv_sum, nww_sum
+ * accumulate the trilinear scatter of mpw, mpw*vel, mpw*vx*vx, mpw*vy*vy, mpw*vz*vz (products left to right). */
+void orc_sample_moments(const orc_mesh *m, const orc_particles *p, double *n_sum, double *nv_sum, double *nuu_sum,
+                        double *nvv_sum, double *nww_sum)
+{
+    size_t nn = (size_t)m->ni * m->nj * m->nk;
+    /* Field3::scatter adds value*(w_i)*(w_j)*(w_k) component-wise: scatter each component into a strided view */
+    double *tmp = (double *)calloc(nn, sizeof(double));
+    for (int c = 0; c < 3; c++) {
+        memset(tmp, 0, nn * sizeof(double));
+        for (size_t u = 0; u < nn; u++) tmp[u] = nv_sum[3 * u + c];
+        for (int64_t q = 0; q < p->np; q++) {
+            double pos[3] = { p->x[q], p->y[q], p->z[q] }, lc[3];
+            const double v = c == 0 ? p->vx[q] : (c == 1 ? p->vy[q] : p->vz[q]);
+            orc_xtol(m, pos, lc);
+            orc_scatter(m, tmp, lc, p->mpw[q] * v);
+        }
+        for (size_t u = 0; u < nn; u++) nv_sum[3 * u + c] = tmp[u];
+    }
+    free(tmp);
+    for (int64_t q = 0; q < p->np; q++) {
+        double pos[3] = { p->x[q], p->y[q], p->z[q] }, lc[3];
+        orc_xtol(m, pos, lc);
+        orc_scatter(m, n_sum, lc, p->mpw[q]);
+        orc_scatter(m, nuu_sum, lc, p->mpw[q] * p->vx[q] * p->vx[q]);
+        orc_scatter(m, nvv_sum, lc, p->mpw[q] * p->vy[q] * p->vy[q]);
+        orc_scatter(m, nww_sum, lc, p->mpw[q] * p->vz[q] * p->vz[q]);
+    }
+}
+
+/* Species::computeGasProperties, ch4/Species.cpp:203-226 with Field operator/ (ch4/Field.h:192-204):
+ * vel = nv_sum/n_sum (0 where n_sum == 0); T = mass/(2K) * ((<u2>-<u>^2) + (<v2>-<v>^2) + (<w2>-<w>^2)), 0 where count <= 0 */
+void orc_gas_properties(const orc_mesh *m, double mass, const double *n_sum, const double *nv_sum, const double *nuu_sum,
+                        const double *nvv_sum, const double *nww_sum, double *vel, double *T)
+{
+    const double K = 1.380648e-23;      /* Const::K, ch4/World.h:18 */
+    size_t nn = (size_t)m->ni * m->nj * m->nk;
+    for (size_t u = 0; u < nn; u++) {
+        for (int c = 0; c < 3; c++) vel[3 * u + c] = (n_sum[u] != 0) ? nv_sum[3 * u + c] / n_sum[u] : 0.0;
+        double count = n_sum[u];
+        if (count <= 0) { T[u] = 0; continue; }
+        double u_ave = vel[3 * u], v_ave = vel[3 * u + 1], w_ave = vel[3 * u + 2];
+        double u2_ave = nuu_sum[u] / count, v2_ave = nvv_sum[u] / count, w2_ave = nww_sum[u] / count;
+        double uu = u2_ave - u_ave * u_ave, vv = v2_ave - v_ave * v_ave, ww = w2_ave - w_ave * w_ave;
+        T[u] = mass / (2 * K) * (uu + vv + ww);
+    }
+}
+
 /* World::computeChargeDensity, ch3/ver2/World.cpp:46-54: rho=0; rho += charge*den (charge!=0) */
 void orc_rho_clear(const orc_mesh *m, double *rho)
 {

@@ -72,6 +72,8 @@ def lib():
         L.orc_advance_box.argtypes = L.orc_advance_sphere.argtypes
         L.orc_push_sphere_nocompact.argtypes = L.orc_advance_sphere.argtypes
         L.orc_number_density.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles), dp]
+        L.orc_sample_moments.argtypes = [C.POINTER(CMesh), C.POINTER(CParticles), dp, dp, dp, dp, dp]
+        L.orc_gas_properties.argtypes = [C.POINTER(CMesh), C.c_double, dp, dp, dp, dp, dp, dp, dp]
         L.orc_rho_add.argtypes = [C.POINTER(CMesh), dp, dp, C.c_double]
         L.orc_momentum.argtypes = [C.POINTER(CParticles), C.c_double, dp]
         L.orc_ke.argtypes = [C.POINTER(CParticles), C.c_double]
@@ -157,6 +159,30 @@ class Species:
     def compute_number_density(self):
         p = self._c()
         lib().orc_number_density(C.byref(self.world.m), _dp(self.world.node_vol), C.byref(p), _dp(self.den))
+
+    # ---- velocity moments (ch4/Species.cpp:190-241)
+    def _moment_arrays(self):
+        if not hasattr(self, "n_sum"):
+            nn = self.world.nn
+            self.n_sum, self.nv_sum = np.zeros(nn), np.zeros(3 * nn)
+            self.nuu_sum, self.nvv_sum, self.nww_sum = np.zeros(nn), np.zeros(nn), np.zeros(nn)
+            self.vel, self.T = np.zeros(3 * nn), np.zeros(nn)
+
+    def clear_samples(self):
+        self._moment_arrays()
+        for a in (self.n_sum, self.nv_sum, self.nuu_sum, self.nvv_sum, self.nww_sum):
+            a[:] = 0
+
+    def sample_moments(self):
+        self._moment_arrays()
+        p = self._c()
+        lib().orc_sample_moments(C.byref(self.world.m), C.byref(p), _dp(self.n_sum), _dp(self.nv_sum), _dp(self.nuu_sum),
+                                 _dp(self.nvv_sum), _dp(self.nww_sum))
+
+    def compute_gas_properties(self):
+        self._moment_arrays()
+        lib().orc_gas_properties(C.byref(self.world.m), C.c_double(self.mass), _dp(self.n_sum), _dp(self.nv_sum), _dp(self.nuu_sum),
+                                 _dp(self.nvv_sum), _dp(self.nww_sum), _dp(self.vel), _dp(self.T))
 
     def update_averages(self):
         lib().orc_update_average(C.byref(self.world.m), _dp(self.den_ave), _dp(self.den), C.byref(self.ave_samples))

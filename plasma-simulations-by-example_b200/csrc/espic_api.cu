@@ -152,7 +152,7 @@ extern "C" void espic_destroy(espic_ctx *c)
     cudaFree(c->phi); cudaFree(c->rho); cudaFree(c->ef); cudaFree(c->ef4); cudaFree(c->node_vol); cudaFree(c->object_id);
     for (int s = 0; s < c->nsp; s++) {
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }
-        cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc);
+        cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc); cudaFree(c->sp[s].mom);
     }
     cudaFree(c->dead_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
     cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
@@ -214,9 +214,23 @@ extern "C" int espic_add_inlet(espic_ctx *c)
 static int field_ptr(espic_ctx *c, int which, int sp, void **p, size_t *bytes)
 {
     size_t nn = (size_t)c->m.nn;
-    if ((which == ESPIC_DEN || which == ESPIC_DEN_AVE) && (sp < 0 || sp >= c->nsp)) {
+    if (which >= ESPIC_DEN && (sp < 0 || sp >= c->nsp)) {
         espic_set_error("field: bad species %d", sp);
         return -1;
+    }
+    if (which >= ESPIC_VEL && which <= ESPIC_NWW_SUM) {
+        if (espic_ensure_moments(c, sp)) return -1;
+        double *m = c->sp[sp].mom;
+        // layout: n_sum | nv_sum[3] | nuu | nvv | nww | vel[3] | T
+        switch (which) {
+            case ESPIC_N_SUM: *p = m; *bytes = nn * 8; return 0;
+            case ESPIC_NV_SUM: *p = m + nn; *bytes = nn * 24; return 0;
+            case ESPIC_NUU_SUM: *p = m + 4 * nn; *bytes = nn * 8; return 0;
+            case ESPIC_NVV_SUM: *p = m + 5 * nn; *bytes = nn * 8; return 0;
+            case ESPIC_NWW_SUM: *p = m + 6 * nn; *bytes = nn * 8; return 0;
+            case ESPIC_VEL: *p = m + 7 * nn; *bytes = nn * 24; return 0;
+            case ESPIC_T: *p = m + 10 * nn; *bytes = nn * 8; return 0;
+        }
     }
     switch (which) {
         case ESPIC_PHI: *p = c->phi; *bytes = nn * 8; return 0;
@@ -229,6 +243,16 @@ static int field_ptr(espic_ctx *c, int which, int sp, void **p, size_t *bytes)
     }
     espic_set_error("field: unknown id %d", which);
     return -1;
+}
+
+int espic_ensure_moments(espic_ctx *c, int sp)
+{
+    Species &s = c->sp[sp];
+    if (s.mom) return 0;
+    const size_t nb = (size_t)c->m.nn * 11 * sizeof(double);
+    CK(cudaMalloc(&s.mom, nb));
+    CK(cudaMemsetAsync(s.mom, 0, nb, c->stream));
+    return 0;
 }
 
 extern "C" int espic_field_download(espic_ctx *c, int which, int sp, void *host)

@@ -29,6 +29,7 @@ struct Species {
     long long alt_cap = 0;
     double *den = nullptr, *den_ave = nullptr;
     double *acc = nullptr;             // FP64 scatter accumulator (also aliased as int64 in fixed-point mode)
+    double *mom = nullptr;             // velocity moments, allocated on first use: n_sum | nv_sum[3] | nuu | nvv | nww | vel[3] | T
     int ave_samples = 0;
     bool acc_fresh = false;            // accumulator holds the scatter of the current particle state
     int acc_mode = ESPIC_DEPOSIT_FP64;
@@ -90,6 +91,7 @@ template <typename T> static inline int ensure_buf(T **ptr, long long *cap, long
 #define SCAN_CHUNK_LOG2 13
 int espic_scan_u32(espic_ctx *ctx, const uint32_t *in, long long n, unsigned long long *d_total);
 
+int espic_ensure_moments(espic_ctx *c, int sp);   // espic_api.cu: allocate + zero the 11 moment arrays of a species
 int espic_repack_ef(espic_ctx *c);
 void espic_mg_destroy(espic_ctx *c);   // espic_fields.cu     // espic_api.cu: refresh ef4 after ef was written from outside
 

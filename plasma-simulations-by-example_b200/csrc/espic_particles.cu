@@ -704,6 +704,98 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
 }
 
 // =====================================================================================================
+// velocity moments (ch4 Species::sampleMoments / computeGasProperties / clearSamples, Species.cpp:190-241)
+// =====================================================================================================
+
+// First version: one thread per particle, the eight sampled quantities scattered with 64 RED.ADD.F64 (same node and
+// factor order as Field::scatter).  Not yet run-merged like the density deposit.
+__global__ void __launch_bounds__(256) k_sample_moments(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                        const double *__restrict__ z, const double *__restrict__ vx,
+                                                        const double *__restrict__ vy, const double *__restrict__ vz,
+                                                        const double *__restrict__ mpw, long long n, double *mom)
+{
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n) return;
+    const double w = mpw[idx];
+    if (!(w != 0)) return;
+    int i, j, k; double di, dj, dk;
+    cell3(m, x[idx], y[idx], z[idx], i, j, k, di, dj, dk);
+    if (i < 0 || j < 0 || k < 0) return;
+    const double u = vx[idx], v = vy[idx], ww = vz[idx];
+    // values in the reference's evaluation order: mpw*vel (component-wise), mpw*vx*vx = (mpw*vx)*vx, ...
+    const double val[8] = {w, w * u, w * v, w * ww, w * u * u, w * v * v, w * ww * ww, 0};
+    const long long nn = m.nn, sj = m.ni, sk = (long long)m.ni * m.nj;
+    const long long u0 = node_u(m, i, j, k);
+    const long long node[8] = {u0, u0 + 1, u0 + 1 + sj, u0 + sj, u0 + sk, u0 + 1 + sk, u0 + 1 + sj + sk, u0 + sj + sk};
+    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
+    const double fi[8] = {ai, di, di, ai, ai, di, di, ai}, fj[8] = {aj, aj, dj, dj, aj, aj, dj, dj}, fk[8] = {ak, ak, ak, ak, dk, dk, dk, dk};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const long long un = node[c];
+        atomicAdd(mom + un, val[0] * fi[c] * fj[c] * fk[c]);                         // n_sum
+        atomicAdd(mom + nn + 3 * un, val[1] * fi[c] * fj[c] * fk[c]);                // nv_sum
+        atomicAdd(mom + nn + 3 * un + 1, val[2] * fi[c] * fj[c] * fk[c]);
+        atomicAdd(mom + nn + 3 * un + 2, val[3] * fi[c] * fj[c] * fk[c]);
+        atomicAdd(mom + 4 * nn + un, val[4] * fi[c] * fj[c] * fk[c]);                // nuu_sum
+        atomicAdd(mom + 5 * nn + un, val[5] * fi[c] * fj[c] * fk[c]);                // nvv_sum
+        atomicAdd(mom + 6 * nn + un, val[6] * fi[c] * fj[c] * fk[c]);                // nww_sum
+    }
+}
+
+// Species::computeGasProperties with Field operator/ (ch4/Field.h:192-204)
+__global__ void __launch_bounds__(256) k_gas_properties(long long nn, double mass, double *mom)
+{
+    const long long u = blockIdx.x * 256ll + threadIdx.x;
+    if (u >= nn) return;
+    const double K = 1.380648e-23;          // Const::K (ch4/World.h:18)
+    const double count = mom[u];
+    double vel[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { vel[c] = (count != 0) ? mom[nn + 3 * u + c] / count : 0.0; mom[7 * nn + 3 * u + c] = vel[c]; }
+    double T = 0;
+    if (count > 0) {
+        const double u2 = mom[4 * nn + u] / count, v2 = mom[5 * nn + u] / count, w2 = mom[6 * nn + u] / count;
+        const double uu = u2 - vel[0] * vel[0], vv = v2 - vel[1] * vel[1], wv = w2 - vel[2] * vel[2];
+        T = mass / (2 * K) * (uu + vv + wv);
+    }
+    mom[10 * nn + u] = T;
+}
+
+extern "C" int espic_sample_moments(espic_ctx *c, int sp)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    int r;
+    if ((r = espic_ensure_moments(c, sp))) return r;
+    Species &s = c->sp[sp];
+    if (s.np == 0) return 0;
+    k_sample_moments<<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], s.np, s.mom);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+extern "C" int espic_compute_gas_properties(espic_ctx *c, int sp)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    int r;
+    if ((r = espic_ensure_moments(c, sp))) return r;
+    k_gas_properties<<<nblk(c->m.nn, 256), 256, 0, c->stream>>>(c->m.nn, c->sp[sp].mass, c->sp[sp].mom);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+extern "C" int espic_clear_samples(espic_ctx *c, int sp)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    int r;
+    if ((r = espic_ensure_moments(c, sp))) return r;
+    CK(cudaMemsetAsync(c->sp[sp].mom, 0, (size_t)c->m.nn * 7 * sizeof(double), c->stream));
+    return 0;
+}
+
+// =====================================================================================================
 // sort by cell (counting sort; cell key as ch4 World::XtoC: c = k*(nj-1)*(ni-1) + j*(ni-1) + i)
 // =====================================================================================================
 

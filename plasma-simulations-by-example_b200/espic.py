@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libespic_cuda.so")
 
-PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE = range(7)
+PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM, NVV_SUM, NWW_SUM = range(14)
 WALL_ABSORB, WALL_REFLECT = 0, 1
 PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_FIXED_POINT = 1, 2, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
@@ -22,7 +22,7 @@ EXPORTS = [
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
-    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_species_diag", "espic_update_average",
+    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
 ]
@@ -89,6 +89,9 @@ def load():
                                          C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_species_diag.argtypes = [vp, C.c_int, dp]
     L.espic_update_average.argtypes = [vp, C.c_int]
+    L.espic_sample_moments.argtypes = [vp, C.c_int]
+    L.espic_compute_gas_properties.argtypes = [vp, C.c_int]
+    L.espic_clear_samples.argtypes = [vp, C.c_int]
     L.espic_charge_density.argtypes = [vp]
     L.espic_solve.argtypes = [vp, C.POINTER(SolveParams), C.POINTER(SolveInfo)]
     L.espic_compute_ef.argtypes = [vp]
@@ -169,7 +172,7 @@ class Engine:
 
     def field(self, which, sp=0, out=None):
         """Download a node field.  `out`: optional preallocated (e.g. pinned) array to receive it."""
-        n, dt = self.nn * (3 if which == EF else 1), (np.int32 if which == OBJECT_ID else np.float64)
+        n, dt = self.nn * (3 if which in (EF, VEL, NV_SUM) else 1), (np.int32 if which == OBJECT_ID else np.float64)
         if out is None:
             out = np.zeros(n, dtype=dt)
         assert out.size == n and out.dtype == dt and out.flags["C_CONTIGUOUS"]
@@ -264,6 +267,15 @@ class Engine:
         out = np.zeros(5)
         self._ck(self.L.espic_species_diag(self.h, sp, _dp(out)))
         return out
+
+    def sample_moments(self, sp):
+        self._ck(self.L.espic_sample_moments(self.h, sp))
+
+    def compute_gas_properties(self, sp):
+        self._ck(self.L.espic_compute_gas_properties(self.h, sp))
+
+    def clear_samples(self, sp):
+        self._ck(self.L.espic_clear_samples(self.h, sp))
 
     def update_average(self, sp):
         self._ck(self.L.espic_update_average(self.h, sp))

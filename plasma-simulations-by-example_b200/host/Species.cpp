@@ -11,7 +11,7 @@ static int default_sort_every()
 
 Species::Species(std::string name, double mass, double charge, double mpw0, World &world)
     : name(name), mass(mass), charge(charge), mpw0(mpw0), den(world.ni, world.nj, world.nk), den_ave(world.ni, world.nj, world.nk),
-      sort_every(default_sort_every()), world(world), reflect(false)
+      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), sort_every(default_sort_every()), world(world), reflect(false)
 {
     sp_id = world.register_species(this, mass, charge, mpw0);
     bind_fields();
@@ -19,7 +19,7 @@ Species::Species(std::string name, double mass, double charge, double mpw0, Worl
 
 Species::Species(std::string name, double mass, double charge, World &world)
     : name(name), mass(mass), charge(charge), mpw0(0), den(world.ni, world.nj, world.nk), den_ave(world.ni, world.nj, world.nk),
-      sort_every(default_sort_every()), world(world), reflect(true)
+      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), sort_every(default_sort_every()), world(world), reflect(true)
 {
     sp_id = world.register_species(this, mass, charge, 0);
     bind_fields();
@@ -27,7 +27,7 @@ Species::Species(std::string name, double mass, double charge, World &world)
 
 Species::Species(Species &&o)
     : name(o.name), mass(o.mass), charge(o.charge), mpw0(o.mpw0), den(std::move(o.den)), den_ave(std::move(o.den_ave)),
-      sort_every(o.sort_every), world(o.world), sp_id(o.sp_id), reflect(o.reflect), n_advance(o.n_advance), diag_valid(o.diag_valid)
+      T(std::move(o.T)), vel(std::move(o.vel)), sort_every(o.sort_every), world(o.world), sp_id(o.sp_id), reflect(o.reflect), n_advance(o.n_advance), diag_valid(o.diag_valid)
 {
     for (int q = 0; q < 7; q++) pending[q] = std::move(o.pending[q]);
     for (int q = 0; q < 5; q++) diag[q] = o.diag[q];
@@ -110,6 +110,29 @@ void Species::updateAverages()
     den_ave.to_device();
     espic_host::check(espic_update_average(world.engine(), sp_id), "espic_update_average");
     den_ave.mark_device_wrote();
+}
+
+// ch4/Species.cpp:190-241, on the device
+void Species::sampleMoments()
+{
+    flush();
+    espic_host::check(espic_sample_moments(world.engine(), sp_id), "espic_sample_moments");
+}
+
+void Species::computeGasProperties()
+{
+    espic_host::check(espic_compute_gas_properties(world.engine(), sp_id), "espic_compute_gas_properties");
+    if (!T.bound()) {          // the moment arrays exist on the device from the first use on
+        T.bind(world.engine(), ESPIC_T, sp_id, true);
+        vel.bind(world.engine(), ESPIC_VEL, sp_id, true);
+    }
+    T.mark_device_wrote();
+    vel.mark_device_wrote();
+}
+
+void Species::clearSamples()
+{
+    espic_host::check(espic_clear_samples(world.engine(), sp_id), "espic_clear_samples");
 }
 
 void Species::sortByCell()

@@ -42,6 +42,10 @@ public:
     void loadParticlesBox(double3 x1, double3 x2, double num_den, int num_mp);
     void loadParticlesBoxQS(double3 x1, double3 x2, double num_den, int3 num_mp);
     void updateAverages();
+    // velocity moments of ch4 (ch4/Species.h:53-62): mesh-averaged stream velocity and temperature
+    void sampleMoments();
+    void computeGasProperties();
+    void clearSamples();
 
     const std::string name;
     const double mass;
@@ -50,6 +54,8 @@ public:
 
     Field den;
     Field den_ave;
+    Field T;          // temperature (ch4/Species.h:85), valid after computeGasProperties()
+    Field3 vel;       // stream velocity (ch4/Species.h:86)
 
     // ---- not in the reference API ----
     int id() const { return sp_id; }
