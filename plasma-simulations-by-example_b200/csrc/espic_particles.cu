@@ -707,38 +707,51 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
 // velocity moments (ch4 Species::sampleMoments / computeGasProperties / clearSamples, Species.cpp:190-241)
 // =====================================================================================================
 
-// First version: one thread per particle, the eight sampled quantities scattered with 64 RED.ADD.F64 (same node and
-// factor order as Field::scatter).  Not yet run-merged like the density deposit.
+// One thread per particle; the seven sampled quantities times eight node weights are 56 sums per particle (same node and
+// factor order as Field::scatter).  A warp whose 32 particles share one cell (the common case right after a cell sort)
+// adds them up with shuffles and lane 0 issues the 56 REDs; any other warp scatters per particle.
 __global__ void __launch_bounds__(256) k_sample_moments(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
                                                         const double *__restrict__ z, const double *__restrict__ vx,
                                                         const double *__restrict__ vy, const double *__restrict__ vz,
                                                         const double *__restrict__ mpw, long long n, double *mom)
 {
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
-    if (idx >= n) return;
-    const double w = mpw[idx];
-    if (!(w != 0)) return;
-    int i, j, k; double di, dj, dk;
-    cell3(m, x[idx], y[idx], z[idx], i, j, k, di, dj, dk);
-    if (i < 0 || j < 0 || k < 0) return;
-    const double u = vx[idx], v = vy[idx], ww = vz[idx];
+    const int lane = threadIdx.x & 31;
+    if (idx - lane >= n) return;                                     // whole warp past the end
+    double w = 0, u = 0, v = 0, ww = 0, di = 0, dj = 0, dk = 0;
+    long long u0 = -1;
+    if (idx < n) {
+        w = mpw[idx];
+        if (w != 0) {
+            int i, j, k;
+            cell3(m, x[idx], y[idx], z[idx], i, j, k, di, dj, dk);
+            if (i >= 0 && j >= 0 && k >= 0) { u0 = node_u(m, i, j, k); u = vx[idx]; v = vy[idx]; ww = vz[idx]; }
+        }
+    }
     // values in the reference's evaluation order: mpw*vel (component-wise), mpw*vx*vx = (mpw*vx)*vx, ...
-    const double val[8] = {w, w * u, w * v, w * ww, w * u * u, w * v * v, w * ww * ww, 0};
+    const double val[7] = {w, w * u, w * v, w * ww, w * u * u, w * v * v, w * ww * ww};
     const long long nn = m.nn, sj = m.ni, sk = (long long)m.ni * m.nj;
-    const long long u0 = node_u(m, i, j, k);
-    const long long node[8] = {u0, u0 + 1, u0 + 1 + sj, u0 + sj, u0 + sk, u0 + 1 + sk, u0 + 1 + sj + sk, u0 + sj + sk};
     const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
     const double fi[8] = {ai, di, di, ai, ai, di, di, ai}, fj[8] = {aj, aj, dj, dj, aj, aj, dj, dj}, fk[8] = {ak, ak, ak, ak, dk, dk, dk, dk};
+    const long long off[8] = {0, 1, 1 + sj, sj, sk, 1 + sk, 1 + sj + sk, sj + sk};
+    const long long first = __shfl_sync(0xffffffffu, u0, 0);
+    const bool uniform = __all_sync(0xffffffffu, u0 == first) && first >= 0;
+    if (!uniform && u0 < 0) return;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        const long long un = node[c];
-        atomicAdd(mom + un, val[0] * fi[c] * fj[c] * fk[c]);                         // n_sum
-        atomicAdd(mom + nn + 3 * un, val[1] * fi[c] * fj[c] * fk[c]);                // nv_sum
-        atomicAdd(mom + nn + 3 * un + 1, val[2] * fi[c] * fj[c] * fk[c]);
-        atomicAdd(mom + nn + 3 * un + 2, val[3] * fi[c] * fj[c] * fk[c]);
-        atomicAdd(mom + 4 * nn + un, val[4] * fi[c] * fj[c] * fk[c]);                // nuu_sum
-        atomicAdd(mom + 5 * nn + un, val[5] * fi[c] * fj[c] * fk[c]);                // nvv_sum
-        atomicAdd(mom + 6 * nn + un, val[6] * fi[c] * fj[c] * fk[c]);                // nww_sum
+        const long long un = (uniform ? first : u0) + off[c];
+        double *dst[7] = {mom + un, mom + nn + 3 * un, mom + nn + 3 * un + 1, mom + nn + 3 * un + 2,
+                          mom + 4 * nn + un, mom + 5 * nn + un, mom + 6 * nn + un};
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            double t = val[q] * fi[c] * fj[c] * fk[c];
+            if (uniform) {
+                t = warp_sum(t);
+                if (lane == 0) atomicAdd(dst[q], t);
+            } else {
+                atomicAdd(dst[q], t);
+            }
+        }
     }
 }
 

@@ -59,6 +59,9 @@ def main():
     timed("deposit fp64 (5 steps after sort)", lambda: e.deposit(sp, es.DEPOSIT_FP64), 32)
     timed("push only + removal (5 steps after sort)", lambda: e.push(sp, B.DT, es.WALL_ABSORB, 0), 104, reps=2)
     timed("diag", lambda: e.diag(sp), 32)
+    timed("sample_moments (5+ steps after sort)", lambda: e.sample_moments(sp), 56, reps=3)
+    e.sort_by_cell(sp)
+    timed("sample_moments (sorted)", lambda: e.sample_moments(sp), 56, reps=3)
     print("launches:", e.kernel_launches())
 
 
