@@ -102,6 +102,12 @@ int espic_sort_by_cell(espic_ctx *ctx, int sp);
 int espic_inject_cold_beam(espic_ctx *ctx, int sp, double v_drift, double den, double dt,
                            uint64_t seed, uint32_t stream, uint32_t step, long long *n_added);
 
+/* WarmBeamSource::sample (ch4/Source.cpp:31-56): Maxwellian beam at temperature T (Kelvin) -- Birdsall's sum-of-three-uniforms
+ * speed times an isotropic direction (Species::sampleIsotropicVel / sampleVth, ch4/Species.cpp:149-173) plus the drift along z,
+ * from Philox counters (seven blocks per particle), admitted and rewound like espic_inject_cold_beam. */
+int espic_inject_warm_beam(espic_ctx *ctx, int sp, double v_drift, double den, double T, double dt,
+                           uint64_t seed, uint32_t stream, uint32_t step, long long *n_added);
+
 /* Species::getRealCount/getMomentum/getKE (Species.cpp:84-108): out = {sum mpw, px, py, pz, KE} */
 int espic_species_diag(espic_ctx *ctx, int sp, double out[5]);
 /* Species::updateAverages -> Field::updateAverage (Field.h:214-221) */

@@ -500,6 +500,68 @@ int64_t orc_cold_beam_sample_philox(const orc_mesh *m, const double *ef, orc_par
     return added;
 }
 
+/* Species::sampleIsotropicVel + sampleVth, ch4/Species.cpp:149-173, from eleven uniforms in the reference's draw order:
+ * u[0] theta, u[1] direction cosine, u[2..10] three sums of three (Birdsall) */
+void orc_isotropic_vel(double T, double mass, const double u[11], double vel[3])
+{
+    const double K = 1.380648e-23, PI = 3.141592653;       /* Const::K, Const::PI (ch4/World.h:18-19) */
+    double theta = 2 * PI * u[0];
+    double r = -1.0 + 2 * u[1];
+    double a = sqrt(1 - r * r);
+    double d[3] = { r, cos(theta) * a, sin(theta) * a };
+    double v_th = sqrt(2 * K * T / mass);
+    double v1 = v_th * (u[2] + u[3] + u[4] - 1.5);
+    double v2 = v_th * (u[5] + u[6] + u[7] - 1.5);
+    double v3 = v_th * (u[8] + u[9] + u[10] - 1.5);
+    double mag = 3 / sqrt(2 + 2 + 2) * sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    for (int c = 0; c < 3; c++) vel[c] = d[c] * mag;         /* v_th*d: vec3 scalar multiplication a(c)*s */
+}
+
+/* WarmBeamSource::sample, ch4/Source.cpp:31-56, uniforms from mt19937 in the reference's call order */
+int64_t orc_warm_beam_sample_mt(const orc_mesh *m, const double *ef, orc_particles *p, double charge, double mass,
+                                double mpw0, double v_drift, double den, double T, double dt, orc_mt19937 *g)
+{
+    double Lx = m->dh[0] * (m->ni - 1);
+    double Ly = m->dh[1] * (m->nj - 1);
+    int64_t num_sim = orc_cold_beam_num_sim(m, den, v_drift, dt, mpw0, orc_mt_uniform(g));
+    int64_t added = 0;
+    for (int64_t i = 0; i < num_sim; i++) {
+        double pos[3], vel[3], u[11];
+        pos[0] = m->x0[0] + orc_mt_uniform(g) * Lx;
+        pos[1] = m->x0[1] + orc_mt_uniform(g) * Ly;
+        pos[2] = m->x0[2];
+        for (int q = 0; q < 11; q++) u[q] = orc_mt_uniform(g);
+        orc_isotropic_vel(T, mass, u, vel);
+        vel[2] += v_drift;
+        added += orc_add_particle(m, ef, p, pos, vel, mpw0, charge, mass, dt);
+    }
+    return added;
+}
+
+/* Same sampler, uniforms from Philox4x32-10.  Draw layout (shared with the CUDA injector): idx = 2^64-1 -> Bernoulli
+ * fraction; particle i uses the seven blocks idx = 8*i + j: j=0 (x, y), j=1 (theta, cosine), j=2..6 the nine Birdsall
+ * uniforms in order (the second output of block 6 is unused). */
+int64_t orc_warm_beam_sample_philox(const orc_mesh *m, const double *ef, orc_particles *p, double charge, double mass,
+                                    double mpw0, double v_drift, double den, double T, double dt,
+                                    uint64_t seed, uint32_t stream, uint32_t step)
+{
+    double Lx = m->dh[0] * (m->ni - 1);
+    double Ly = m->dh[1] * (m->nj - 1);
+    double u2[2];
+    orc_philox_uniform2(seed, stream, step, ~(uint64_t)0, u2);
+    int64_t num_sim = orc_cold_beam_num_sim(m, den, v_drift, dt, mpw0, u2[0]);
+    int64_t added = 0;
+    for (int64_t i = 0; i < num_sim; i++) {
+        double w[14];
+        for (int j = 0; j < 7; j++) orc_philox_uniform2(seed, stream, step, 8 * (uint64_t)i + j, w + 2 * j);
+        double pos[3] = { m->x0[0] + w[0] * Lx, m->x0[1] + w[1] * Ly, m->x0[2] }, vel[3];
+        orc_isotropic_vel(T, mass, w + 2, vel);
+        vel[2] += v_drift;
+        added += orc_add_particle(m, ef, p, pos, vel, mpw0, charge, mass, dt);
+    }
+    return added;
+}
+
 /* Species::loadParticlesBoxQS, ch2/Species.cpp:101-141 */
 int64_t orc_load_box_qs(const orc_mesh *m, const double *ef, orc_particles *p, const double x1[3], const double x2[3],
                         double num_den, const int num_mp[3], double charge, double mass, double dt)

@@ -65,6 +65,8 @@ def lib():
         L.orc_advance_sphere.restype = C.c_int64
         L.orc_cold_beam_num_sim.restype = C.c_int64
         L.orc_cold_beam_sample_mt.restype = C.c_int64
+        L.orc_warm_beam_sample_mt.restype = C.c_int64
+        L.orc_warm_beam_sample_philox.restype = C.c_int64
         L.orc_cold_beam_sample_philox.restype = C.c_int64
         L.orc_load_box_qs.restype = C.c_int64
         L.orc_cold_beam_num_sim.argtypes = [C.POINTER(CMesh)] + [C.c_double] * 5
@@ -85,6 +87,9 @@ def lib():
         L.orc_solve_nrpcg.argtypes = [C.POINTER(CMesh), ip, dp, dp, C.c_double, C.c_double, C.c_double,
                                       C.c_uint, C.c_double, C.c_int, C.c_double, C.POINTER(CSolveInfo)]
         L.orc_cold_beam_sample_mt.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles)] + [C.c_double] * 6 + [C.POINTER(CMT)]
+        L.orc_warm_beam_sample_mt.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles)] + [C.c_double] * 7 + [C.POINTER(CMT)]
+        L.orc_warm_beam_sample_philox.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles)] + [C.c_double] * 7 + \
+            [C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_cold_beam_sample_philox.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles)] + [C.c_double] * 6 + \
                                                  [C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_load_box_qs.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles), dp, dp, C.c_double,
@@ -226,6 +231,24 @@ class Species:
         p = self._c()
         added = lib().orc_cold_beam_sample_philox(C.byref(self.world.m), _dp(self.world.ef), C.byref(p), self.charge,
                                                   self.mass, self.mpw0, v_drift, den, dt, seed, stream, step)
+        self.np = p.np
+        return added
+
+    def sample_warm_beam_mt(self, v_drift, den, T, dt, mt):
+        n_max = int(lib().orc_cold_beam_num_sim(C.byref(self.world.m), den, v_drift, dt, self.mpw0, 1.0)) + 1
+        self.reserve(self.np + n_max)
+        p = self._c()
+        added = lib().orc_warm_beam_sample_mt(C.byref(self.world.m), _dp(self.world.ef), C.byref(p), self.charge, self.mass,
+                                              self.mpw0, v_drift, den, T, dt, C.byref(mt))
+        self.np = p.np
+        return added
+
+    def sample_warm_beam_philox(self, v_drift, den, T, dt, seed, stream, step):
+        n_max = int(lib().orc_cold_beam_num_sim(C.byref(self.world.m), den, v_drift, dt, self.mpw0, 1.0)) + 1
+        self.reserve(self.np + n_max)
+        p = self._c()
+        added = lib().orc_warm_beam_sample_philox(C.byref(self.world.m), _dp(self.world.ef), C.byref(p), self.charge,
+                                                  self.mass, self.mpw0, v_drift, den, T, dt, seed, stream, step)
         self.np = p.np
         return added
 

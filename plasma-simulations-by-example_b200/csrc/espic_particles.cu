@@ -923,21 +923,42 @@ __device__ __forceinline__ void philox_uniform2(uint64_t seed, uint32_t stream, 
 }
 
 struct AddSrc {
-    int philox;                 // 1: cold beam from Philox, 0: staged host particles
+    int philox;                 // 0: staged host particles, 1: cold beam from Philox, 2: warm (Maxwellian) beam from Philox
     const double *in[7];
     uint64_t seed; uint32_t stream, step;
     double Lx, Ly, v_drift, mpw0;
+    double v_th;                // sqrt(2*K*T/mass), warm beam only
 };
 
 __device__ __forceinline__ void add_candidate(const MeshC &m, const AddSrc &a, long long i, double q[7])
 {
-    if (a.philox) {
+    if (a.philox == 1) {
         double u0, u1;
         philox_uniform2(a.seed, a.stream, a.step, (uint64_t)i, u0, u1);
         q[0] = m.x0[0] + u0 * a.Lx;       // Source.cpp:22
         q[1] = m.x0[1] + u1 * a.Ly;
         q[2] = m.x0[2];
         q[3] = 0; q[4] = 0; q[5] = a.v_drift;
+        q[6] = a.mpw0;
+    } else if (a.philox == 2) {
+        // WarmBeamSource::sample (ch4/Source.cpp:48-55) with Species::sampleIsotropicVel / sampleVth (ch4/Species.cpp:149-173).
+        // Seven Philox blocks per particle, idx = 8*i + j: (x, y), (theta, cosine), then the nine Birdsall uniforms.
+        double w[14];
+#pragma unroll
+        for (int j = 0; j < 7; j++) philox_uniform2(a.seed, a.stream, a.step, 8 * (uint64_t)i + j, w[2 * j], w[2 * j + 1]);
+        q[0] = m.x0[0] + w[0] * a.Lx;
+        q[1] = m.x0[1] + w[1] * a.Ly;
+        q[2] = m.x0[2];
+        const double theta = 2 * 3.141592653 * w[2];          // Const::PI as the reference spells it
+        const double r = -1.0 + 2 * w[3];
+        const double sc = sqrt(1 - r * r);
+        const double v1 = a.v_th * (w[4] + w[5] + w[6] - 1.5);
+        const double v2 = a.v_th * (w[7] + w[8] + w[9] - 1.5);
+        const double v3 = a.v_th * (w[10] + w[11] + w[12] - 1.5);
+        const double mag = 3 / sqrt(2.0 + 2 + 2) * sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+        q[3] = r * mag;
+        q[4] = cos(theta) * sc * mag;
+        q[5] = sin(theta) * sc * mag + a.v_drift;
         q[6] = a.mpw0;
     } else {
 #pragma unroll
@@ -1047,6 +1068,37 @@ extern "C" int espic_inject_cold_beam(espic_ctx *c, int sp, double v_drift, doub
     memset(&a, 0, sizeof(a));
     a.philox = 1; a.seed = seed; a.stream = stream; a.step = step;
     a.Lx = Lx; a.Ly = Ly; a.v_drift = v_drift; a.mpw0 = s.mpw0;
+    if (s.mpw0 > s.mpw_max) s.mpw_max = s.mpw0;
+    return add_common(c, sp, a, num_sim, dt, n_added);
+}
+
+// WarmBeamSource::sample (ch4/Source.cpp:31-56): same draw count and admission as the cold beam, Maxwellian velocities
+extern "C" int espic_inject_warm_beam(espic_ctx *c, int sp, double v_drift, double den, double T, double dt,
+                                      uint64_t seed, uint32_t stream, uint32_t step, long long *n_added)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[sp];
+    const MeshC &m = c->m;
+    double Lx = m.dh[0] * (m.ni - 1);
+    double Ly = m.dh[1] * (m.nj - 1);
+    double A = Lx * Ly;
+    double num_real = den * v_drift * A * dt;
+    uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = step, c3 = stream, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    uint64_t a64 = ((uint64_t)c1 << 32) | c0;
+    double u = (double)(a64 >> 11) * (1.0 / 9007199254740992.0);
+    long long num_sim = (int)(num_real / s.mpw0 + u);
+    AddSrc a;
+    memset(&a, 0, sizeof(a));
+    a.philox = 2; a.seed = seed; a.stream = stream; a.step = step;
+    a.Lx = Lx; a.Ly = Ly; a.v_drift = v_drift; a.mpw0 = s.mpw0;
+    a.v_th = sqrt(2 * 1.380648e-23 * T / s.mass);          // Const::K (ch4/World.h:18), Species.cpp:152
     if (s.mpw0 > s.mpw_max) s.mpw_max = s.mpw0;
     return add_common(c, sp, a, num_sim, dt, n_added);
 }

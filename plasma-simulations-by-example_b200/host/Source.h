@@ -8,7 +8,14 @@
 #include "Species.h"
 #include "World.h"
 
-class ColdBeamSource {
+// base class of ch4 (ch4/Source.h:8-13); the ch3/ch9 programs use ColdBeamSource by value and never see it
+class Source {
+public:
+    virtual void sample() = 0;
+    virtual ~Source() {}
+};
+
+class ColdBeamSource : public Source {
 public:
     ColdBeamSource(Species &species, World &world, double v_drift, double den)
         : sp{species}, world{world}, v_drift{v_drift}, den{den}, stream{world.next_source_stream()} {}
@@ -20,6 +27,22 @@ protected:
     double v_drift;
     double den;
     unsigned stream;      // Philox stream id: one per source so that sources never share random numbers
+};
+
+// Maxwellian beam at temperature T (ch4/Source.h:32-46, Source.cpp:31-56): espic_inject_warm_beam
+class WarmBeamSource : public Source {
+public:
+    WarmBeamSource(Species &species, World &world, double v_drift, double den, double T)
+        : sp{species}, world{world}, v_drift{v_drift}, den{den}, T{T}, stream{world.next_source_stream()} {}
+    void sample();
+
+protected:
+    Species &sp;
+    World &world;
+    double v_drift;
+    double den;
+    double T;
+    unsigned stream;
 };
 
 #endif
