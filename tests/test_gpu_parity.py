@@ -458,3 +458,67 @@ def test_properties_at_baseline_size():
     assert np.all((part[0] - 0.0) ** 2 + part[1] ** 2 + (part[2] - 0.15) ** 2 > 0.05 ** 2)
     assert d[4] < ke0
     e.close()
+
+
+def test_properties_at_full_baseline_size():
+    """BASELINE configs[3] at FULL size: 128^3 mesh, 2e8 ions (11.2 GB of particles, generated on the device like bench.py
+    does).  No oracle can run this in seconds, so only size-independent properties are checked: charge conservation of the
+    scatter, bit-reproducibility and order-independence of the fixed-point scatter, count/weight conservation of push +
+    removal with the production kernel path (push -> cell sort -> deposit), idempotence of the Poisson solve."""
+    import sys
+    import torch
+    sys.path.insert(0, sf.ROOT)
+    import bench as B
+    es = _espic()
+    n = 200_000_000
+    mpw = 1e12 * 0.016 / n
+    e = es.Engine(128, 128, 128, B.X0, B.XM)
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    e.add_sphere(*B.SPHERE)
+    e.add_inlet()
+    e.set_reference_values(B.PHI0, B.TE0, B.N0)
+    sp = e.add_species(16 * AMU, QE, mpw, capacity=n + 1024)
+    t = B.make_particles_device(torch, n, 4242, mpw, torch.device("cuda", 0))
+    e.upload_device(sp, [t[c].data_ptr() for c in range(7)], n, mpw)
+    e.sync()
+    del t
+    torch.cuda.empty_cache()
+    vol = e.field(es.NODE_VOL)
+    total = e.diag(sp)[0]
+    assert abs(total / (n * mpw) - 1) < 1e-12
+    e.deposit(sp, es.DEPOSIT_FP64)                       # unsorted input: the tile-grouping kernel
+    den = e.field(es.DEN, sp)
+    assert abs((den * vol).sum() / total - 1) < 1e-12, "trilinear weights sum to one: the scatter conserves charge"
+    e.deposit(sp, es.DEPOSIT_FIXED)
+    fixed = e.field(es.DEN, sp)
+    assert np.abs(fixed - den).max() <= 1e-10 * den.max()
+    e.sort_by_cell(sp)
+    e.deposit(sp, es.DEPOSIT_FIXED)                      # sorted input: the warp-merge kernel
+    assert_bits(e.field(es.DEN, sp), fixed, "fixed-point scatter: same bits for another particle order and another kernel")
+    # the production step: push -> (sort) -> deposit -> rho -> multigrid Newton-PCG -> E
+    e.compute_charge_density()
+    e.solve(es.SOLVE_QN, 1, 1.0)
+    info = e.solve(es.SOLVE_PCG_MG, 5000, 1e-4)
+    assert info["converged"] == 1
+    e.compute_ef()
+    before = e.count(sp)
+    for step in range(3):
+        e.push(sp, 1e-7, es.WALL_ABSORB, 0)
+        if step == 1:
+            e.sort_by_cell(sp)
+        e.deposit(sp, es.DEPOSIT_FP64)
+    after = e.count(sp)
+    d = e.diag(sp)
+    assert 0 < before - after < 0.02 * before, "a few particles leave through the walls / hit the sphere, none is duplicated"
+    assert abs(d[0] / (after * mpw) - 1) < 1e-12, "every survivor still carries its weight"
+    den3 = e.field(es.DEN, sp)
+    assert abs((den3 * vol).sum() / d[0] - 1) < 1e-12
+    e.compute_charge_density()
+    first = e.solve(es.SOLVE_PCG_MG, 5000, 1e-4)
+    phi1 = e.field(es.PHI)
+    again = e.solve(es.SOLVE_PCG_MG, 5000, 1e-4)          # same rho: the solve is (nearly) idempotent
+    phi2 = e.field(es.PHI)
+    assert first["converged"] == 1 and again["converged"] == 1
+    assert again["lin_iters"] <= first["lin_iters"] // 2 + 1
+    assert np.abs(phi2 - phi1).max() <= 2e-3, "a converged potential moves by less than the Newton tolerance when re-solved"
+    e.close()
