@@ -18,6 +18,8 @@
  *     positions, velocities, kill masks, particle order, E and rho-from-density are bit-identical to
  *     the reference; reductions (deposition sums, dot products, diagnostics) differ by summation order only.
  *   - calls are asynchronous on the context's stream unless they return a host value.
+ *   - a context is bound to one device and is not thread-safe: drive it from one host thread (the reference's drivers are
+ *     single-threaded); several contexts (one per GPU / process) are independent.
  */
 #ifndef ESPIC_H
 #define ESPIC_H
