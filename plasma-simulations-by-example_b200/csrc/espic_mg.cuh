@@ -22,6 +22,10 @@
 
 struct MgLevel {
     int ni, nj, nk;
+    int fi, fj, fk;           // log2 of the coarsening factor from the next finer level to this one, per dimension (0 or 1):
+                              // a direction whose spacing is already > sqrt(2) x the smallest one is not coarsened (semi-
+                              // coarsening: the reference mesh has dz = 2 dx, a 4:4:1 anisotropic stencil on which point
+                              // smoothers with full coarsening converge ~1.4x slower)
     long long nn;
     double *diag, *minv;      // Galerkin diagonal and its inverse (0 on nodes without unknowns)
     double *cx, *cy, *cz;     // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
@@ -64,16 +68,16 @@ __global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const u
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
     double lx = 0, ly = 0, lz = 0;
-    for (int dk = 0; dk < 2; dk++)
-        for (int dj = 0; dj < 2; dj++)
-            for (int di = 0; di < 2; di++) {
-                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+    for (int dk = 0; dk <= C.fk; dk++)
+        for (int dj = 0; dj <= C.fj; dj++)
+            for (int di = 0; di <= C.fi; di++) {
+                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                 const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
                 if (type[u] != NT_REG) continue;
-                if (di == 1 && i + 1 < s.ni && type[u + 1] == NT_REG) lx += s.gdx2;
-                if (dj == 1 && j + 1 < s.nj && type[u + s.sj] == NT_REG) ly += s.gdy2;
-                if (dk == 1 && k + 1 < s.nk && type[u + s.sk] == NT_REG) lz += s.gdz2;
+                if (di == C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) lx += s.gdx2;
+                if (dj == C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) ly += s.gdy2;
+                if (dk == C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) lz += s.gdz2;
             }
     C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
 }
@@ -85,15 +89,15 @@ __global__ void __launch_bounds__(256) k_mg_links_from_links(MgLevel F, MgLevel 
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
     double lx = 0, ly = 0, lz = 0;
-    for (int dk = 0; dk < 2; dk++)
-        for (int dj = 0; dj < 2; dj++)
-            for (int di = 0; di < 2; di++) {
-                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+    for (int dk = 0; dk <= C.fk; dk++)
+        for (int dj = 0; dj <= C.fj; dj++)
+            for (int di = 0; di <= C.fi; di++) {
+                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
                 const long long u = ((long long)k * F.nj + j) * F.ni + i;
-                if (di == 1) lx += F.cx[u];
-                if (dj == 1) ly += F.cy[u];
-                if (dk == 1) lz += F.cz[u];
+                if (di == C.fi) lx += F.cx[u];
+                if (dj == C.fj) ly += F.cy[u];
+                if (dk == C.fk) lz += F.cz[u];
             }
     C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
 }
@@ -105,17 +109,17 @@ __global__ void __launch_bounds__(256) k_mg_diag_from_fine(StencilC s, const uin
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
     double d = 0;
-    for (int dk = 0; dk < 2; dk++)
-        for (int dj = 0; dj < 2; dj++)
-            for (int di = 0; di < 2; di++) {
-                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+    for (int dk = 0; dk <= C.fk; dk++)
+        for (int dj = 0; dj <= C.fj; dj++)
+            for (int di = 0; di <= C.fi; di++) {
+                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                 const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
                 if (type[u] != NT_REG) continue;
                 d += diagJ[u];
-                if (di == 0 && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
-                if (dj == 0 && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
-                if (dk == 0 && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
+                if (di < C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
+                if (dj < C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
+                if (dk < C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
             }
     C.diag[I] = d;
     C.minv[I] = d > 0 ? 1.0 / d : 0.0;
@@ -127,16 +131,16 @@ __global__ void __launch_bounds__(256) k_mg_diag_from_level(MgLevel F, MgLevel C
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
     double d = 0;
-    for (int dk = 0; dk < 2; dk++)
-        for (int dj = 0; dj < 2; dj++)
-            for (int di = 0; di < 2; di++) {
-                const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+    for (int dk = 0; dk <= C.fk; dk++)
+        for (int dj = 0; dj <= C.fj; dj++)
+            for (int di = 0; di <= C.fi; di++) {
+                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
                 const long long u = ((long long)k * F.nj + j) * F.ni + i;
                 d += F.diag[u];
-                if (di == 0 && i + 1 < F.ni) d -= 2 * F.cx[u];
-                if (dj == 0 && j + 1 < F.nj) d -= 2 * F.cy[u];
-                if (dk == 0 && k + 1 < F.nk) d -= 2 * F.cz[u];
+                if (di < C.fi && i + 1 < F.ni) d -= 2 * F.cx[u];
+                if (dj < C.fj && j + 1 < F.nj) d -= 2 * F.cy[u];
+                if (dk < C.fk && k + 1 < F.nk) d -= 2 * F.cz[u];
             }
     C.diag[I] = d;
     C.minv[I] = d > 0 ? 1.0 / d : 0.0;
@@ -276,7 +280,8 @@ __device__ __forceinline__ void mg_down0(const Own &own, const StencilC &s, cons
                 for (int dj = 0; dj < 2; dj++)
 #pragma unroll
                     for (int di = 0; di < 2; di++) {
-                        const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                        if (di > C.fi || dj > C.fj || dk > C.fk) continue;
+                        const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                         if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                         const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
                         const double dg = diag[u];
@@ -313,8 +318,9 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
         double res = 0;
         if (live) {
             const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-            const int i = 2 * ci + (c & 1), j = 2 * cj + ((c >> 1) & 1), k = 2 * ck + (c >> 2);
-            if (i < F.ni && j < F.nj && k < F.nk) {
+            const int di = c & 1, dj = (c >> 1) & 1, dk = c >> 2;
+            const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
+            if (di <= C.fi && dj <= C.fj && dk <= C.fk && i < F.ni && j < F.nj && k < F.nk) {
                 const long long u = ((long long)k * F.nj + j) * F.ni + i;
                 const double mi = F.minv[u];
                 double xu = 0;
@@ -384,7 +390,7 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
     const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
     auto val = [&](long long v, int vi, int vj, int vk) {
         // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
-        return F.x[v] + e[((long long)(vk >> 1) * C.nj + (vj >> 1)) * C.ni + (vi >> 1)];
+        return F.x[v] + e[((long long)(vk >> C.fk) * C.nj + (vj >> C.fj)) * C.ni + (vi >> C.fi)];
     };
     if (count * 2 > stride) {          // a big level: one thread per node keeps every lane busy
         for (long long u = first + t0; u < first + count; u += stride) {
@@ -443,19 +449,20 @@ __device__ __forceinline__ double mg_up0(const Own &own, const StencilC &s, cons
             for (int dj = 0; dj < 2; dj++)
 #pragma unroll
                 for (int di = 0; di < 2; di++) {
-                    const int i = 2 * ci + di, j = 2 * cj + dj, k = 2 * ck + dk;
+                    if (di > C.fi || dj > C.fj || dk > C.fk) continue;
+                    const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                     if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                     const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
                     const unsigned m = nbmask[u];
                     double zu = 0;
                     if (m & 64u) {
                         // the neighbour on the inner side of the aggregate shares e0, the outer one takes the next aggregate's
-                        const double vxm = (m & 1u) ? x0[u - 1] + (di ? e0 : exm) : 0.0;
-                        const double vxp = (m & 2u) ? x0[u + 1] + (di ? exp_ : e0) : 0.0;
-                        const double vym = (m & 4u) ? x0[u - s.sj] + (dj ? e0 : eym) : 0.0;
-                        const double vyp = (m & 8u) ? x0[u + s.sj] + (dj ? eyp : e0) : 0.0;
-                        const double vzm = (m & 16u) ? x0[u - s.sk] + (dk ? e0 : ezm) : 0.0;
-                        const double vzp = (m & 32u) ? x0[u + s.sk] + (dk ? ezp : e0) : 0.0;
+                        const double vxm = (m & 1u) ? x0[u - 1] + (di > 0 ? e0 : exm) : 0.0;
+                        const double vxp = (m & 2u) ? x0[u + 1] + (di < C.fi ? e0 : exp_) : 0.0;
+                        const double vym = (m & 4u) ? x0[u - s.sj] + (dj > 0 ? e0 : eym) : 0.0;
+                        const double vyp = (m & 8u) ? x0[u + s.sj] + (dj < C.fj ? e0 : eyp) : 0.0;
+                        const double vzm = (m & 16u) ? x0[u - s.sk] + (dk > 0 ? e0 : ezm) : 0.0;
+                        const double vzp = (m & 32u) ? x0[u + s.sk] + (dk < C.fk ? e0 : ezp) : 0.0;
                         const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
                         const double xu = x0[u] + e0;
                         zu = xu + MG_OMEGA * minv[u] * (r[u] - (diag[u] * xu - off));
@@ -652,15 +659,23 @@ __global__ void __launch_bounds__(512, 2) k_mg_pcg_slab(MgPcgArgs a, OwnSlab own
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 
-// number of levels and their dimensions for an (ni,nj,nk) mesh
-static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3])
+// number of levels, their dimensions and per-dimension coarsening shifts for an (ni,nj,nk) mesh with spacings dh
+static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3], int shifts[MG_MAX_LEVELS][3])
 {
-    int ni = s.ni, nj = s.nj, nk = s.nk, nlev = 1;
-    dims[0][0] = ni; dims[0][1] = nj; dims[0][2] = nk;
+    int n[3] = {s.ni, s.nj, s.nk}, nlev = 1;
+    // spacing from the stencil coefficients: g = 1/dh^2
+    double h[3] = {1.0 / sqrt(s.gdx2), 1.0 / sqrt(s.gdy2), 1.0 / sqrt(s.gdz2)};
+    for (int a = 0; a < 3; a++) { dims[0][a] = n[a]; shifts[0][a] = 0; }
+    static const bool semi = getenv("ESPIC_MG_FULL_COARSENING") == nullptr;
     // halve (rounding up) while every dimension stays > 4 and the level is worth a barrier
-    while (nlev < MG_MAX_LEVELS && std::min(ni, std::min(nj, nk)) > 4 && (long long)ni * nj * nk > MG_COARSEST_NODES) {
-        ni = (ni + 1) / 2; nj = (nj + 1) / 2; nk = (nk + 1) / 2;
-        dims[nlev][0] = ni; dims[nlev][1] = nj; dims[nlev][2] = nk;
+    while (nlev < MG_MAX_LEVELS && std::min(n[0], std::min(n[1], n[2])) > 4 && (long long)n[0] * n[1] * n[2] > MG_COARSEST_NODES) {
+        const double hmin = std::min(h[0], std::min(h[1], h[2]));
+        for (int a = 0; a < 3; a++) {
+            const bool coarsen = !semi || h[a] <= 1.42 * hmin;
+            shifts[nlev][a] = coarsen ? 1 : 0;
+            if (coarsen) { n[a] = (n[a] + 1) / 2; h[a] *= 2; }
+            dims[nlev][a] = n[a];
+        }
         nlev++;
     }
     return nlev;
@@ -669,7 +684,8 @@ static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3])
 static long long mg_coarse_doubles(const StencilC &s)
 {
     long long dims[MG_MAX_LEVELS][3];
-    const int nlev = mg_level_dims(s, dims);
+    int shifts[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims, shifts);
     long long total = 0;
     for (int l = 1; l < nlev; l++) total += 8 * dims[l][0] * dims[l][1] * dims[l][2];
     return total;
@@ -685,7 +701,8 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *ext
     k_mg_nbmask<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->nbmask);
     LAUNCH_CHECK(c);
     long long dims[MG_MAX_LEVELS][3];
-    const int nlev = mg_level_dims(s, dims);
+    int shifts[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims, shifts);
     const long long total = mg_coarse_doubles(s);
     if (external) H->pool = external;
     else if (total > 0) CK(cudaMalloc(&H->pool, (size_t)total * sizeof(double)));
@@ -693,6 +710,7 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *ext
     for (int l = 0; l < nlev; l++) {
         MgLevel &L = H->L[l];
         L.ni = (int)dims[l][0]; L.nj = (int)dims[l][1]; L.nk = (int)dims[l][2];
+        L.fi = shifts[l][0]; L.fj = shifts[l][1]; L.fk = shifts[l][2];
         L.nn = dims[l][0] * dims[l][1] * dims[l][2];
         if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = nullptr; continue; }
         L.diag = p; p += L.nn; L.minv = p; p += L.nn; L.cx = p; p += L.nn; L.cy = p; p += L.nn; L.cz = p; p += L.nn;
@@ -850,10 +868,13 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     if (S->ready && S->geom_version == c->geom_version) return 0;
     if (S->ready) { espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: the geometry changed after the slab solver was set up"); return -1; }
     long long dims[MG_MAX_LEVELS][3];
-    const int nlev = mg_level_dims(s, dims);
-    const int unit = 1 << (nlev - 1);                 // fine planes per coarsest plane
+    int shifts[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims, shifts);
+    int kshift = 0;
+    for (int l = 1; l < nlev; l++) kshift += shifts[l][2];
+    const int unit = 1 << kshift;                     // fine planes per coarsest plane
     if (s.nk % (c->nranks * unit) != 0) {
-        espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: nk=%d must be a multiple of nranks*2^(levels-1) = %d", s.nk, c->nranks * unit);
+        espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: nk=%d must be a multiple of nranks*2^(k-coarsenings) = %d", s.nk, c->nranks * unit);
         return -1;
     }
     const int planes = s.nk / c->nranks;
@@ -894,9 +915,10 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
         own.peer[q] = (long long)((char *)S->peer_base[q] - (char *)S->pool);
     }
     for (int l = 0; l < MG_MAX_LEVELS; l++) { own.k0[l] = 0; own.k1[l] = 0; }
-    for (int l = 0; l < nlev; l++) {
-        own.k0[l] = (c->rank * planes) >> l;
-        own.k1[l] = (c->rank + 1 == c->nranks) ? (int)dims[l][2] : (((c->rank + 1) * planes) >> l);
+    for (int l = 0, sh = 0; l < nlev; l++) {
+        sh += shifts[l][2];
+        own.k0[l] = (c->rank * planes) >> sh;
+        own.k1[l] = (c->rank + 1 == c->nranks) ? (int)dims[l][2] : (((c->rank + 1) * planes) >> sh);
     }
     // ---- hierarchy inside the pool
     if ((r = mg_setup(c, s, &S->H, S->coarse))) return r;
