@@ -643,14 +643,17 @@ __device__ __forceinline__ void mg_pcg_body(MgPcgArgs &a, Own &own)
     if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; a.out[3] = l2_start; }
 }
 
-__global__ void __launch_bounds__(512, 2) k_mg_pcg(MgPcgArgs a)
+#ifndef MG_BLOCK
+#define MG_BLOCK 512
+#endif
+__global__ void __launch_bounds__(MG_BLOCK, 1024 / MG_BLOCK) k_mg_pcg(MgPcgArgs a)
 {
     OwnAll own;
     mg_pcg_body(a, own);
 }
 
 // slab-decomposed variant: one of these kernels per rank, running concurrently, talking through peer memory only
-__global__ void __launch_bounds__(512, 2) k_mg_pcg_slab(MgPcgArgs a, OwnSlab own, unsigned long long *epoch_io)
+__global__ void __launch_bounds__(MG_BLOCK, 1024 / MG_BLOCK) k_mg_pcg_slab(MgPcgArgs a, OwnSlab own, unsigned long long *epoch_io)
 {
     own.epoch = *epoch_io;
     mg_pcg_body(a, own);
@@ -752,9 +755,9 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         c->diag0_version = c->geom_version;
     }
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, 512, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, MG_BLOCK, 0));
     if (bps < 1) { espic_set_error("k_mg_pcg cannot be made resident"); return -1; }
-    long long want = (s.nn + 511) / 512;
+    long long want = (s.nn + MG_BLOCK - 1) / MG_BLOCK;
     int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
     if (3 * grid > 4096) grid = 4096 / 3;
     const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
@@ -789,7 +792,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
         a.rel_tol = (it == 0 && inexact) ? forcing * std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
         CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
         void *args[] = {&a};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(512), args, 0, c->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
         LAUNCH_CHECK(c);
         k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
         LAUNCH_CHECK(c);
@@ -945,7 +948,7 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         S->diag0_done = true;
     }
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg_slab, 512, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg_slab, MG_BLOCK, 0));
     if (bps < 1) { espic_set_error("k_mg_pcg_slab cannot be made resident"); return -1; }
     // the same grid on every rank (the partial-sum layout depends on it): all blocks the device can hold
     int grid = bps * c->sm_count;
@@ -981,7 +984,7 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         if ((r = espic_comm_allgather_doubles(c, S->part, 1))) return r;
         OwnSlab own = S->own;
         void *args[] = {&a, &own, &S->epoch};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg_slab, dim3(grid), dim3(512), args, 0, c->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg_slab, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
         LAUNCH_CHECK(c);
         // every rank needs the whole update: gather the slabs of delta
         if ((r = espic_comm_allgather_doubles(c, S->delta, (size_t)slab_nn))) return r;
