@@ -152,23 +152,26 @@ __device__ __forceinline__ long long particle_weights(const MeshC &m, double x, 
     return node_u(m, i, j, k);
 }
 
-template <int MODE>
+// STRIDE: distance (in elements) between consecutive nodes of the target array (3 for one component of an interleaved
+// vector field such as nv_sum, whose component offset is already added to acc)
+template <int MODE, int STRIDE = 1>
 __device__ __forceinline__ void red8(const MeshC &m, double *acc, long long u, const typename AccVal<MODE>::T w[8])
 {
     // four row bases, the +1 neighbours are immediate offsets
-    double *p00 = acc + u, *p10 = p00 + m.ni, *p01 = p00 + (long long)m.ni * m.nj, *p11 = p01 + m.ni;
+    double *p00 = acc + u * STRIDE, *p10 = p00 + (long long)m.ni * STRIDE, *p01 = p00 + (long long)m.ni * m.nj * STRIDE,
+           *p11 = p01 + (long long)m.ni * STRIDE;
     AccVal<MODE>::red(p00, 0, w[0]);
-    AccVal<MODE>::red(p00, 1, w[1]);
-    AccVal<MODE>::red(p10, 1, w[2]);
+    AccVal<MODE>::red(p00, STRIDE, w[1]);
+    AccVal<MODE>::red(p10, STRIDE, w[2]);
     AccVal<MODE>::red(p10, 0, w[3]);
     AccVal<MODE>::red(p01, 0, w[4]);
-    AccVal<MODE>::red(p01, 1, w[5]);
-    AccVal<MODE>::red(p11, 1, w[6]);
+    AccVal<MODE>::red(p01, STRIDE, w[5]);
+    AccVal<MODE>::red(p11, STRIDE, w[6]);
     AccVal<MODE>::red(p11, 0, w[7]);
 }
 
 // Whole-warp call.  u = lower node of the lane's cell (-1: nothing to deposit), w = its eight weights.
-template <int MODE>
+template <int MODE, int STRIDE = 1>
 __device__ __forceinline__ void warp_deposit(const MeshC &m, double *acc, long long u, typename AccVal<MODE>::T w[8])
 {
     const unsigned FULL = 0xffffffffu;
@@ -176,7 +179,7 @@ __device__ __forceinline__ void warp_deposit(const MeshC &m, double *acc, long l
     const long long up = __shfl_up_sync(FULL, u, 1);
     const unsigned heads = __ballot_sync(FULL, lane == 0 || up != u);
     if (heads == FULL) {                   // no two neighbours share a cell: nothing to combine
-        if (u >= 0) red8<MODE>(m, acc, u, w);
+        if (u >= 0) red8<MODE, STRIDE>(m, acc, u, w);
         return;
     }
     // last lane of this lane's run = lane before the next head
@@ -191,7 +194,7 @@ __device__ __forceinline__ void warp_deposit(const MeshC &m, double *acc, long l
             if (take) w[q] += t;
         }
     }
-    if (((heads >> lane) & 1u) && u >= 0) red8<MODE>(m, acc, u, w);
+    if (((heads >> lane) & 1u) && u >= 0) red8<MODE, STRIDE>(m, acc, u, w);
 }
 
 // two particles per thread (adjacent in memory: one 128-bit load per array), merged in registers when they share a cell
@@ -264,10 +267,13 @@ __global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restri
 #define DT_SLOT_BITS 10
 #define DT_EMPTY 0xffffffffu
 
-template <int MODE>
+// VAL selects what is scattered: 0 the weight mpw (number density), 1 mpw*v, 2 (mpw*v)*v with v = vcomp[] (velocity moments,
+// ch4 Species::sampleMoments: the same kernel runs once per sampled quantity)
+template <int MODE, int VAL = 0, int STRIDE = 1>
 __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
                                                               const double *__restrict__ z, const double *__restrict__ mpw,
-                                                              long long n, double *acc, double scale, int ahead)
+                                                              long long n, double *acc, double scale, int ahead,
+                                                              const double *__restrict__ vcomp = nullptr)
 {
     typedef typename AccVal<MODE>::T T;
     __shared__ double sx[DT_TILE], sy[DT_TILE], sz[DT_TILE], sw[DT_TILE];
@@ -291,6 +297,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         const long long g = base + p;
         double2 X = make_double2(0, 0), Y = X, Z = X, W = X;
         if (g < n) { X = ld2(x + g); Y = ld2(y + g); Z = ld2(z + g); W = ld2(mpw + g); }     // capacity is even: g+1 is allocated
+        if (VAL > 0 && g < n) {
+            const double2 V = ld2(vcomp + g);
+            W.x = W.x * V.x; W.y = W.y * V.y;                         // mpw*v
+            if (VAL == 2) { W.x = W.x * V.x; W.y = W.y * V.y; }       // (mpw*v)*v
+        }
         if (g + 1 >= n) W.y = 0;
         sx[p] = X.x; sx[p + 1] = X.y; sy[p] = Y.x; sy[p + 1] = Y.y;
         sz[p] = Z.x; sz[p + 1] = Z.y; sw[p] = W.x; sw[p + 1] = W.y;
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         else if (slot == 0xfffeu) {                        // table overflow: this particle deposits on its own
             T v[8];
             const long long u = particle_weights<MODE>(m, sx[p], sy[p], sz[p], sw[p], scale, v);
-            if (u >= 0) red8<MODE>(m, acc, u, v);
+            if (u >= 0) red8<MODE, STRIDE>(m, acc, u, v);
         }
     }
     __syncthreads();
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         T v[8];
         const long long u = particle_weights<MODE>(m, sx[p], sy[p], sz[p], sw[p], scale, v);
         if (u != ua) {
-            if (ua >= 0) red8<MODE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
+            if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
             ua = u;
 #pragma unroll
             for (int t = 0; t < 8; t++) a[t] = v[t];
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
             for (int t = 0; t < 8; t++) a[t] += v[t];
         }
     }
-    warp_deposit<MODE>(m, acc, ua, a);
+    warp_deposit<MODE, STRIDE>(m, acc, ua, a);
 }
 
 // den = acc / node_vol (0 where node_vol == 0): Field::operator/= (Field.h:125-134)
@@ -782,8 +793,26 @@ extern "C" int espic_sample_moments(espic_ctx *c, int sp)
     if ((r = espic_ensure_moments(c, sp))) return r;
     Species &s = c->sp[sp];
     if (s.np == 0) return 0;
-    k_sample_moments<<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], s.np, s.mom);
+    static const bool simple = getenv("ESPIC_MOMENTS_SIMPLE") != nullptr;
+    if (simple) {
+        k_sample_moments<<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], s.np, s.mom);
+        LAUNCH_CHECK(c);
+        return 0;
+    }
+    // one pass of the tile-grouping scatter per sampled quantity (7 x 32..40 B/particle of traffic, but no per-particle REDs)
+    const long long nn = c->m.nn;
+    const unsigned grid = nblk(s.np, DT_TILE);
+    const int ahead = 0;
+#define TILE_ARGS(dst, v) c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, (dst), 1.0, ahead, (v)
+    k_deposit_tile<ESPIC_DEPOSIT_FP64, 0, 1><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom, nullptr));              // n_sum
     LAUNCH_CHECK(c);
+    for (int q = 0; q < 3; q++) {
+        k_deposit_tile<ESPIC_DEPOSIT_FP64, 1, 3><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + nn + q, s.p[3 + q]));  // nv_sum
+        LAUNCH_CHECK(c);
+        k_deposit_tile<ESPIC_DEPOSIT_FP64, 2, 1><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + (4 + q) * nn, s.p[3 + q]));   // nuu, nvv, nww
+        LAUNCH_CHECK(c);
+    }
+#undef TILE_ARGS
     return 0;
 }
 
