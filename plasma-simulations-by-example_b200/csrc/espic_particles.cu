@@ -132,14 +132,12 @@ __device__ __forceinline__ void cell3(const MeshC &m, double x, double y, double
     cell_frac(z, m.x0[2], m.dh[2], m.rdh[2], m.nk, k, dk);
 }
 
-// the eight node weights in the reference's node order, each mpw*w_i*w_j*w_k multiplied left to right (Field.h:177-184)
+// the eight node weights in the reference's node order, each mpw*w_i*w_j*w_k multiplied left to right (Field.h:177-184),
+// from the cell fractions
 template <int MODE>
-__device__ __forceinline__ long long particle_weights(const MeshC &m, double x, double y, double z, double mpw, double scale,
-                                                      typename AccVal<MODE>::T w[8])
+__device__ __forceinline__ void weights_from_fractions(double di, double dj, double dk, double mpw, double scale,
+                                                       typename AccVal<MODE>::T w[8])
 {
-    int i, j, k; double di, dj, dk;
-    cell3(m, x, y, z, i, j, k, di, dj, dk);
-    if (i < 0 || j < 0 || k < 0) return -1;     // never for in-bounds particles; keeps stray input from writing out of range
     const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
     w[0] = AccVal<MODE>::quant(mpw * ai * aj * ak, scale);
     w[1] = AccVal<MODE>::quant(mpw * di * aj * ak, scale);
@@ -149,6 +147,16 @@ __device__ __forceinline__ long long particle_weights(const MeshC &m, double x, 
     w[5] = AccVal<MODE>::quant(mpw * di * aj * dk, scale);
     w[6] = AccVal<MODE>::quant(mpw * di * dj * dk, scale);
     w[7] = AccVal<MODE>::quant(mpw * ai * dj * dk, scale);
+}
+
+template <int MODE>
+__device__ __forceinline__ long long particle_weights(const MeshC &m, double x, double y, double z, double mpw, double scale,
+                                                      typename AccVal<MODE>::T w[8])
+{
+    int i, j, k; double di, dj, dk;
+    cell3(m, x, y, z, i, j, k, di, dj, dk);
+    if (i < 0 || j < 0 || k < 0) return -1;     // never for in-bounds particles; keeps stray input from writing out of range
+    weights_from_fractions<MODE>(di, dj, dk, mpw, scale, w);
     return node_u(m, i, j, k);
 }
 
@@ -257,7 +265,8 @@ __global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restri
 //   1. coalesced load of x,y,z,mpw into shared memory; each particle's cell is entered into a small open-addressing hash
 //      table (32-bit shared atomics) which hands out a slot per distinct cell; slots are counted;
 //   2. exclusive scan of the slot counts, then every particle id is written to its place in slot order (counting sort);
-//   3. each thread takes DT_PER consecutive entries of that order -- now runs of one cell -- recomputes the weights, merges
+//   3. each thread takes DT_PER consecutive entries of that order -- now runs of one cell -- forms the weights from the
+//      cell fractions step 1 left in shared memory (the cell itself is the slot's key), merges
 //      them in registers, the warp merges runs across lanes with shuffles, run heads issue the REDs.
 // REDs per tile drop from (#runs x 8) to about (#distinct cells x 8), independent of how scrambled the stream is.
 #define DT_THREADS 256
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(256) k_deposit(MeshC m, const double *__restri
 #define DT_SLOTS 1024                     // hash table entries (a tile of 1024 particles cannot touch more cells)
 #define DT_SLOT_BITS 10
 #define DT_EMPTY 0xffffffffu
+static_assert(DT_SLOTS >= DT_TILE && DT_SLOTS == (1 << DT_SLOT_BITS), "one hash slot per particle of the tile");
 
 // VAL selects what is scattered: 0 the weight mpw (number density), 1 mpw*v, 2 (mpw*v)*v with v = vcomp[] (velocity moments,
 // ch4 Species::sampleMoments: the same kernel runs once per sampled quantity)
@@ -308,20 +318,24 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             const double px = q ? X.y : X.x, py = q ? Y.y : Y.x, pz = q ? Z.y : Z.x, pw = q ? W.y : W.x;
-            // 0xffff: nothing to deposit, 0xfffe: table full.  Lanes with the same cell elect one leader that talks to the
+            // slot 0xffff: nothing to deposit (the table has a slot for every particle of the tile, it cannot fill up).  Lanes with the same cell elect one leader that talks to the
             // hash table (a freshly sorted tile would otherwise send 32 CAS + 32 adds to the same shared-memory word)
             uint32_t key = DT_EMPTY;
             if (pw != 0) {
                 int ci, cj, ck; double d0, d1, d2;
                 cell3(m, px, py, pz, ci, cj, ck, d0, d1, d2);
-                if (ci >= 0 && cj >= 0 && ck >= 0) key = (uint32_t)node_u(m, ci, cj, ck);
+                if (ci >= 0 && cj >= 0 && ck >= 0) {
+                    key = (uint32_t)node_u(m, ci, cj, ck);
+                    // from here on only the fractions are needed: they replace the position in shared memory, the cell is
+                    // recovered from the hash slot (hkey[slot] is the lower node index of the cell)
+                    sx[p + q] = d0; sy[p + q] = d1; sz[p + q] = d2;
+                }
             }
             const unsigned peers = __match_any_sync(0xffffffffu, key);
             const int leader = __ffs(peers) - 1;
             uint32_t slot = 0xffffu;
             if (key != DT_EMPTY && lane == leader) {
                 uint32_t h = (key * 2654435761u) >> (32 - DT_SLOT_BITS);
-                slot = 0xfffeu;
                 for (int probe = 0; probe < DT_SLOTS; probe++) {
                     const uint32_t old = atomicCAS(&hkey[h], DT_EMPTY, key);
                     if (old == DT_EMPTY || old == key) { slot = h; break; }
@@ -365,11 +379,6 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         if (slot < DT_SLOTS && lane == leader) at = atomicAdd(&hcnt[slot], (uint32_t)__popc(peers));
         at = __shfl_sync(0xffffffffu, at, leader);
         if (slot < DT_SLOTS) order[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)p;
-        else if (slot == 0xfffeu) {                        // table overflow: this particle deposits on its own
-            T v[8];
-            const long long u = particle_weights<MODE>(m, sx[p], sy[p], sz[p], sw[p], scale, v);
-            if (u >= 0) red8<MODE, STRIDE>(m, acc, u, v);
-        }
     }
     __syncthreads();
     // ---- 3. walk the grouped order: DT_PER consecutive entries per thread, merged in registers, then across the warp
@@ -384,7 +393,8 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         if (q >= M) break;
         const int p = order[q];
         T v[8];
-        const long long u = particle_weights<MODE>(m, sx[p], sy[p], sz[p], sw[p], scale, v);
+        const long long u = (long long)hkey[pslot[p]];
+        weights_from_fractions<MODE>(sx[p], sy[p], sz[p], sw[p], scale, v);
         if (u != ua) {
             if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
             ua = u;
