@@ -966,3 +966,179 @@ void orc_compute_ef(const orc_mesh *m, const double *phi, double *ef)
                 else ef[3 * u + 2] = -(phi[U(m, i, j, k + 1)] - phi[U(m, i, j, k - 1)]) / (2 * dz);
             }
 }
+
+/* ======================================================================================================
+ * ch4: Species::advance(neutrals, spherium) with surface interactions (ch4/Species.cpp:8-91),
+ * World::lineSphereIntersect (ch4/World.cpp:160-183), World::sphereDiffuseVector (:185-199),
+ * Species::sampleReflectedVelocity (ch4/Species.cpp:93-100), Species::sampleVth (:149-159).
+ *
+ * Particle::dt (ch4/Species.h:15) is carried in a separate array pdt[] parallel to the SoA particle arrays.
+ * Random numbers: mode 0 = the reference's sequential mt19937 stream (pinned against oracle/_ref/ref_ch4_surface),
+ * mode 1 = Philox counters shared with the CUDA engine: particle i, bounce/emission e use the six blocks
+ * idx = (i << 20) + 8*e + j (j = 0..5, e >= 1 for emissions); the two emission-count uniforms of ion i are block (i << 20).
+ * ====================================================================================================== */
+typedef struct {
+    const orc_surface_rng *cfg;
+    uint64_t base;      /* Philox: first block of the current group */
+    int k;              /* Philox: uniforms already taken from the group */
+} rng_cursor;
+
+static double rng_draw(rng_cursor *r)
+{
+    if (r->cfg->mode == 0) return orc_mt_uniform(r->cfg->mt);
+    double u2[2];
+    orc_philox_uniform2(r->cfg->seed, r->cfg->stream, r->cfg->step, r->base + (uint64_t)(r->k >> 1), u2);
+    return u2[(r->k++) & 1];
+}
+static void rng_seek(rng_cursor *r, uint64_t base, int k) { r->base = base; r->k = k; }
+
+double orc_line_sphere_intersect(const orc_mesh *m, const double x1[3], const double x2[3])
+{
+    double B[3], A[3];
+    for (int c = 0; c < 3; c++) { B[c] = x2[c] - x1[c]; A[c] = x1[c] - m->sphere_c[c]; }
+    double a = 0, b = 0, cc = 0;
+    for (int c = 0; c < 3; c++) a += B[c] * B[c];
+    for (int c = 0; c < 3; c++) b += A[c] * B[c];
+    b = 2 * b;
+    for (int c = 0; c < 3; c++) cc += A[c] * A[c];
+    cc = cc - m->sphere_r2;
+    double det = b * b - 4 * a * cc;
+    if (det < 0) return 0.5;
+    double tp = (-b + sqrt(det)) / (2 * a);
+    if (tp < 0 || tp > 1.0) {
+        tp = (-b - sqrt(det)) / (2 * a);
+        if (tp < 0 || tp > 1.0) tp = 0.5;
+    }
+    return tp;
+}
+
+static void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* u[0..8]: the nine sampleVth uniforms, u[9]: sin_theta, u[10]: psi/(2 pi) */
+void orc_reflected_velocity(const orc_mesh *m, const double pos[3], double v_mag1, double mass, const double u[11], double vel[3])
+{
+    const double K = 1.380648e-23, PI = 3.141592653;
+    /* sampleVth(1000) */
+    double v_th = sqrt(2 * K * 1000 / mass);
+    double v1 = v_th * (u[0] + u[1] + u[2] - 1.5);
+    double v2 = v_th * (u[3] + u[4] + u[5] - 1.5);
+    double v3 = v_th * (u[6] + u[7] + u[8] - 1.5);
+    double vth = 3 / sqrt(2 + 2 + 2) * sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    const double a_th = 1;
+    double v_mag2 = v_mag1 + a_th * (vth - v_mag1);
+    /* sphereDiffuseVector(pos) */
+    double sin_theta = u[9];
+    double cos_theta = sqrt(1 - sin_theta * sin_theta);
+    double psi = 2 * PI * u[10];
+    double n[3], t1[3], t2[3], d[3];
+    for (int c = 0; c < 3; c++) d[c] = pos[c] - m->sphere_c[c];
+    double s = 0;
+    for (int c = 0; c < 3; c++) s += d[c] * d[c];
+    double mg = sqrt(s);
+    for (int c = 0; c < 3; c++) n[c] = d[c] / mg;
+    const double ex[3] = { 1, 0, 0 }, ey[3] = { 0, 1, 0 };
+    double dn = 0;
+    for (int c = 0; c < 3; c++) dn += n[c] * ex[c];
+    if (dn != 0) cross3(n, ex, t1); else cross3(n, ey, t1);
+    cross3(n, t1, t2);
+    double cp = sin_theta * cos(psi), sp = sin_theta * sin(psi);
+    for (int c = 0; c < 3; c++) {
+        double r = t1[c] * cp + t2[c] * sp + n[c] * cos_theta;       /* s*vec evaluates a(i)*s (ch4/Field.h:59-60) */
+        vel[c] = r * v_mag2;
+    }
+}
+
+static void draw_reflected(const orc_mesh *m, rng_cursor *r, const double pos[3], double v_mag1, double mass, double vel[3])
+{
+    double u[11];
+    for (int q = 0; q < 11; q++) u[q] = rng_draw(r);
+    orc_reflected_velocity(m, pos, v_mag1, mass, u, vel);
+}
+
+static int add_with_dt(const orc_mesh *m, const double *ef, orc_surface_target *t, const double pos[3], const double vel[3], double dt)
+{
+    int64_t before = t->p->np;
+    int ok = orc_add_particle(m, ef, t->p, pos, vel, t->mpw0, t->charge, t->mass, dt);
+    if (ok) t->pdt[before] = dt;          /* addParticle(pos,vel) -> dt = world.getDt() (ch4/Species.h:65) */
+    return ok;
+}
+
+int64_t orc_advance_surface(const orc_mesh *m, const double *ef, orc_particles *p, double *pdt, double charge, double mass,
+                            double mpw0, double dt, orc_surface_target *neutrals, orc_surface_target *sput,
+                            const orc_surface_rng *rng, int64_t emitted[2])
+{
+    rng_cursor rc = { rng, 0, 0 };
+    emitted[0] = emitted[1] = 0;
+    for (int64_t q = 0; q < p->np; q++) {
+        pdt[q] += dt;
+        double pos[3] = { p->x[q], p->y[q], p->z[q] }, vel[3] = { p->vx[q], p->vy[q], p->vz[q] };
+        double lc[3], e[3];
+        orc_xtol(m, pos, lc);
+        orc_gather3(m, ef, lc, e);
+        const double s = pdt[q] * charge / mass;
+        for (int c = 0; c < 3; c++) vel[c] += e[c] * s;
+        int64_t bounce = 0;
+        while (pdt[q] > 0 && p->mpw[q] > 0) {
+            double pos_old[3] = { pos[0], pos[1], pos[2] };
+            for (int c = 0; c < 3; c++) pos[c] += vel[c] * pdt[q];
+            if (!orc_in_bounds(m, pos)) {
+                p->mpw[q] = 0;
+            } else if (orc_in_sphere(m, pos)) {
+                double tp = orc_line_sphere_intersect(m, pos_old, pos);
+                double dt_rem = (1 - tp) * pdt[q];
+                pdt[q] -= dt_rem;
+                const double f = 0.999 * tp;
+                for (int c = 0; c < 3; c++) pos[c] = pos_old[c] + (pos[c] - pos_old[c]) * f;
+                double v2 = 0;
+                for (int c = 0; c < 3; c++) v2 += vel[c] * vel[c];
+                double v_mag1 = sqrt(v2);
+                if (charge == 0) {
+                    rng_seek(&rc, ((uint64_t)q << 20) + 8 * (uint64_t)bounce, 0);
+                    draw_reflected(m, &rc, pos, v_mag1, mass, vel);
+                    bounce++;
+                } else {
+                    double mpw_ratio = mpw0 / neutrals->mpw0;
+                    p->mpw[q] = 0;
+                    rng_seek(&rc, (uint64_t)q << 20, 0);
+                    int mp_create = (int)(mpw_ratio + rng_draw(&rc));
+                    for (int i = 0; i < mp_create; i++) {
+                        double v[3];
+                        rng_seek(&rc, ((uint64_t)q << 20) + 8 * (uint64_t)(1 + i), 0);
+                        draw_reflected(m, &rc, pos, v_mag1, mass, v);
+                        emitted[0] += add_with_dt(m, ef, neutrals, pos, v, dt);
+                    }
+                    double sput_yield = (v_mag1 > 5000) ? 0.1 : 0;
+                    double sput_mpw_ratio = sput_yield * mpw0 / sput->mpw0;
+                    rng_seek(&rc, (uint64_t)q << 20, 1);
+                    int sput_mp_create = (int)(sput_mpw_ratio + rng_draw(&rc));
+                    for (int i = 0; i < sput_mp_create; i++) {
+                        double v[3];
+                        rng_seek(&rc, ((uint64_t)q << 20) + 8 * (uint64_t)(1 + mp_create + i), 0);
+                        draw_reflected(m, &rc, pos, v_mag1, mass, v);
+                        emitted[1] += add_with_dt(m, ef, sput, pos, v, dt);
+                    }
+                }
+                continue;
+            }
+            pdt[q] = 0;
+        }
+        p->x[q] = pos[0]; p->y[q] = pos[1]; p->z[q] = pos[2];
+        p->vx[q] = vel[0]; p->vy[q] = vel[1]; p->vz[q] = vel[2];
+    }
+    /* removal, ch4/Species.cpp:77-88 (the whole Particle incl. dt moves) */
+    int64_t np = p->np;
+    for (int64_t q = 0; q < np; q++) {
+        if (p->mpw[q] > 0) continue;
+        copy_particle(p, q, np - 1);
+        pdt[q] = pdt[np - 1];
+        np--;
+        q--;
+    }
+    p->np = np;
+    return np;
+}

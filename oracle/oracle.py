@@ -43,6 +43,15 @@ class CSolveInfo(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class CSurfaceRng(C.Structure):
+    _fields_ = [("mode", C.c_int), ("mt", C.c_void_p), ("seed", C.c_uint64), ("stream", C.c_uint32), ("step", C.c_uint32)]
+
+
+class CSurfaceTarget(C.Structure):
+    _fields_ = [("p", C.POINTER(CParticles)), ("pdt", C.POINTER(C.c_double)),
+                ("charge", C.c_double), ("mass", C.c_double), ("mpw0", C.c_double)]
+
+
 class CMT(C.Structure):
     _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int)]
 
@@ -96,6 +105,11 @@ def lib():
                                       C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double]
         L.orc_philox_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, dp]
         L.orc_add_particle.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles), dp, dp] + [C.c_double] * 4
+        L.orc_advance_surface.restype = C.c_int64
+        L.orc_advance_surface.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles), dp] + [C.c_double] * 4 + \
+            [C.POINTER(CSurfaceTarget), C.POINTER(CSurfaceTarget), C.POINTER(CSurfaceRng), C.POINTER(C.c_int64)]
+        L.orc_line_sphere_intersect.restype = C.c_double
+        L.orc_line_sphere_intersect.argtypes = [C.POINTER(CMesh), dp, dp]
         _lib = L
     return _lib
 
@@ -119,6 +133,7 @@ class Species:
         self.cap = 0
         self.np = 0
         self.arr = np.zeros((7, 0))
+        self.pdt = np.zeros(0)              # ch4 Particle::dt (Species.h:15), used by advance_surface only
         self.reserve(cap)
         self.den = np.zeros(world.nn)
         self.den_ave = np.zeros(world.nn)
@@ -129,7 +144,9 @@ class Species:
             return
         new = np.zeros((7, cap))
         new[:, :self.np] = self.arr[:, :self.np]
-        self.arr, self.cap = new, cap
+        pdt = np.zeros(cap)
+        pdt[:self.np] = self.pdt[:self.np]
+        self.arr, self.pdt, self.cap = new, pdt, cap
 
     def set_particles(self, soa):
         soa = np.ascontiguousarray(soa, dtype=np.float64)
@@ -152,6 +169,33 @@ class Species:
     def advance(self, dt):
         p = self._c()
         self.np = lib().orc_advance_sphere(C.byref(self.world.m), _dp(self.world.ef), C.byref(p), self.charge, self.mass, dt)
+
+    def advance_surface(self, dt, neutrals, sput, rng, headroom=None):
+        """ch4 Species::advance(neutrals, spherium).  rng = ("mt", CMT) or ("philox", seed, stream, step).
+        Returns (emitted into neutrals, emitted into sput)."""
+        targets = [neutrals] if sput is neutrals else [neutrals, sput]
+        for t in targets:
+            if t is not self:
+                t.reserve(t.np + (headroom if headroom is not None else 4 * self.np + 64))
+        p = self._c()
+        cps = {id(self): p}
+        for t in targets:
+            if id(t) not in cps:
+                cps[id(t)] = t._c()
+        def target(t):
+            return CSurfaceTarget(C.pointer(cps[id(t)]), _dp(t.pdt), t.charge, t.mass, t.mpw0)
+        tn, ts = target(neutrals), target(sput)
+        r = CSurfaceRng()
+        if rng[0] == "mt":
+            r.mode, r.mt = 0, C.cast(C.pointer(rng[1]), C.c_void_p)
+        else:
+            r.mode, r.seed, r.stream, r.step = 1, rng[1], rng[2], rng[3]
+        em = (C.c_int64 * 2)()
+        self.np = lib().orc_advance_surface(C.byref(self.world.m), _dp(self.world.ef), C.byref(p), _dp(self.pdt),
+                                            self.charge, self.mass, self.mpw0, dt, C.byref(tn), C.byref(ts), C.byref(r), em)
+        for t in targets:
+            t.np = cps[id(t)].np
+        return int(em[0]), int(em[1])
 
     def push_nocompact(self, dt):
         p = self._c()
