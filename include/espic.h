@@ -110,6 +110,21 @@ int espic_inject_cold_beam(espic_ctx *ctx, int sp, double v_drift, double den, d
 int espic_inject_warm_beam(espic_ctx *ctx, int sp, double v_drift, double den, double T, double dt,
                            uint64_t seed, uint32_t stream, uint32_t step, long long *n_added);
 
+/* ch4 Species::advance(neutrals, spherium) (ch4/Species.cpp:8-100): push with surface interactions.  Every particle runs the
+ * reference's sub-step loop: leave the box -> removed; enter the sphere -> World::lineSphereIntersect (ch4/World.cpp:160-183),
+ * step back to 0.999 of the way to the surface; a NEUTRAL species (charge 0) is re-emitted diffusely with the Birdsall speed of
+ * the 1000 K wall (sampleReflectedVelocity, Species.cpp:93-100; World::sphereDiffuseVector, ch4/World.cpp:185-199) and keeps
+ * moving for the rest of its step; an ION dies and appends (int)(mpw0/neutrals.mpw0 + R) particles to species `neutrals_sp`
+ * and (int)(yield*mpw0/sput.mpw0 + R) (yield 0.1 above 5 km/s impact speed) to species `sput_sp` through addParticle, in the
+ * reference's order; emitted[0], emitted[1] return those counts (their sum in emitted[0] when both targets are the same
+ * species).  Removal is the reference's swap-with-last order.  R comes from Philox counters keyed (seed, stream, step).
+ * Particle::dt (ch4/Species.h:15): particles added since the species' last advance move for 2*dt on their first step, as in the
+ * reference (addParticle(pos,vel) stores dt = world dt, advance adds another); the engine tracks them by index instead of an
+ * eighth array, so espic_sort_by_cell refuses to run between an injection and the next advance of such a species.
+ * For a neutral species neutrals_sp / sput_sp are ignored. */
+int espic_push_surface(espic_ctx *ctx, int sp, double dt, int neutrals_sp, int sput_sp,
+                       uint64_t seed, uint32_t stream, uint32_t step, long long emitted[2]);
+
 /* Species::getRealCount/getMomentum/getKE (Species.cpp:84-108): out = {sum mpw, px, py, pz, KE} */
 int espic_species_diag(espic_ctx *ctx, int sp, double out[5]);
 /* Species::updateAverages -> Field::updateAverage (Field.h:214-221) */

@@ -154,7 +154,7 @@ extern "C" void espic_destroy(espic_ctx *c)
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }
         cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc); cudaFree(c->sp[s].mom);
     }
-    cudaFree(c->dead_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
+    cudaFree(c->dead_words); cudaFree(c->hit_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
     cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
     for (int q = 0; q < 8; q++) cudaFree(c->sv[q]);
     if (c->push_ev0) { cudaEventDestroy(c->push_ev0); cudaEventDestroy(c->push_ev1); }
@@ -351,6 +351,7 @@ extern "C" int espic_species_upload(espic_ctx *c, int sp, const double *const co
     CK(cudaStreamSynchronize(c->stream));
     for (long long i = 0; i < n; i++) if (comp[6][i] > s.mpw_max) s.mpw_max = comp[6][i];
     s.np = base + n;
+    if (!append) s.n_settled = s.np;     // a restored state: every particle finished its last step (ch4 Particle::dt = 0)
     s.acc_fresh = false;
     s.pushes_since_sort = 1 << 20;       // arbitrary order
     return 0;
@@ -368,6 +369,7 @@ extern "C" int espic_species_upload_device(espic_ctx *c, int sp, const double *c
         if (n > 0) CK(cudaMemcpyAsync(s.p[q] + base, dcomp[q], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     if (mpw_max > s.mpw_max) s.mpw_max = mpw_max;
     s.np = base + n;
+    if (!append) s.n_settled = s.np;     // a restored state: every particle finished its last step (ch4 Particle::dt = 0)
     s.acc_fresh = false;
     s.pushes_since_sort = 1 << 20;       // arbitrary order
     return 0;

@@ -36,6 +36,10 @@ struct Species {
     int acc_shift = 0;                 // fixed point: value * 2^shift
     double mpw_max = 0;                // upper bound of any mpw seen (fixed-point scale)
     int pushes_since_sort = 1 << 20;   // how scrambled the cell order is: chooses the deposit kernel
+    // ch4 Particle::dt by index (espic_surface.cuh): particles [0, n_settled) went through the last advance (dt = 0),
+    // particles [n_settled, np) were added since (dt = world dt)
+    long long n_settled = 0;
+    bool substep = false;              // the species is advanced with espic_push_surface
 };
 
 struct espic_ctx {
@@ -55,6 +59,7 @@ struct espic_ctx {
     bool push_timed = false;
     // scratch
     uint32_t *dead_words = nullptr; long long dead_words_cap = 0;
+    uint32_t *hit_words = nullptr;  long long hit_words_cap = 0;    // ions that hit the sphere (espic_push_surface)
     uint32_t *scan_pre = nullptr;  long long scan_cap = 0;
     uint32_t *scan_coff = nullptr; long long scan_coff_cap = 0;
     long long *lists = nullptr;    long long lists_cap = 0;   // holes | fillers

@@ -586,6 +586,40 @@ static int prepare_acc(espic_ctx *c, Species &s, int mode)
     return 0;
 }
 
+// count the dead of dead_words (one bit per particle of [0,n)), then remove them in the reference's order
+static int compact_dead(espic_ctx *c, Species &s, long long n)
+{
+    const long long nw = (n + 31) / 32;
+    int r;
+    static const bool trace = getenv("ESPIC_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_a = trace ? now() : 0;
+    if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
+    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, c->cell_cnt);
+    LAUNCH_CHECK(c);
+    if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
+    unsigned long long *h = (unsigned long long *)c->hpin;
+    CK(cudaMemcpyAsync(h, c->dscal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    const double t_b = trace ? now() : 0;
+    CK(cudaStreamSynchronize(c->stream));
+    const double t_c = trace ? now() : 0;
+    const long long D = (long long)h[0];
+    if (D == 0) return 0;
+    if (D < n) {
+        if ((r = ensure_buf(&c->lists, &c->lists_cap, std::max(2 * D, n / 64), c->stream))) return r;
+        CK(cudaMemsetAsync(c->lists, 0xff, (size_t)D * sizeof(long long), c->stream));
+        k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
+                                                           c->lists, c->lists + D);
+        LAUNCH_CHECK(c);
+        k_move<<<nblk(D, 256), 256, 0, c->stream>>>(D, c->lists, c->lists + D, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
+        LAUNCH_CHECK(c);
+    }
+    s.np = n - D;
+    if (trace) fprintf(stderr, "[espic_push] n=%lld D=%lld host ms: enqueue %.3f  wait-for-count %.3f  removal-enqueue %.3f\n",
+                       n, D, t_b - t_a, t_c - t_b, now() - t_c);
+    return 0;
+}
+
 extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int flags)
 {
     SP_CHECK(c, sp);
@@ -624,36 +658,11 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     c->push_timed = true;
     if (fuse) s.acc_fresh = true;
     if (s.pushes_since_sort < (1 << 20)) s.pushes_since_sort++;
-    if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) return 0;
+    if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) { s.n_settled = s.np; return 0; }
 
-    // count the dead, then remove them in the reference's order
-    static const bool trace = getenv("ESPIC_TRACE") != nullptr;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_a = trace ? now() : 0;
-    if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
-    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, c->cell_cnt);
-    LAUNCH_CHECK(c);
-    if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
-    unsigned long long *h = (unsigned long long *)c->hpin;
-    CK(cudaMemcpyAsync(h, c->dscal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    const double t_b = trace ? now() : 0;
-    CK(cudaStreamSynchronize(c->stream));
-    const double t_c = trace ? now() : 0;
-    const long long D = (long long)h[0];
-    if (D == 0) return 0;
-    if (D < n) {
-        if ((r = ensure_buf(&c->lists, &c->lists_cap, std::max(2 * D, n / 64), c->stream))) return r;
-        CK(cudaMemsetAsync(c->lists, 0xff, (size_t)D * sizeof(long long), c->stream));
-        k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
-                                                           c->lists, c->lists + D);
-        LAUNCH_CHECK(c);
-        k_move<<<nblk(D, 256), 256, 0, c->stream>>>(D, c->lists, c->lists + D, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
-        LAUNCH_CHECK(c);
-    }
-    s.np = n - D;
-    if (trace) fprintf(stderr, "[espic_push] n=%lld D=%lld host ms: enqueue %.3f  wait-for-count %.3f  removal-enqueue %.3f\n",
-                       n, D, t_b - t_a, t_c - t_b, now() - t_c);
-    return 0;
+    int rr = compact_dead(c, s, n);
+    s.n_settled = s.np;
+    return rr;
 }
 
 // device time of the most recent k_push launch alone (no removal bookkeeping), from events on the launching stream
@@ -915,6 +924,11 @@ extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
     Species &s = c->sp[sp];
     const long long n = s.np;
     if (n < 2) return 0;
+    if (s.substep && s.n_settled < n) {
+        espic_set_error("espic_sort_by_cell: species %d holds particles added since its last espic_push_surface; their "
+                        "Particle::dt is tracked by index -- sort after the advance", sp);
+        return -1;
+    }
     const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1) * SORT_ZBINS;
     int r;
     if (s.alt_cap < s.cap) {
@@ -1198,3 +1212,5 @@ extern "C" int espic_species_diag(espic_ctx *c, int sp, double out[5])
     out[4] = 0.5 * s.mass * h[4];                                             // Species.cpp:107
     return 0;
 }
+
+#include "espic_surface.cuh"

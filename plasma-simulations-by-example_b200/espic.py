@@ -22,7 +22,7 @@ EXPORTS = [
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
-    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
+    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
 ]
@@ -89,6 +89,8 @@ def load():
                                          C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_inject_cold_beam.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
                                          C.c_uint32, C.POINTER(C.c_longlong)]
+    L.espic_push_surface.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
+                                     C.POINTER(C.c_longlong)]
     L.espic_species_diag.argtypes = [vp, C.c_int, dp]
     L.espic_update_average.argtypes = [vp, C.c_int]
     L.espic_sample_moments.argtypes = [vp, C.c_int]
@@ -269,6 +271,12 @@ class Engine:
         added = C.c_longlong(0)
         self._ck(self.L.espic_inject_warm_beam(self.h, sp, v_drift, den, T, dt, seed, stream, step, C.byref(added)))
         return added.value
+
+    def push_surface(self, sp, dt, neutrals_sp, sput_sp, seed, stream, step):
+        """ch4 Species::advance(neutrals, spherium); returns (emitted into neutrals_sp, emitted into sput_sp)"""
+        em = (C.c_longlong * 2)()
+        self._ck(self.L.espic_push_surface(self.h, sp, dt, neutrals_sp, sput_sp, seed, stream, step, em))
+        return int(em[0]), int(em[1])
 
     def diag(self, sp):
         out = np.zeros(5)

@@ -109,3 +109,92 @@ def test_bounced_neutrals_leave_the_sphere_with_wall_temperature():
     # sampleVth: three components v_th*(u1+u2+u3-1.5), each of variance v_th^2/4, magnitude scaled by 3/sqrt(6)
     assert abs(np.sqrt((speed[slow] ** 2).mean()) / (v_th * np.sqrt(0.75 * 1.5)) - 1) < 0.1
     assert np.all(got[6] == 0)             # every survivor finished its step: Particle::dt == 0
+
+
+# ---- GPU: espic_push_surface against the oracle's Philox mode -----------------------------------------------------------
+
+def _stage(w, charge, n, seed):
+    """Oracle species triplet and the matching GPU engine: the settled particles (Particle::dt = 0) are uploaded, the fresh ones
+    (dt = world dt) go through addParticle on both sides."""
+    from engines import GpuEngine
+    part, pdt = sc.make_particles(w, seed, n, mpw=5.0)
+    settled, fresh = part[:, pdt == 0], part[:, pdt != 0]
+    adv, neut, sput = sc.species_triplet(w, charge, cap=2 * n)
+    adv.set_particles(settled)
+    st = sf.state_from_oracle(w, [adv, neut, sput], sc.DT)
+    g = GpuEngine(st)
+    for q in range(fresh.shape[1]):
+        adv.add_particle(fresh[:3, q], fresh[3:6, q], fresh[6, q], sc.DT)
+    adv.pdt[settled.shape[1]:adv.np] = sc.DT
+    added = g.e.add_particles(g.species[0], np.ascontiguousarray(fresh), sc.DT)
+    assert added == fresh.shape[1] == adv.np - settled.shape[1]
+    return g, (adv, neut, sput)
+
+
+def _compare(g, osp, idx, exact_positions):
+    a, b = g.e.download(g.species[idx]), osp.particles()
+    assert a.shape == b.shape, (idx, a.shape, b.shape)
+    if a.shape[1] == 0:
+        return 0
+    if exact_positions:
+        assert np.array_equal(a[:3].view(np.uint64), b[:3].view(np.uint64)), "positions"
+    else:
+        # a re-emitted particle moves on with a velocity that went through sin/cos: CUDA's differ from glibc's by <= 1 ulp
+        assert np.abs(a[:3] - b[:3]).max() <= 1e-13, "positions"
+    assert np.array_equal(a[6], b[6]), "weights"
+    assert np.abs(a[3:6] - b[3:6]).max() <= 1e-12 * np.abs(b[3:6]).max(), "velocities (libm differences only)"
+    return a.shape[1]
+
+
+@pytest.mark.gpu
+def test_gpu_neutral_surface_bounce_matches_oracle_philox():
+    w = sc.make_world()
+    g, (adv, _, _) = _stage(w, 0.0, 6000, 41)
+    n0 = adv.np
+    for step in range(3):
+        g.e.push_surface(g.species[0], sc.DT, 0, 0, 0x5EED5EED77, 4, step)
+        adv.advance_surface(sc.DT, adv, adv, ("philox", 0x5EED5EED77, 4, step))
+        n = _compare(g, adv, 0, exact_positions=False)
+    assert 0.3 * n0 < n < n0
+    # bit-exact where no libm call is involved: particles that never touched the sphere
+    a, b = g.e.download(g.species[0]), adv.particles()
+    same = np.all(a[3:6].view(np.uint64) == b[3:6].view(np.uint64), axis=0)
+    assert same.mean() > 0.3 and np.array_equal(a[:3, same].view(np.uint64), b[:3, same].view(np.uint64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("same_target", [True, False])
+def test_gpu_ion_impact_emission_matches_oracle_philox(same_target):
+    w = sc.make_world()
+    g, (adv, neut, sput) = _stage(w, QE, 6000, 43)
+    tgt = neut if same_target else sput
+    gi = 1 if same_target else 2
+    for step in range(2):
+        em_g = g.e.push_surface(g.species[0], sc.DT, g.species[1], g.species[gi], 0xABCDEF, 1, step)
+        em_o = adv.advance_surface(sc.DT, neut, tgt, ("philox", 0xABCDEF, 1, step))
+        if same_target:
+            assert em_g[0] == sum(em_o) and em_g[1] == 0
+        else:
+            assert em_g == em_o
+        _compare(g, adv, 0, exact_positions=True)          # ions: no libm on their own path
+        assert _compare(g, neut, 1, exact_positions=True) > (300 if step == 0 else 0)
+        ns = _compare(g, sput, 2, exact_positions=True)
+        assert same_target or ns > 5 or step > 0
+    # the emitted neutrals are new particles of their species: their first advance moves them for 2*dt and bounces them
+    g.e.push_surface(g.species[1], sc.DT, 0, 0, 0xABCDEF, 2, 7)
+    neut.advance_surface(sc.DT, neut, neut, ("philox", 0xABCDEF, 2, 7))
+    assert _compare(g, neut, 1, exact_positions=False) > 300
+
+
+@pytest.mark.gpu
+def test_gpu_sort_refused_between_injection_and_surface_advance():
+    w = sc.make_world()
+    g, _ = _stage(w, 0.0, 500, 47)
+    es = g.es
+    g.e.push_surface(g.species[0], sc.DT, 0, 0, 1, 0, 0)
+    g.e.sort_by_cell(g.species[0])                                   # fine: everything settled
+    g.e.inject_warm_beam(g.species[0], 7000.0, 2e7, 1000.0, sc.DT, 5, 0, 1)
+    with pytest.raises(Exception, match="sort after the advance"):
+        g.e.sort_by_cell(g.species[0])
+    g.e.push_surface(g.species[0], sc.DT, 0, 0, 1, 0, 1)
+    g.e.sort_by_cell(g.species[0])
