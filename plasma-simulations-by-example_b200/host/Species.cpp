@@ -96,6 +96,22 @@ void Species::advance()
     particles_changed();
 }
 
+// ch4 Species::advance(neutrals, spherium) (ch4/Species.cpp:8-91).  Philox key: (world seed, 0x100 + species id, time step).
+void Species::advance(Species &neutrals, Species &spherium)
+{
+    flush();
+    neutrals.flush();
+    spherium.flush();
+    world.fields_to_device();
+    n_advance++;
+    long long emitted[2] = {0, 0};
+    espic_host::check(espic_push_surface(world.engine(), sp_id, world.getDt(), neutrals.sp_id, spherium.sp_id, rnd.seed(),
+                                         0x100u + (unsigned)sp_id, (unsigned)world.getTs(), emitted),
+                      "espic_push_surface");
+    particles_changed();
+    if (emitted[0] || emitted[1]) { neutrals.particles_changed(); spherium.particles_changed(); }
+}
+
 // Species::computeNumberDensity (Species.cpp:51-62)
 void Species::computeNumberDensity()
 {

@@ -37,8 +37,12 @@ public:
     double getKE();
 
     void advance();
+    // ch4 form (ch4/Species.cpp:8-91): sub-step loop with surface interactions -- neutrals bounce off the sphere diffusely at the
+    // wall temperature, ions that hit it die and emit neutrals into `neutrals` and sputtered material into `spherium`
+    void advance(Species &neutrals, Species &spherium);
     void computeNumberDensity();
     void addParticle(double3 pos, double3 vel, double mpwt);
+    void addParticle(double3 pos, double3 vel) { addParticle(pos, vel, mpw0); }      // ch4/Species.h:65
     void loadParticlesBox(double3 x1, double3 x2, double num_den, int num_mp);
     void loadParticlesBoxQS(double3 x1, double3 x2, double num_den, int3 num_mp);
     void updateAverages();

@@ -3,11 +3,13 @@
 // (tests/statefile.py) so that pytest can compare it with the CPU oracle.  Scenarios:
 //   shim_check sphere <ni> <nj> <nk> <steps> <GS|PCG|QN> <tol> <out.state>     ch3/ver2/Main.cpp:16-91 flow
 //   shim_check box <n> <ions_grid> <eles_grid> <steps> <out.state>             ch2/Main.cpp:14-75 flow
+//   shim_check surface <steps> <QN|PCG> <out.state>                               ch4/Main.cpp:19-110 flow (ions + neutrals)
 //   shim_check fieldio <out.state>                                             host writes to Field mirrors reach the GPU
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -111,6 +113,54 @@ int run_sphere(int argc, char **args)
     return 0;
 }
 
+// ch4/Main.cpp flow with its commented-out ion species switched on: warm neutral beam + cold ion beam, every species advanced with
+// surface interactions (neutrals bounce off the sphere, ions that hit it come back as neutrals), moments sampled every step
+int run_surface(int argc, char **args)
+{
+    if (argc < 5) return 1;
+    const int steps = atoi(args[2]);
+    const std::string st = args[3];
+    World world(21, 21, 41);
+    world.setExtents({-0.1, -0.1, 0}, {0.1, 0.1, 0.4});
+    world.setTime(2e-7, steps);
+    const double3 sc{0, 0, 0.15};
+    world.addSphere(sc, 0.05, -100);
+    world.addInlet();
+    std::vector<Species> species;
+    species.reserve(2);
+    species.push_back(Species("O", 16 * AMU, 0, 50, world));       // light neutral macroparticles: every ion impact emits two
+    species.push_back(Species("O+", 16 * AMU, QE, 1e2, world));
+    Species &neutrals = species[0];
+    Species &ions = species[1];
+    const double nda = 1e10, ndi = 1e10;
+    std::vector<std::unique_ptr<Source>> sources;
+    sources.emplace_back(new WarmBeamSource(neutrals, world, 7000, nda, 1000));
+    sources.emplace_back(new ColdBeamSource(ions, world, 7000, ndi));
+    PotentialSolver solver(world, st == "PCG" ? SolverType::PCG : SolverType::QN, 1000, 1e-4);
+    solver.setReferenceValues(0, 1.5, ndi);
+    bool ok = solver.solve();
+    solver.computeEF();
+    double emitted_weight = 0;
+    while (world.advanceTime()) {
+        for (auto &source : sources) source->sample();
+        for (Species &sp : species) {
+            const double before = neutrals.getRealCount();
+            sp.advance(neutrals, neutrals);
+            if (&sp == &ions) emitted_weight += neutrals.getRealCount() - before;
+            sp.computeNumberDensity();
+            sp.sampleMoments();
+        }
+        world.computeChargeDensity(species);
+        ok = solver.solve();
+        solver.computeEF();
+        Output::screenOutput(world, species);
+    }
+    for (Species &sp : species) sp.computeGasProperties();
+    printf("emitted neutral weight = %.15g\n", emitted_weight);
+    dump_state(args[4], world, species, 3, sc, 0.05, -100, 0, 1.5, ndi, ok);
+    return 0;
+}
+
 int run_box(int argc, char **args)
 {
     if (argc < 7) return 1;
@@ -187,11 +237,12 @@ int main(int argc, char **args)
     try {
         if (argc > 1 && !strcmp(args[1], "sphere")) rc = run_sphere(argc, args);
         else if (argc > 1 && !strcmp(args[1], "box")) rc = run_box(argc, args);
+        else if (argc > 1 && !strcmp(args[1], "surface")) rc = run_surface(argc, args);
         else if (argc > 1 && !strcmp(args[1], "fieldio")) rc = run_fieldio(argc, args);
     } catch (const std::exception &e) {
         std::cerr << "shim_check: " << e.what() << std::endl;
         return 3;
     }
-    if (rc == 1) std::cerr << "usage: shim_check sphere|box|fieldio ... (see the header of shim_check.cpp)" << std::endl;
+    if (rc == 1) std::cerr << "usage: shim_check sphere|box|surface|fieldio ... (see the header of shim_check.cpp)" << std::endl;
     return rc;
 }

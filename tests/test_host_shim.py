@@ -297,3 +297,47 @@ def test_reference_ch9_mt_main_three_species(tmp_path):
     assert abs(last[5]) < 1e-6 * abs(last[7]) and abs(last[6]) < 1e-6 * abs(last[7])
     ke_per_real = last[8] / last[4]
     assert abs(ke_per_real / (0.5 * 16 * AMU * 7000.0 ** 2) - 1) < 1e-5      # the CSV carries 6 significant digits
+
+
+@pytest.mark.gpu
+def test_surface_flow_through_class_api(tmp_path):
+    """ch4/Main.cpp flow through the class API: warm neutral beam + cold ion beam, Species::advance(neutrals, neutrals) with surface
+    interactions for both species, moments, QN potential -- against the oracle stepping the same Philox counters."""
+    steps, seed, dt = 150, 777, 2e-7
+    st = run_check(tmp_path, "surface", steps, "QN", seed=seed)
+    w = orc.World(21, 21, 41, (-0.1, -0.1, 0.0), (0.1, 0.1, 0.4))
+    w.add_sphere((0, 0, 0.15), 0.05, -100.0)
+    w.add_inlet()
+    neut = orc.Species(w, 16 * AMU, 0.0, 50.0, cap=4_000_000)
+    ions = orc.Species(w, 16 * AMU, QE, 1e2, cap=2_000_000)
+    w.set_reference_values(0.0, 1.5, 1e12)      # the constructor's solveQN runs on the defaults
+    w.solve_qn()
+    w.set_reference_values(0.0, 1.5, 1e10)
+    w.solve_qn()
+    w.compute_ef()
+    emitted = 0
+    for ts in range(steps + 1):
+        n0 = neut.np
+        neut.sample_warm_beam_philox(7000.0, 1e10, 1000.0, dt, seed, 0, ts)
+        neut.pdt[n0:neut.np] = dt               # addParticle(pos,vel): Particle::dt = world dt (ch4/Species.h:65)
+        n0 = ions.np
+        ions.sample_cold_beam_philox(7000.0, 1e10, dt, seed, 1, ts)
+        ions.pdt[n0:ions.np] = dt
+        neut.advance_surface(dt, neut, neut, ("philox", seed, 0x100, ts))
+        neut.compute_number_density()           # as in Main.cpp: before the ions of this step add their neutrals
+        emitted += sum(ions.advance_surface(dt, neut, neut, ("philox", seed, 0x101, ts), headroom=200000))
+        ions.compute_number_density()
+        w.compute_charge_density([neut, ions])
+        w.solve_qn()
+        w.compute_ef()
+    assert emitted > 2000, "ions must have reached the sphere"
+    assert abs(float(st.stdout.split("emitted neutral weight =")[1].split()[0]) / (50.0 * emitted) - 1) < 1e-12
+    for got, sp, name in ((st.species[0], neut, "neutrals"), (st.species[1], ions, "ions")):
+        ref = sp.particles()
+        assert got["part"].shape == ref.shape, "%s count after %d steps" % (name, steps)
+        close(got["part"][:3], ref[:3], 1e-9, name + " positions")
+        close(got["part"][3:6], ref[3:6], 1e-9, name + " velocities")
+        close(got["den"], sp.den, 1e-9, name + " den")
+        c = np.array([0, 0, 0.15])[:, None]
+        assert np.all(((got["part"][:3] - c) ** 2).sum(0) > 0.05 ** 2), "no live particle inside the sphere"
+    close(st.phi, w.phi, 1e-9, "phi")
