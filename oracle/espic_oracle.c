@@ -1142,3 +1142,100 @@ int64_t orc_advance_surface(const orc_mesh *m, const double *ef, orc_particles *
     p->np = np;
     return np;
 }
+
+/* ======================================================================================================
+ * ch4: DSMC_MEX::apply / collide / evalSigma (ch4/Collisions.cpp:84-182, ch4/Collisions.h:59-83) -- Bird's NTC scheme
+ * with VHS cross-sections on the particles of one species, cell by cell -- and Species::computeMPC (ch4/Species.cpp:228-235).
+ * Cell of a particle: World::XtoC (ch4/World.h:88-98), c = k*(nj-1)*(ni-1) + j*(ni-1) + i.  The per-cell particle lists keep
+ * the particle order (push_back while looping over the particles).
+ * Random numbers: mode 0 = the reference's sequential mt19937 stream; mode 1 = Philox, draw number q of cell c is element
+ * q&1 of block (c << 24) + (q >> 1)  (shared with the CUDA engine).
+ * ====================================================================================================== */
+static int64_t cell_index(const orc_mesh *m, double x, double y, double z)
+{
+    double pos[3] = { x, y, z }, lc[3], d;
+    int i, j, k;
+    orc_xtol(m, pos, lc);
+    cell_of(lc[0], m->ni, &i, &d);
+    cell_of(lc[1], m->nj, &j, &d);
+    cell_of(lc[2], m->nk, &k, &d);
+    return ((int64_t)k * (m->nj - 1) + j) * (m->ni - 1) + i;
+}
+
+void orc_compute_mpc(const orc_mesh *m, const orc_particles *p, double *mpc)
+{
+    int64_t nc = (int64_t)(m->ni - 1) * (m->nj - 1) * (m->nk - 1);
+    for (int64_t c = 0; c < nc; c++) mpc[c] = 0;
+    for (int64_t q = 0; q < p->np; q++) mpc[cell_index(m, p->x[q], p->y[q], p->z[q])] += 1;
+}
+
+double orc_vhs_sigma(double mass, double g_rel)
+{
+    const double K = 1.380648e-23, PI = 3.141592653;
+    double mr = mass * mass / (mass + mass);
+    double c0 = 4.07e-10, c1 = 0.77, c2 = 2 * K * 273.15 / mr, c3 = tgamma(2.5 - c1);
+    return PI * c0 * c0 * pow(c2 / (g_rel * g_rel), c1 - 0.5) / c3;
+}
+
+int64_t orc_dsmc_mex(const orc_mesh *m, orc_particles *p, double mass, double mpw0, double dt, double *sigma_cr_max_io,
+                     const orc_surface_rng *rng)
+{
+    const double PI = 3.141592653;
+    int64_t nc = (int64_t)(m->ni - 1) * (m->nj - 1) * (m->nk - 1);
+    int64_t *start = (int64_t *)calloc((size_t)nc + 1, sizeof(int64_t));
+    int64_t *list = (int64_t *)malloc((size_t)(p->np > 0 ? p->np : 1) * sizeof(int64_t));
+    int64_t *cell = (int64_t *)malloc((size_t)(p->np > 0 ? p->np : 1) * sizeof(int64_t));
+    for (int64_t q = 0; q < p->np; q++) { cell[q] = cell_index(m, p->x[q], p->y[q], p->z[q]); start[cell[q] + 1]++; }
+    for (int64_t c = 0; c < nc; c++) start[c + 1] += start[c];
+    {
+        int64_t *cur = (int64_t *)malloc((size_t)nc * sizeof(int64_t));
+        memcpy(cur, start, (size_t)nc * sizeof(int64_t));
+        for (int64_t q = 0; q < p->np; q++) list[cur[cell[q]]++] = q;
+        free(cur);
+    }
+    double sigma_cr_max = *sigma_cr_max_io, sigma_cr_max_temp = 0;
+    double dV = m->dh[0] * m->dh[1] * m->dh[2];
+    double Fn = mpw0;
+    int64_t num_cols = 0;
+    rng_cursor rc = { rng, 0, 0 };
+    for (int64_t c = 0; c < nc; c++) {
+        const int64_t *parts = list + start[c];
+        int np = (int)(start[c + 1] - start[c]);
+        if (np < 2) continue;
+        rng_seek(&rc, (uint64_t)c << 24, 0);
+        double ng_f = 0.5 * np * np * Fn * sigma_cr_max * dt / dV;
+        int ng = (int)(ng_f + 0.5);
+        for (int g = 0; g < ng; g++) {
+            int p1 = (int)(rng_draw(&rc) * np), p2;
+            do { p2 = (int)(rng_draw(&rc) * np); } while (p2 == p1);
+            int64_t a = parts[p1], b = parts[p2];
+            double v1[3] = { p->vx[a], p->vy[a], p->vz[a] }, v2[3] = { p->vx[b], p->vy[b], p->vz[b] };
+            double cr_vec[3], s = 0;
+            for (int d = 0; d < 3; d++) { cr_vec[d] = v1[d] - v2[d]; s += cr_vec[d] * cr_vec[d]; }
+            double cr = sqrt(s);
+            double sigma = orc_vhs_sigma(mass, cr);
+            double sigma_cr = sigma * cr;
+            if (sigma_cr > sigma_cr_max_temp) sigma_cr_max_temp = sigma_cr;
+            double P = sigma_cr / sigma_cr_max;
+            if (P > rng_draw(&rc)) {
+                num_cols++;
+                /* DSMC_MEX::collide(vel1, vel2, mass, mass), ch4/Collisions.cpp:84-106 */
+                double cm[3], crr[3];
+                for (int d = 0; d < 3; d++) cm[d] = (v1[d] * mass + v2[d] * mass) / (mass + mass);
+                double cr_mag = cr;                       /* mag(vel1 - vel2): the same expression again */
+                double cos_chi = 2 * rng_draw(&rc) - 1;
+                double sin_chi = sqrt(1 - cos_chi * cos_chi);
+                double eps = 2 * PI * rng_draw(&rc);
+                crr[0] = cr_mag * cos_chi;
+                crr[1] = cr_mag * sin_chi * cos(eps);
+                crr[2] = cr_mag * sin_chi * sin(eps);
+                double f2 = mass / (mass + mass);
+                p->vx[a] = cm[0] + crr[0] * f2; p->vy[a] = cm[1] + crr[1] * f2; p->vz[a] = cm[2] + crr[2] * f2;
+                p->vx[b] = cm[0] - crr[0] * f2; p->vy[b] = cm[1] - crr[1] * f2; p->vz[b] = cm[2] - crr[2] * f2;
+            }
+        }
+    }
+    free(start); free(list); free(cell);
+    if (num_cols) *sigma_cr_max_io = sigma_cr_max_temp;
+    return num_cols;
+}

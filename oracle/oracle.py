@@ -108,6 +108,12 @@ def lib():
         L.orc_advance_surface.restype = C.c_int64
         L.orc_advance_surface.argtypes = [C.POINTER(CMesh), dp, C.POINTER(CParticles), dp] + [C.c_double] * 4 + \
             [C.POINTER(CSurfaceTarget), C.POINTER(CSurfaceTarget), C.POINTER(CSurfaceRng), C.POINTER(C.c_int64)]
+        L.orc_dsmc_mex.restype = C.c_int64
+        L.orc_dsmc_mex.argtypes = [C.POINTER(CMesh), C.POINTER(CParticles), C.c_double, C.c_double, C.c_double, dp,
+                                   C.POINTER(CSurfaceRng)]
+        L.orc_compute_mpc.argtypes = [C.POINTER(CMesh), C.POINTER(CParticles), dp]
+        L.orc_vhs_sigma.restype = C.c_double
+        L.orc_vhs_sigma.argtypes = [C.c_double, C.c_double]
         L.orc_line_sphere_intersect.restype = C.c_double
         L.orc_line_sphere_intersect.argtypes = [C.POINTER(CMesh), dp, dp]
         _lib = L
@@ -196,6 +202,30 @@ class Species:
         for t in targets:
             t.np = cps[id(t)].np
         return int(em[0]), int(em[1])
+
+    @staticmethod
+    def _rng(rng):
+        r = CSurfaceRng()
+        if rng[0] == "mt":
+            r.mode, r.mt = 0, C.cast(C.pointer(rng[1]), C.c_void_p)
+        else:
+            r.mode, r.seed, r.stream, r.step = 1, rng[1], rng[2], rng[3]
+        return r
+
+    def dsmc_mex(self, dt, sigma_cr_max, rng):
+        """ch4 DSMC_MEX::apply on this species; returns (collisions, new sigma_cr_max)"""
+        p = self._c()
+        s = np.array([sigma_cr_max], dtype=np.float64)
+        r = self._rng(rng)
+        cols = lib().orc_dsmc_mex(C.byref(self.world.m), C.byref(p), self.mass, self.mpw0, dt, _dp(s), C.byref(r))
+        return int(cols), float(s[0])
+
+    def compute_mpc(self):
+        w = self.world
+        mpc = np.zeros((w.ni - 1) * (w.nj - 1) * (w.nk - 1))
+        p = self._c()
+        lib().orc_compute_mpc(C.byref(w.m), C.byref(p), _dp(mpc))
+        return mpc
 
     def push_nocompact(self, dt):
         p = self._c()
