@@ -59,7 +59,8 @@ int espic_add_inlet(espic_ctx *ctx);
 enum { ESPIC_PHI = 0, ESPIC_RHO = 1, ESPIC_EF = 2, ESPIC_NODE_VOL = 3, ESPIC_OBJECT_ID = 4,
        ESPIC_DEN = 5, ESPIC_DEN_AVE = 6,
        /* per-species velocity-moment fields of ch4 (Species.h:85-95); VEL and NV_SUM are interleaved [3*u+c] */
-       ESPIC_VEL = 7, ESPIC_T = 8, ESPIC_N_SUM = 9, ESPIC_NV_SUM = 10, ESPIC_NUU_SUM = 11, ESPIC_NVV_SUM = 12, ESPIC_NWW_SUM = 13 };
+       ESPIC_VEL = 7, ESPIC_T = 8, ESPIC_N_SUM = 9, ESPIC_NV_SUM = 10, ESPIC_NUU_SUM = 11, ESPIC_NVV_SUM = 12, ESPIC_NWW_SUM = 13,
+       ESPIC_MPC = 14 };   /* macroparticles per CELL, (ni-1)(nj-1)(nk-1) doubles in World::XtoC order (ch4/Species.h:88) */
 int espic_field_download(espic_ctx *ctx, int which, int species, void *host);
 int espic_field_upload(espic_ctx *ctx, int which, int species, const void *host);
 /* device pointer of a field (zero-copy interop: NCCL, torch.from_blob, ...) */
@@ -124,6 +125,16 @@ int espic_inject_warm_beam(espic_ctx *ctx, int sp, double v_drift, double den, d
  * For a neutral species neutrals_sp / sput_sp are ignored. */
 int espic_push_surface(espic_ctx *ctx, int sp, double dt, int neutrals_sp, int sput_sp,
                        uint64_t seed, uint32_t stream, uint32_t step, long long emitted[2]);
+
+/* ch4 DSMC_MEX::apply(dt) (ch4/Collisions.cpp:84-182): momentum-exchange collisions among the particles of species `sp`, cell by
+ * cell (World::XtoC), Bird's no-time-counter pair selection with VHS cross-sections (ch4/Collisions.h:59-83).  *sigma_cr_max is
+ * the object's running (sigma*cr)_max: read, and replaced by the maximum seen when at least one collision happened (start from
+ * 1e-14 like the reference).  Pairs inside a cell are processed in the reference's order (cell lists in particle order);
+ * random numbers are Philox counters keyed (seed, stream, step; cell, draw). */
+int espic_dsmc_mex(espic_ctx *ctx, int sp, double dt, double *sigma_cr_max, uint64_t seed, uint32_t stream, uint32_t step,
+                   long long *num_cols);
+/* ch4 Species::computeMPC (ch4/Species.cpp:228-235): macroparticles per cell -> field ESPIC_MPC */
+int espic_compute_mpc(espic_ctx *ctx, int sp);
 
 /* Species::getRealCount/getMomentum/getKE (Species.cpp:84-108): out = {sum mpw, px, py, pz, KE} */
 int espic_species_diag(espic_ctx *ctx, int sp, double out[5]);

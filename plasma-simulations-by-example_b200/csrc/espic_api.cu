@@ -152,7 +152,7 @@ extern "C" void espic_destroy(espic_ctx *c)
     cudaFree(c->phi); cudaFree(c->rho); cudaFree(c->ef); cudaFree(c->ef4); cudaFree(c->node_vol); cudaFree(c->object_id);
     for (int s = 0; s < c->nsp; s++) {
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }
-        cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc); cudaFree(c->sp[s].mom);
+        cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc); cudaFree(c->sp[s].mom); cudaFree(c->sp[s].mpc);
     }
     cudaFree(c->dead_words); cudaFree(c->hit_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
     cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
@@ -240,6 +240,14 @@ static int field_ptr(espic_ctx *c, int which, int sp, void **p, size_t *bytes)
         case ESPIC_OBJECT_ID: *p = c->object_id; *bytes = nn * 4; return 0;
         case ESPIC_DEN: *p = c->sp[sp].den; *bytes = nn * 8; return 0;
         case ESPIC_DEN_AVE: *p = c->sp[sp].den_ave; *bytes = nn * 8; return 0;
+        case ESPIC_MPC: {
+            const size_t nc = (size_t)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1);
+            if (!c->sp[sp].mpc) {
+                if (cudaMalloc(&c->sp[sp].mpc, nc * 8) != cudaSuccess) { espic_set_error("field: out of memory (mpc)"); return -1; }
+                cudaMemsetAsync(c->sp[sp].mpc, 0, nc * 8, c->stream);
+            }
+            *p = c->sp[sp].mpc; *bytes = nc * 8; return 0;
+        }
     }
     espic_set_error("field: unknown id %d", which);
     return -1;

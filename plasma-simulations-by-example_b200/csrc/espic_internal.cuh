@@ -29,6 +29,7 @@ struct Species {
     long long alt_cap = 0;
     double *den = nullptr, *den_ave = nullptr;
     double *acc = nullptr;             // FP64 scatter accumulator (also aliased as int64 in fixed-point mode)
+    double *mpc = nullptr;             // macroparticles per cell (ch4 Species::mpc), allocated on first use
     double *mom = nullptr;             // velocity moments, allocated on first use: n_sum | nv_sum[3] | nuu | nvv | nww | vel[3] | T
     int ave_samples = 0;
     bool acc_fresh = false;            // accumulator holds the scatter of the current particle state

@@ -1214,3 +1214,4 @@ extern "C" int espic_species_diag(espic_ctx *c, int sp, double out[5])
 }
 
 #include "espic_surface.cuh"
+#include "espic_collide.cuh"

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libespic_cuda.so")
 
-PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM, NVV_SUM, NWW_SUM = range(14)
+PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM, NVV_SUM, NWW_SUM, MPC = range(15)
 WALL_ABSORB, WALL_REFLECT = 0, 1
 PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_FIXED_POINT = 1, 2, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
@@ -22,7 +22,7 @@ EXPORTS = [
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
-    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
+    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
 ]
@@ -91,6 +91,8 @@ def load():
                                          C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_push_surface.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                                      C.POINTER(C.c_longlong)]
+    L.espic_dsmc_mex.argtypes = [vp, C.c_int, C.c_double, dp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_longlong)]
+    L.espic_compute_mpc.argtypes = [vp, C.c_int]
     L.espic_species_diag.argtypes = [vp, C.c_int, dp]
     L.espic_update_average.argtypes = [vp, C.c_int]
     L.espic_sample_moments.argtypes = [vp, C.c_int]
@@ -277,6 +279,19 @@ class Engine:
         em = (C.c_longlong * 2)()
         self._ck(self.L.espic_push_surface(self.h, sp, dt, neutrals_sp, sput_sp, seed, stream, step, em))
         return int(em[0]), int(em[1])
+
+    def dsmc_mex(self, sp, dt, sigma_cr_max, seed, stream, step):
+        """ch4 DSMC_MEX::apply; returns (collisions, new sigma_cr_max)"""
+        s = np.array([sigma_cr_max], dtype=np.float64)
+        cols = C.c_longlong(0)
+        self._ck(self.L.espic_dsmc_mex(self.h, sp, dt, _dp(s), seed, stream, step, C.byref(cols)))
+        return cols.value, float(s[0])
+
+    def compute_mpc(self, sp):
+        self._ck(self.L.espic_compute_mpc(self.h, sp))
+        out = np.zeros((self.ni - 1) * (self.nj - 1) * (self.nk - 1))
+        self._ck(self.L.espic_field_download(self.h, MPC, sp, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def diag(self, sp):
         out = np.zeros(5)
