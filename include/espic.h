@@ -133,6 +133,11 @@ int espic_push_surface(espic_ctx *ctx, int sp, double dt, int neutrals_sp, int s
  * random numbers are Philox counters keyed (seed, stream, step; cell, draw). */
 int espic_dsmc_mex(espic_ctx *ctx, int sp, double dt, double *sigma_cr_max, uint64_t seed, uint32_t stream, uint32_t step,
                    long long *num_cols);
+/* ch4 MCC_CEX::apply(dt) (ch4/Collisions.cpp:43-82): Monte Carlo collisions of the particles of `source_sp` with the gas of
+ * `target_sp` given by its mesh fields (ESPIC_DEN, ESPIC_VEL): P = 1 - exp(-n*1e-16*|v - u|*dt) per particle; a colliding
+ * particle's velocity is set to zero, as in the reference. */
+int espic_mcc_cex(espic_ctx *ctx, int source_sp, int target_sp, double dt, uint64_t seed, uint32_t stream, uint32_t step,
+                  long long *num_cols);
 /* ch4 Species::computeMPC (ch4/Species.cpp:228-235): macroparticles per cell -> field ESPIC_MPC */
 int espic_compute_mpc(espic_ctx *ctx, int sp);
 

@@ -1239,3 +1239,55 @@ int64_t orc_dsmc_mex(const orc_mesh *m, orc_particles *p, double mass, double mp
     if (num_cols) *sigma_cr_max_io = sigma_cr_max_temp;
     return num_cols;
 }
+
+/* ======================================================================================================
+ * ch4: MCC_CEX::apply (ch4/Collisions.cpp:43-82): Monte Carlo collisions of `source` particles with the mesh-averaged
+ * target gas (density den, stream velocity vel[3*u+c], temperature T on the nodes).  A colliding particle's velocity is set to
+ * zero (the reference has the charge-exchange assignment commented out, :78-79) after Species::sampleIsotropicVel consumed
+ * eleven random numbers.  mode 0: sequential mt19937; mode 1: Philox, particle q compares against element 0 of block q.
+ * ====================================================================================================== */
+double orc_gather1(const orc_mesh *m, const double *f, const double lc[3])
+{
+    int i, j, k; double di, dj, dk;
+    cell_of(lc[0], m->ni, &i, &di);
+    cell_of(lc[1], m->nj, &j, &dj);
+    cell_of(lc[2], m->nk, &k, &dk);
+    const size_t n[8] = { U(m, i, j, k), U(m, i + 1, j, k), U(m, i + 1, j + 1, k), U(m, i, j + 1, k),
+                          U(m, i, j, k + 1), U(m, i + 1, j, k + 1), U(m, i + 1, j + 1, k + 1), U(m, i, j + 1, k + 1) };
+    const double wi[8] = { 1 - di, di, di, 1 - di, 1 - di, di, di, 1 - di };
+    const double wj[8] = { 1 - dj, 1 - dj, dj, dj, 1 - dj, 1 - dj, dj, dj };
+    const double wk[8] = { 1 - dk, 1 - dk, 1 - dk, 1 - dk, dk, dk, dk, dk };
+    double val = f[n[0]] * wi[0] * wj[0] * wk[0];
+    for (int t = 1; t < 8; t++) val = val + f[n[t]] * wi[t] * wj[t] * wk[t];
+    return val;
+}
+
+int64_t orc_mcc_cex(const orc_mesh *m, orc_particles *p, const double *target_den, const double *target_vel,
+                    const double *target_T, double target_mass, double dt, const orc_surface_rng *rng)
+{
+    int64_t cols = 0;
+    rng_cursor rc = { rng, 0, 0 };
+    for (int64_t q = 0; q < p->np; q++) {
+        double pos[3] = { p->x[q], p->y[q], p->z[q] }, lc[3], vt[3];
+        orc_xtol(m, pos, lc);
+        orc_gather3(m, target_vel, lc, vt);
+        double nn = orc_gather1(m, target_den, lc);
+        double r0 = p->vx[q] - vt[0], r1 = p->vy[q] - vt[1], r2 = p->vz[q] - vt[2];
+        double s = 0;
+        s += r0 * r0; s += r1 * r1; s += r2 * r2;
+        double v_rel_mag = sqrt(s);
+        double sigma = 1e-16;
+        double P = 1 - exp(-nn * sigma * v_rel_mag * dt);
+        rng_seek(&rc, (uint64_t)q, 0);
+        if (P >= rng_draw(&rc)) {
+            if (rng->mode == 0) {
+                double T_target = orc_gather1(m, target_T, lc), u[11], v[3];
+                for (int t = 0; t < 11; t++) u[t] = rng_draw(&rc);
+                orc_isotropic_vel(T_target, target_mass, u, v);       /* sampled and dropped, as in the reference */
+            }
+            p->vx[q] = 0; p->vy[q] = 0; p->vz[q] = 0;
+            cols++;
+        }
+    }
+    return cols;
+}

@@ -114,6 +114,9 @@ def lib():
         L.orc_compute_mpc.argtypes = [C.POINTER(CMesh), C.POINTER(CParticles), dp]
         L.orc_vhs_sigma.restype = C.c_double
         L.orc_vhs_sigma.argtypes = [C.c_double, C.c_double]
+        L.orc_mcc_cex.restype = C.c_int64
+        L.orc_mcc_cex.argtypes = [C.POINTER(CMesh), C.POINTER(CParticles), dp, dp, dp, C.c_double, C.c_double,
+                                  C.POINTER(CSurfaceRng)]
         L.orc_line_sphere_intersect.restype = C.c_double
         L.orc_line_sphere_intersect.argtypes = [C.POINTER(CMesh), dp, dp]
         _lib = L
@@ -219,6 +222,13 @@ class Species:
         r = self._rng(rng)
         cols = lib().orc_dsmc_mex(C.byref(self.world.m), C.byref(p), self.mass, self.mpw0, dt, _dp(s), C.byref(r))
         return int(cols), float(s[0])
+
+    def mcc_cex(self, target_den, target_vel, target_T, target_mass, dt, rng):
+        """ch4 MCC_CEX::apply with this species as the source; returns the number of collisions"""
+        p = self._c()
+        r = self._rng(rng)
+        return int(lib().orc_mcc_cex(C.byref(self.world.m), C.byref(p), _dp(target_den), _dp(target_vel), _dp(target_T),
+                                     target_mass, dt, C.byref(r)))
 
     def compute_mpc(self):
         w = self.world

@@ -42,13 +42,13 @@ def build(force=False, verbose=False):
 
 
 HOST = os.path.join(HERE, "host")
-HOST_SRC = ["World.cpp", "Species.cpp", "Source.cpp", "PotentialSolver.cpp", "Output.cpp"]
+HOST_SRC = ["World.cpp", "Species.cpp", "Source.cpp", "PotentialSolver.cpp", "Output.cpp", "Collisions.cpp"]
 BIN = os.path.join(HERE, "bin")
 CXX = os.environ.get("CXX", "g++")
 CXXFLAGS = ["-O2", "-std=c++11", "-Wall", "-I" + HOST, "-I" + os.path.join(ROOT, "include")]
 LINK = ["-L" + os.path.join(HERE, "lib"), "-lespic_host", "-lespic_cuda", "-Wl,-rpath,$ORIGIN/../lib"]
 # the book's drivers that must compile UNCHANGED against host/*.h; read from the reference tree where it lies
-REF_MAINS = {"main_ch2": "ch2/Main.cpp", "main_ch3": "ch3/ver2/Main.cpp", "main_ch9": "ch9/Main.cpp",
+REF_MAINS = {"main_ch2": "ch2/Main.cpp", "main_ch3": "ch3/ver2/Main.cpp", "main_ch4": "ch4/Main.cpp", "main_ch9": "ch9/Main.cpp",
              "main_ch9mt": "ch9/MT/Main.cpp", "main_ch9cuda": "ch9/CUDA/Main.cpp"}
 
 

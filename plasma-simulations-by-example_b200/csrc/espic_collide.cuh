@@ -198,3 +198,79 @@ extern "C" int espic_dsmc_mex(espic_ctx *c, int sp, double dt, double *sigma_cr_
     if (num_cols) *num_cols = (long long)h[5];
     return 0;
 }
+
+// =====================================================================================================
+// MCC_CEX::apply (ch4/Collisions.cpp:43-82): every source particle collides with the mesh-averaged target gas with
+// probability P = 1 - exp(-n*sigma*|v - u|*dt), n and u gathered from the target's density and stream-velocity fields
+// (Field::gather, ch4/Field.h:234-256), sigma = 1e-16 m^2; a colliding particle's velocity becomes zero (the reference has the
+// charge-exchange assignment itself commented out, :78-79).  Philox: particle i compares against element 0 of block i.
+// =====================================================================================================
+
+// trilinear gather of component c of a node array with `stride` doubles per node, the reference's term order
+__device__ __forceinline__ double gather_node_field(const MeshC &m, const double *__restrict__ f, int stride, int c,
+                                                    int i, int j, int k, double di, double dj, double dk)
+{
+    const long long u = node_u(m, i, j, k), sj = m.ni, sk = (long long)m.ni * m.nj;
+    const double ai = 1 - di, aj = 1 - dj, ak = 1 - dk;
+    double v = f[stride * u + c] * ai * aj * ak;
+    v = v + f[stride * (u + 1) + c] * di * aj * ak;
+    v = v + f[stride * (u + 1 + sj) + c] * di * dj * ak;
+    v = v + f[stride * (u + sj) + c] * ai * dj * ak;
+    v = v + f[stride * (u + sk) + c] * ai * aj * dk;
+    v = v + f[stride * (u + 1 + sk) + c] * di * aj * dk;
+    v = v + f[stride * (u + 1 + sj + sk) + c] * di * dj * dk;
+    v = v + f[stride * (u + sj + sk) + c] * ai * dj * dk;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_mcc_cex(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                 const double *__restrict__ z, double *vx, double *vy, double *vz, long long n,
+                                                 const double *__restrict__ tden, const double *__restrict__ tvel, double dt,
+                                                 uint64_t seed, uint32_t stream, uint32_t step, unsigned long long *ncols)
+{
+    const long long q = blockIdx.x * 256ll + threadIdx.x;
+    bool hit = false;
+    if (q < n) {
+        int i, j, k; double di, dj, dk;
+        cell3(m, x[q], y[q], z[q], i, j, k, di, dj, dk);
+        if (i < 0) i = 0;
+        if (j < 0) j = 0;
+        if (k < 0) k = 0;
+        const double ut0 = gather_node_field(m, tvel, 3, 0, i, j, k, di, dj, dk);
+        const double ut1 = gather_node_field(m, tvel, 3, 1, i, j, k, di, dj, dk);
+        const double ut2 = gather_node_field(m, tvel, 3, 2, i, j, k, di, dj, dk);
+        const double nn = gather_node_field(m, tden, 1, 0, i, j, k, di, dj, dk);
+        const double r0 = vx[q] - ut0, r1 = vy[q] - ut1, r2 = vz[q] - ut2;
+        const double v_rel_mag = sqrt((r0 * r0 + r1 * r1) + r2 * r2);
+        const double sigma = 1e-16;
+        const double P = 1 - exp(-nn * sigma * v_rel_mag * dt);
+        double u0, u1;
+        philox_uniform2(seed, stream, step, (uint64_t)q, u0, u1);
+        if (P >= u0) { vx[q] = 0; vy[q] = 0; vz[q] = 0; hit = true; }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(ncols, (unsigned long long)__popc(b));
+}
+
+extern "C" int espic_mcc_cex(espic_ctx *c, int source_sp, int target_sp, double dt, uint64_t seed, uint32_t stream, uint32_t step,
+                             long long *num_cols)
+{
+    SP_CHECK(c, source_sp);
+    SP_CHECK(c, target_sp);
+    CK(cudaSetDevice(c->device));
+    Species &s = c->sp[source_sp];
+    if (num_cols) *num_cols = 0;
+    if (s.np == 0) return 0;
+    int r;
+    if ((r = espic_ensure_moments(c, target_sp))) return r;       // stream velocity: zero until computeGasProperties ran
+    Species &t = c->sp[target_sp];
+    CK(cudaMemsetAsync(c->dscal + 7, 0, sizeof(unsigned long long), c->stream));
+    k_mcc_cex<<<nblk(s.np, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.np, t.den,
+                                                      t.mom + 7 * c->m.nn, dt, seed, stream, step, c->dscal + 7);
+    LAUNCH_CHECK(c);
+    unsigned long long *h = (unsigned long long *)c->hpin;
+    CK(cudaMemcpyAsync(h + 7, c->dscal + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (num_cols) *num_cols = (long long)h[7];
+    return 0;
+}

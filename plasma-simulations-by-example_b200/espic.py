@@ -22,7 +22,7 @@ EXPORTS = [
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
-    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
+    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
 ]
@@ -93,6 +93,7 @@ def load():
                                      C.POINTER(C.c_longlong)]
     L.espic_dsmc_mex.argtypes = [vp, C.c_int, C.c_double, dp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_compute_mpc.argtypes = [vp, C.c_int]
+    L.espic_mcc_cex.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_species_diag.argtypes = [vp, C.c_int, dp]
     L.espic_update_average.argtypes = [vp, C.c_int]
     L.espic_sample_moments.argtypes = [vp, C.c_int]
@@ -187,7 +188,7 @@ class Engine:
 
     def set_field(self, which, arr, sp=0):
         arr = np.ascontiguousarray(arr, dtype=np.int32 if which == OBJECT_ID else np.float64)
-        assert arr.size == self.nn * (3 if which == EF else 1)
+        assert arr.size == self.nn * (3 if which in (EF, VEL, NV_SUM) else 1)
         self._ck(self.L.espic_field_upload(self.h, which, sp, arr.ctypes.data_as(C.c_void_p)))
 
     def field_devptr(self, which, sp=0):
@@ -286,6 +287,11 @@ class Engine:
         cols = C.c_longlong(0)
         self._ck(self.L.espic_dsmc_mex(self.h, sp, dt, _dp(s), seed, stream, step, C.byref(cols)))
         return cols.value, float(s[0])
+
+    def mcc_cex(self, source_sp, target_sp, dt, seed, stream, step):
+        cols = C.c_longlong(0)
+        self._ck(self.L.espic_mcc_cex(self.h, source_sp, target_sp, dt, seed, stream, step, C.byref(cols)))
+        return cols.value
 
     def compute_mpc(self, sp):
         self._ck(self.L.espic_compute_mpc(self.h, sp))

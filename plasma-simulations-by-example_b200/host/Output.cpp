@@ -19,6 +19,12 @@ std::ofstream f_diag;
 
 void Output::fields(World &world, std::vector<Species> &species)
 {
+    // ch4 (ch4/Output.cpp:12-118): a program that samples velocity moments also gets stream velocity, temperature and the
+    // macroparticles-per-cell array, and its samples are restarted after every file until steady state
+    bool moments = false;
+    for (Species &sp : species) moments = moments || sp.samplesMoments();
+    if (moments)
+        for (Species &sp : species) sp.computeGasProperties();
     std::stringstream name;
     name << "results/fields_" << std::setfill('0') << std::setw(5) << world.getTs() << ".vti";
     std::ofstream out(name.str());
@@ -36,8 +42,21 @@ void Output::fields(World &world, std::vector<Species> &species)
     data_array(out, "rho", 1, "Float64", world.rho);
     for (Species &sp : species) data_array(out, "nd." + sp.name, 1, "Float64", sp.den);
     for (Species &sp : species) data_array(out, "nd-ave." + sp.name, 1, "Float64", sp.den_ave);
+    if (moments) {
+        for (Species &sp : species) data_array(out, "vel." + sp.name, 3, "Float64", sp.vel);
+        for (Species &sp : species) data_array(out, "T." + sp.name, 1, "Float64", sp.T);
+    }
     data_array(out, "ef", 3, "Float64", world.ef);
-    out << "</PointData>\n</ImageData>\n</VTKFile>\n";
+    out << "</PointData>\n";
+    if (moments) {
+        out << "<CellData>\n";
+        for (Species &sp : species) data_array(out, "mpc." + sp.name, 1, "Float64", sp.mpc);
+        out << "</CellData>\n";
+    }
+    out << "</ImageData>\n</VTKFile>\n";
+    out.close();
+    if (moments && !world.isSteadyState())
+        for (Species &sp : species) sp.clearSamples();
 }
 
 void Output::screenOutput(World &world, std::vector<Species> &species)

@@ -11,7 +11,7 @@ static int default_sort_every()
 
 Species::Species(std::string name, double mass, double charge, double mpw0, World &world)
     : name(name), mass(mass), charge(charge), mpw0(mpw0), den(world.ni, world.nj, world.nk), den_ave(world.ni, world.nj, world.nk),
-      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), sort_every(default_sort_every()), world(world), reflect(false)
+      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), mpc(world.ni - 1, world.nj - 1, world.nk - 1), sort_every(default_sort_every()), world(world), reflect(false)
 {
     sp_id = world.register_species(this, mass, charge, mpw0);
     bind_fields();
@@ -19,7 +19,7 @@ Species::Species(std::string name, double mass, double charge, double mpw0, Worl
 
 Species::Species(std::string name, double mass, double charge, World &world)
     : name(name), mass(mass), charge(charge), mpw0(0), den(world.ni, world.nj, world.nk), den_ave(world.ni, world.nj, world.nk),
-      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), sort_every(default_sort_every()), world(world), reflect(true)
+      T(world.ni, world.nj, world.nk), vel(world.ni, world.nj, world.nk), mpc(world.ni - 1, world.nj - 1, world.nk - 1), sort_every(default_sort_every()), world(world), reflect(true)
 {
     sp_id = world.register_species(this, mass, charge, 0);
     bind_fields();
@@ -27,7 +27,7 @@ Species::Species(std::string name, double mass, double charge, World &world)
 
 Species::Species(Species &&o)
     : name(o.name), mass(o.mass), charge(o.charge), mpw0(o.mpw0), den(std::move(o.den)), den_ave(std::move(o.den_ave)),
-      T(std::move(o.T)), vel(std::move(o.vel)), sort_every(o.sort_every), world(o.world), sp_id(o.sp_id), reflect(o.reflect), n_advance(o.n_advance), diag_valid(o.diag_valid)
+      T(std::move(o.T)), vel(std::move(o.vel)), mpc(std::move(o.mpc)), sort_every(o.sort_every), world(o.world), sp_id(o.sp_id), reflect(o.reflect), n_advance(o.n_advance), diag_valid(o.diag_valid), moments_used(o.moments_used)
 {
     for (int q = 0; q < 7; q++) pending[q] = std::move(o.pending[q]);
     for (int q = 0; q < 5; q++) diag[q] = o.diag[q];
@@ -133,6 +133,7 @@ void Species::sampleMoments()
 {
     flush();
     espic_host::check(espic_sample_moments(world.engine(), sp_id), "espic_sample_moments");
+    moments_used = true;
 }
 
 void Species::computeGasProperties()
@@ -144,6 +145,15 @@ void Species::computeGasProperties()
     }
     T.mark_device_wrote();
     vel.mark_device_wrote();
+}
+
+// ch4/Species.cpp:228-235
+void Species::computeMPC()
+{
+    flush();
+    espic_host::check(espic_compute_mpc(world.engine(), sp_id), "espic_compute_mpc");
+    if (!mpc.bound()) mpc.bind(world.engine(), ESPIC_MPC, sp_id, true);
+    mpc.mark_device_wrote();
 }
 
 void Species::clearSamples()

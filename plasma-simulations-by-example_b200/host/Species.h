@@ -50,6 +50,8 @@ public:
     void sampleMoments();
     void computeGasProperties();
     void clearSamples();
+    void computeMPC();                               // macroparticles per cell (ch4/Species.cpp:228-235)
+    bool samplesMoments() const { return moments_used; }
 
     const std::string name;
     const double mass;
@@ -60,6 +62,7 @@ public:
     Field den_ave;
     Field T;          // temperature (ch4/Species.h:85), valid after computeGasProperties()
     Field3 vel;       // stream velocity (ch4/Species.h:86)
+    Field mpc;        // macroparticles per cell, (ni-1)(nj-1)(nk-1) (ch4/Species.h:88), valid after computeMPC()
 
     // ---- not in the reference API ----
     int id() const { return sp_id; }
@@ -78,6 +81,7 @@ protected:
     long long n_advance = 0;
     std::vector<double> pending[7];
     bool diag_valid = false;
+    bool moments_used = false;
     double diag[5] = {0, 0, 0, 0, 0};
     void bind_fields();
     void refresh_diag();

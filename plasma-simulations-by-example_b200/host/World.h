@@ -79,6 +79,9 @@ public:
     int U(int i, int j, int k) { return object_id.U(i, j, k); }
 
     bool steadyState(std::vector<Species> &species);
+    bool isSteadyState() const { return steady_state; }                       // ch4/World.h:76
+    double getCellVolume() const { return dh(0) * dh(1) * dh(2); }             // ch4/World.h:51
+    unsigned next_interaction_stream() { return 0x200u + n_interactions++; }   // Philox stream ids of the collision operators
     void computeChargeDensity(std::vector<Species> &species);
     double getPE();
     void addSphere(double3 x0, double radius, double phi_sphere);
@@ -112,6 +115,7 @@ protected:
     double sphere_rad2 = 0;
     std::chrono::time_point<std::chrono::high_resolution_clock> time_start;
     bool steady_state = false;
+    unsigned n_interactions = 0;
     double last_mass = 0, last_mom = 0, last_en = 0;
     int num_threads = 1;
 

@@ -23,7 +23,7 @@ PKG = os.path.join(sf.ROOT, "plasma-simulations-by-example_b200")
 HOST = os.path.join(PKG, "host")
 BIN = os.path.join(PKG, "bin")
 REF = "/root/reference"
-MAINS = ["ch2/Main.cpp", "ch3/ver2/Main.cpp", "ch9/Main.cpp", "ch9/MT/Main.cpp", "ch9/CUDA/Main.cpp",
+MAINS = ["ch2/Main.cpp", "ch3/ver2/Main.cpp", "ch4/Main.cpp", "ch9/Main.cpp", "ch9/MT/Main.cpp", "ch9/CUDA/Main.cpp",
          "ch3/ver2/Output.cpp", "ch2/Output.cpp"]
 
 
