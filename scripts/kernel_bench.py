@@ -62,6 +62,29 @@ def main():
     timed("sample_moments (5+ steps after sort)", lambda: e.sample_moments(sp), 56, reps=3)
     e.sort_by_cell(sp)
     timed("sample_moments (sorted)", lambda: e.sample_moments(sp), 56, reps=3)
+    # ch4 operators on the same particles (the ions stand in for a neutral gas: a second species with charge 0)
+    if not args.only or "ch4" in args.only:
+        n4 = min(n, 50_000_000)
+        gas = e.add_species(16 * B.AMU, 0.0, mpw, capacity=n4 + 1024)
+        t = B.make_particles_device(torch, n4, 999, mpw, dev)
+        e.upload_device(gas, [t[c].data_ptr() for c in range(7)], n4, mpw)
+        e.sync(); del t; torch.cuda.empty_cache()
+        sp_saved, sp = sp, gas
+        step = [0]
+
+        def surf():
+            step[0] += 1
+            e.push_surface(gas, B.DT, gas, gas, 7, 0, step[0])
+        timed("ch4 push_surface neutral + removal", surf, 104, reps=3)
+        sig = [1e-14]
+
+        def dsmc():
+            step[0] += 1
+            cols, sig[0] = e.dsmc_mex(gas, B.DT, sig[0], 7, 1, step[0])
+        timed("ch4 dsmc_mex (unsorted)", dsmc, 48, reps=3)
+        timed("ch4 compute_mpc", lambda: e.compute_mpc(gas), 24, reps=3)
+        timed("ch4 mcc_cex", lambda: e.mcc_cex(gas, sp_saved, B.DT, 7, 2, 1), 72, reps=3)
+        sp = sp_saved
     print("launches:", e.kernel_launches())
 
 

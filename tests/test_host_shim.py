@@ -341,3 +341,37 @@ def test_surface_flow_through_class_api(tmp_path):
         c = np.array([0, 0, 0.15])[:, None]
         assert np.all(((got["part"][:3] - c) ** 2).sum(0) > 0.05 ** 2), "no live particle inside the sphere"
     close(st.phi, w.phi, 1e-9, "phi")
+
+
+@pytest.mark.gpu
+def test_reference_ch4_main_neutral_flow_statistics(tmp_path):
+    """The reference's own ch4/Main.cpp (warm neutral beam past the sphere, diffuse re-emission from its surface, DSMC collisions,
+    velocity moments, macroparticles per cell; 2000 steps, ~6e6 particles), compiled unchanged against the shim and run on the GPU,
+    must reproduce the observables of the reference build within statistical tolerance (mt19937 seeded from random_device there,
+    Philox here).  Golden: tests/golden/ch4_neutral_flow_statistics.json, generated by tests/golden/make_ch4_statistics.py from a
+    run of the unmodified reference (oracle/_ref/ref_ch4_main)."""
+    import json
+    import sys
+    exe = os.path.join(BIN, "main_ch4")
+    gold = os.path.join(sf.ROOT, "tests", "golden", "ch4_neutral_flow_statistics.json")
+    if not os.path.exists(exe):
+        pytest.skip("bin/main_ch4 is built only where the reference tree is present")
+    sys.path.insert(0, os.path.join(sf.ROOT, "tests", "golden"))
+    from make_ch4_statistics import summarise
+    ref = json.load(open(gold))
+    os.makedirs(str(tmp_path / "results"))
+    with open(str(tmp_path / "run.log"), "w") as log:
+        subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=900, check=True,
+                       env=dict(os.environ, ESPIC_SEED="4242"))
+    got = summarise(str(tmp_path))
+    for ts, row in ref["diag"].items():
+        for key in ("mp_count", "real_count", "pz", "KE"):
+            assert abs(got["diag"][ts][key] / row[key] - 1) < 0.005, (ts, key, got["diag"][ts][key], row[key])
+    assert abs(got["steady_state_ts"] - ref["steady_state_ts"]) <= 60
+    assert abs(got["mpc_total"] / ref["mpc_total"] - 1) < 0.005
+    # mesh fields at the last step: plane means within 2 % of the profile maximum, the 3x3-node column through the sphere
+    # (stagnation pile-up in front of it, heated re-emitted gas, wake behind) within 10 %
+    for key, tol in (("nd_ave_k_profile", 0.02), ("w_k_profile", 0.02), ("T_k_profile", 0.05), ("mpc_k_profile", 0.02),
+                     ("nd_ave_axis_profile", 0.10), ("T_axis_profile", 0.15)):
+        a, b = np.array(got[key]), np.array(ref[key])
+        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (key, np.abs(a - b).max() / np.abs(b).max())
