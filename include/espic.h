@@ -208,6 +208,32 @@ int espic_comm_init(espic_ctx *ctx, int rank, int nranks, const void *id128);
  * Replaces ch9/MPI Field::updateBoundaries (ch9/MPI/include/Field.h:122-179). */
 int espic_allreduce_density(espic_ctx *ctx, int sp);
 
+/* ---- multi-GPU: spatial decomposition with particle migration ------------------- */
+
+/* World::initMPIDomain (ch9/MPI/include/World.h:73-128): this context simulates part `part` of `parts` slabs cut along k.
+ * k_bounds[parts+1] are CELL planes, k_bounds[0] = 0 < ... < k_bounds[parts] = nk-1; part r owns the cells
+ * k_bounds[r] <= k < k_bounds[r+1].  Coordinates stay global and every node array keeps its full size (the reference shifts
+ * x0 per process), so gather, scatter and the push are the single-domain arithmetic; a part's scatter only touches its own node
+ * planes, and the plane two parts share receives both contributions through the density all-reduce of espic_deposit, as
+ * ch9/MPI Field::updateBoundaries (ch9/MPI/include/Field.h:122-179) adds them. */
+int espic_domain_set(espic_ctx *ctx, int parts, int part, const int *k_bounds);
+int espic_domain_get(espic_ctx *ctx, int *parts, int *part, int *k_bounds /* parts+1 ints, may be NULL */);
+
+/* Species::transferParticles (ch9/MPI/src/Species.cpp:204-313) after a push: every particle whose cell belongs to another part
+ * is sent there (any part, not only a face neighbour; nothing is discarded -- the reference drops particles that overshoot the
+ * neighbour, :285-288), the holes are closed in espic_push's swap-with-last order, arrivals are appended by ascending source
+ * part in the sender's particle order.  Counts travel as one all-gathered matrix, the particles in one NCCL send/recv group that
+ * writes straight behind the receiver's live particles.  Needs espic_comm_init with nranks == parts and rank == part.
+ * Collective: every part must call it. */
+int espic_migrate(espic_ctx *ctx, int sp, long long *n_sent, long long *n_received);
+
+/* The two halves of espic_migrate for callers that move the segments themselves (several parts on one device, other
+ * transports): pack removes the leavers and returns counts[parts]; segment returns the device address of the packed particles
+ * bound for `dest` as SoA [7][count] doubles (valid until the next pack); the receiver appends them with
+ * espic_species_upload_device(..., append=1) in ascending source order. */
+int espic_migrate_pack(espic_ctx *ctx, int sp, long long *counts);
+int espic_migrate_segment(espic_ctx *ctx, int dest, void **dptr, long long *count);
+
 #ifdef __cplusplus
 }
 #endif

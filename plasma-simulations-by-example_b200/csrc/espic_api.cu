@@ -149,6 +149,7 @@ extern "C" void espic_destroy(espic_ctx *c)
     cudaStreamSynchronize(c->stream);
     espic_comm_destroy(c);
     espic_mg_destroy(c);
+    espic_migrate_destroy(c);
     cudaFree(c->phi); cudaFree(c->rho); cudaFree(c->ef); cudaFree(c->ef4); cudaFree(c->node_vol); cudaFree(c->object_id);
     for (int s = 0; s < c->nsp; s++) {
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }

@@ -16,6 +16,10 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)(void) = nullptr;
+    int (*GroupEnd)(void) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -31,6 +35,10 @@ static int nccl_load()
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)(void))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)(void))dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { espic_set_error("libnccl lacks required symbols"); return -1; }
     g_nccl.h = h;
@@ -108,6 +116,27 @@ int espic_comm_allgather_bytes(espic_ctx *c, void *buf, size_t bytes)
     if (c->nranks <= 1 || !c->nccl) return 0;
     if (!g_nccl.AllGather) { espic_set_error("libnccl lacks ncclAllGather"); return -1; }
     NCK(g_nccl.AllGather((char *)buf + (size_t)c->rank * bytes, buf, bytes, 0 /* ncclInt8 */, (ncclComm_t)c->nccl, c->stream));
+    return 0;
+}
+
+// particle migration (espic_migrate.cuh): one NCCL group moves every (source, destination) segment.  A segment is SoA
+// [7][count]; component q of the segment from `peer` lands at recvp[peer][q], i.e. straight in the receiver's particle arrays.
+// Both sides know every count from the all-gathered matrix, so each send has exactly one matching receive, in component order.
+int espic_comm_exchange_segments(espic_ctx *c, int parts, int me, const double *const *sendp, const long long *sendn,
+                                 double *(*recvp)[7], const long long *recvn)
+{
+    if (c->nranks <= 1 || !c->nccl) return 0;
+    if (!g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) { espic_set_error("libnccl lacks ncclSend/ncclRecv"); return -1; }
+    ncclComm_t comm = (ncclComm_t)c->nccl;
+    NCK(g_nccl.GroupStart());
+    for (int peer = 0; peer < parts; peer++) {
+        if (peer == me) continue;
+        for (int q = 0; q < 7; q++) {
+            if (sendn[peer] > 0) NCK(g_nccl.Send(sendp[peer] + (size_t)q * sendn[peer], (size_t)sendn[peer], ncclFloat64, peer, comm, c->stream));
+            if (recvn[peer] > 0) NCK(g_nccl.Recv(recvp[peer][q], (size_t)recvn[peer], ncclFloat64, peer, comm, c->stream));
+        }
+    }
+    NCK(g_nccl.GroupEnd());
     return 0;
 }
 

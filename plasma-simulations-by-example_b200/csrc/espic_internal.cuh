@@ -76,6 +76,7 @@ struct espic_ctx {
     int sm_count = 148;
     void *mg = nullptr;            // MgHierarchy of the multigrid-preconditioned solver (espic_mg.cuh)
     void *slab = nullptr;          // SlabState of the slab-decomposed multi-GPU variant (espic_mg.cuh)
+    void *mig = nullptr;           // MigState of the spatial decomposition with particle migration (espic_migrate.cuh)
     // comm
     void *nccl = nullptr; int rank = 0, nranks = 1;
 };
@@ -107,6 +108,9 @@ int  espic_comm_max_double(espic_ctx *c, double *v);
 int  espic_comm_allreduce_acc(espic_ctx *c, Species &s);
 int  espic_comm_allgather_doubles(espic_ctx *c, double *buf, size_t count);
 int  espic_comm_allgather_bytes(espic_ctx *c, void *buf, size_t bytes);
+int  espic_comm_exchange_segments(espic_ctx *c, int parts, int me, const double *const *sendp, const long long *sendn,
+                                  double *(*recvp)[7], const long long *recvn);
+void espic_migrate_destroy(espic_ctx *c);   // espic_migrate.cuh (espic_particles.cu)
 
 // ---- device helpers ---------------------------------------------------------------------------
 

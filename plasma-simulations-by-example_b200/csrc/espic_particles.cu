@@ -1215,3 +1215,4 @@ extern "C" int espic_species_diag(espic_ctx *c, int sp, double out[5])
 
 #include "espic_surface.cuh"
 #include "espic_collide.cuh"
+#include "espic_migrate.cuh"

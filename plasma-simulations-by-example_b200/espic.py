@@ -25,6 +25,7 @@ EXPORTS = [
     "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
+    "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment",
 ]
 
 
@@ -106,6 +107,12 @@ def load():
     L.espic_comm_unique_id.argtypes = [vp]
     L.espic_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.espic_allreduce_density.argtypes = [vp, C.c_int]
+    ip, llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+    L.espic_domain_set.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.espic_domain_get.argtypes = [vp, ip, ip, ip]
+    L.espic_migrate.argtypes = [vp, C.c_int, llp, llp]
+    L.espic_migrate_pack.argtypes = [vp, C.c_int, llp]
+    L.espic_migrate_segment.argtypes = [vp, C.c_int, C.POINTER(vp), llp]
     _lib = L
     return L
 
@@ -324,3 +331,35 @@ class Engine:
 
     def comm_init(self, rank, nranks, uid):
         self._ck(self.L.espic_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
+
+    def allreduce_density(self, sp):
+        self._ck(self.L.espic_allreduce_density(self.h, sp))
+
+    # ---- spatial decomposition with particle migration (ch9/MPI initMPIDomain / transferParticles)
+    def set_domain(self, parts, part, k_bounds):
+        kb = (C.c_int * (parts + 1))(*[int(k) for k in k_bounds])
+        self._ck(self.L.espic_domain_set(self.h, parts, part, kb))
+        self.parts, self.part = parts, part
+
+    def migrate(self, sp):
+        """collective over the communicator: returns (sent, received)"""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.espic_migrate(self.h, sp, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def migrate_pack(self, sp):
+        counts = (C.c_longlong * self.parts)()
+        self._ck(self.L.espic_migrate_pack(self.h, sp, counts))
+        return [int(v) for v in counts]
+
+    def migrate_segment(self, dest):
+        """(device address, count) of the packed SoA [7][count] segment bound for part `dest`"""
+        p, n = C.c_void_p(), C.c_longlong(0)
+        self._ck(self.L.espic_migrate_segment(self.h, dest, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+
+def slab_bounds(nk, parts):
+    """k_bounds of `parts` equal slabs of cells (the last one takes the remainder), the default cut of bench.py"""
+    cells = nk - 1
+    return [cells * r // parts for r in range(parts)] + [cells]

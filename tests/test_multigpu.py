@@ -116,3 +116,79 @@ def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0):
     scale = np.abs(ref.phi).max()
     assert np.abs(r0["phi"] - ref.phi).max() <= 1e-10 * scale
     assert np.abs(r0["ef"] - ref.ef).max() <= 1e-9 * np.abs(ref.ef).max()
+
+
+def _migrate_worker(rank, world, port, path):
+    import torch.distributed as dist
+    import migration_model as mm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    es = _espic()
+    d = np.load(path)
+    st = sf.state_from_dict(d, "in_")
+    kb = es.slab_bounds(st.nk, world)
+    dhz = (st.xm[2] - st.x0[2]) / (st.nk - 1)
+    st.species[0]["part"] = mm.split_by_owner(st.species[0]["part"], st.x0[2], dhz, st.nk, kb)[rank]
+    g = GpuEngine(st, device=rank, fixed=True)
+    uid = [g.e.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.e.comm_init(rank, world, uid[0])
+    g.e.set_domain(world, rank, kb)
+    sp = g.species[0]
+    out = {}
+    moved = 0
+    for step in range(3):                       # frozen field: order and bits against the model
+        g.e.push(sp, st.dt, es.WALL_ABSORB, 0)
+        sent, recv = g.e.migrate(sp)
+        moved += sent
+        out["frozen%d" % step] = g.e.download(sp)
+    for step in range(2):                       # full cycle: the decomposed run is the single-domain run
+        g.e.push(sp, st.dt, es.WALL_ABSORB, 0)
+        sent, recv = g.e.migrate(sp)
+        moved += sent
+        res = g.run(["deposit", "rho", "solve_mg:2000:1e-8", "ef"])
+    out.update(den=res.species[0]["den"], phi=res.phi, part=res.species[0]["part"], moved=moved, diag=g.e.diag(sp))
+    np.savez(path + ".rank%d.npz" % rank, **out)
+    dist.barrier()
+    g.e.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs")
+def test_two_rank_migration_matches_single_gpu(tmp_path):
+    """espic_migrate over NCCL (count matrix all-gather, grouped send/recv straight into the particle arrays): with a frozen
+    field every rank's particles AND their order equal the host model bit for bit; over full PIC cycles (fixed-point deposit
+    all-reduced over the two slabs, replicated multigrid solve) the decomposed run reproduces the single-GPU run."""
+    import torch.multiprocessing as mp
+    import migration_model as mm
+    from test_migration import _oracle_parts, _oracle_decomposed_steps
+    es = _espic()
+    n = 60000
+    w, sp = cases.sphere_case(seed=93, ni=16, nj=12, nk=25, n=n, amp=5.0, mpw=1e10 * 0.016 / n)
+    st = sf.state_from_oracle(w, [sp], 2e-6)
+    path = str(tmp_path / "in.npz")
+    np.savez(path, **sf.state_to_dict(st, "in_"))
+    mp.spawn(_migrate_worker, args=(2, 29800 + os.getpid() % 1000, path), nprocs=2, join=True)
+    r = [np.load(path + ".rank%d.npz" % q) for q in range(2)]
+    kb = es.slab_bounds(st.nk, 2)
+    hist = _oracle_decomposed_steps(w, _oracle_parts(w, sp, kb), kb, st.dt, 3)
+    for step in range(3):
+        for q in range(2):
+            got, want = r[q]["frozen%d" % step], hist[step][0][q]
+            assert got.shape == want.shape and np.array_equal(got.view(np.uint64), want.view(np.uint64)), (step, q)
+    assert int(r[0]["moved"]) + int(r[1]["moved"]) > 0
+    one = GpuEngine(st, fixed=True)
+    for step in range(5):
+        one.e.push(one.species[0], st.dt, es.WALL_ABSORB, 0)
+        if step >= 3:
+            ref = one.run(["deposit", "rho", "solve_mg:2000:1e-8", "ef"])
+    assert r[0]["part"].shape[1] + r[1]["part"].shape[1] == ref.species[0]["part"].shape[1]
+    assert np.array_equal(r[0]["den"], r[1]["den"]) and np.array_equal(r[0]["phi"], r[1]["phi"]), "both ranks hold the same fields"
+    den = ref.species[0]["den"]
+    assert np.abs(r[0]["den"] - den).max() <= 1e-9 * np.abs(den).max()
+    assert np.abs(r[0]["phi"] - ref.phi).max() <= 1e-6 * np.abs(ref.phi).max()
+    dsum = r[0]["diag"] + r[1]["diag"]
+    dref = one.e.diag(one.species[0])
+    for q in (0, 3, 4):                        # sum of weights, p_z, kinetic energy
+        assert abs(dsum[q] - dref[q]) <= 1e-9 * abs(dref[q]), (q, dsum[q], dref[q])
