@@ -140,14 +140,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
-def make_particles_device(torch, n, seed, mpw, dev):
-    """Uniform in the box outside the sphere, drift + thermal velocity; generated on the device."""
+def make_particles_device(torch, n, seed, mpw, dev, zrange=None):
+    """Uniform in the box (or in the z range of one slab) outside the sphere, drift + thermal velocity; generated on the device."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     t = torch.empty((7, n), dtype=torch.float64, device=dev)
+    lo, hi = list(X0), list(XM)
+    if zrange is not None:
+        lo[2], hi[2] = zrange
     for c in range(3):
         t[c].uniform_(0.0, 1.0, generator=g)
-        t[c].mul_(XM[c] - X0[c]).add_(X0[c])
+        t[c].mul_(hi[c] - lo[c]).add_(lo[c])
     (cx, cy, cz), r, _ = SPHERE
     d2 = (t[0] - cx) ** 2 + (t[1] - cy) ** 2 + (t[2] - cz) ** 2
     t[2][d2 <= (1.001 * r) ** 2] += 0.2          # out of the sphere, still inside the box
@@ -255,6 +258,9 @@ def main():
                          "preconditioner, solved by every rank; mgslab: the multigrid solve decomposed into one k-slab per rank")
     ap.add_argument("--sort-every", type=int, default=8)
     ap.add_argument("--fixed-point", action="store_true", help="bit-reproducible int64 deposition")
+    ap.add_argument("--decomp", action="store_true",
+                    help="N>1: spatial decomposition into k-slabs with particle migration (espic_migrate, ch9/MPI's scheme) "
+                         "instead of sharding the particles by index")
     ap.add_argument("--fuse", action="store_true", help="scatter inside the push kernel instead of the tiled deposit kernel")
     ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -309,10 +315,20 @@ def main():
         e.comm_init(rank, world, uid[0])
     n_gen = n_local if args.impl == "ours" else min(n_local, int(2e7))   # reference arm only needs a warm field
     mpw_gen = mpw if args.impl == "ours" else N0 * box_vol / n_gen
-    t = make_particles_device(torch, n_gen, 12345 + rank, mpw_gen, dev)
+    decomp = args.decomp and world > 1 and args.impl == "ours"
+    zrange = None
+    if decomp:
+        kb = es.slab_bounds(n_mesh, world)
+        dhz = (XM[2] - X0[2]) / (n_mesh - 1)
+        zrange = (X0[2] + kb[rank] * dhz, X0[2] + kb[rank + 1] * dhz)
+        e.set_domain(world, rank, kb)
+        workload += "-kslab-migration"
+    t = make_particles_device(torch, n_gen, 12345 + rank, mpw_gen, dev, zrange)
     e.upload_device(sp, [t[c].data_ptr() for c in range(7)], n_gen, mpw_gen)
     e.sync()
     del t
+    if decomp:
+        log("initial migration: sent %d, received %d" % e.migrate(sp))     # particles moved out of the sphere change slab
     torch.cuda.empty_cache()
     dmode = es.DEPOSIT_FIXED if args.fixed_point else es.DEPOSIT_FP64
     pflags = (es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if args.fixed_point else 0)) if args.fuse else 0
@@ -333,6 +349,8 @@ def main():
 
     def pic_step(i, count):
         e.push(sp, DT, es.WALL_ABSORB, pflags)
+        if decomp:
+            e.migrate(sp)
         n_live = e.count(sp)
         if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
             e.sort_by_cell(sp)       # between push and deposit: the scatter sees perfectly ordered particles
@@ -361,6 +379,7 @@ def main():
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
     counts = []
     kernel_ms = []
+    migrated = []
     launches0 = e.kernel_launches()
     if world > 1:
         dist.barrier()
@@ -373,6 +392,8 @@ def main():
         pe[0].record()
         n_before = e.count(sp)
         e.push(sp, DT, es.WALL_ABSORB, pflags)
+        if decomp:
+            migrated.append(e.migrate(sp)[0])    # inside the push phase of the timed region
         pe[1].record()
         kernel_ms.append(e.last_push_ms())       # CUDA events around the k_push launch itself, on the launching stream
         n_live = e.count(sp)
@@ -479,6 +500,8 @@ def main():
         for i in range(nq):
             pushed_q += e.count(sp)
             e.push(sp, DT, es.WALL_ABSORB, pflags)
+            if decomp:
+                e.migrate(sp)
             if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
                 e.sort_by_cell(sp)
             e.deposit(sp, dmode)
@@ -515,8 +538,9 @@ def main():
             "config": {"workload": workload, "mesh": [n_mesh] * 3, "particles_per_gpu": n_local, "solver": args.solver,
                        "solver_tol": tol, "dt": DT, "sort_every": args.sort_every,
                        "deposit": "fixed-point int64" if args.fixed_point else "fp64 atomics",
-                       "parallelism": "particle-index sharding x%d, NCCL density all-reduce, %s" % (
-                           world, "k-slab multigrid Poisson solve over peer memory" if (args.solver == "mgslab" and world > 1) else "replicated field solve"),
+                       "parallelism": "%s x%d, NCCL density all-reduce, %s" % (
+                           "k-slab spatial decomposition with particle migration (%.3g particles sent per rank per step)" % np.mean(migrated)
+                           if decomp else "particle-index sharding", world, "k-slab multigrid Poisson solve over peer memory" if (args.solver == "mgslab" and world > 1) else "replicated field solve"),
                        "l2": "inputs (%.1f GB of particles per GPU) are larger than L2" % (56 * n_local / 1e9),
                        "pcg_iters_per_step": float(np.mean(lin)), "newton_iters_per_step": float(np.mean([c[2]["nr_iters"] for c in counts]))},
             "phases_ms": {"sort(amortised)": float(phase_ms[0]), "push+removal": push_ms, "deposit+rho": float(phase_ms[2]),
