@@ -40,6 +40,27 @@ PUSH_BYTES = 104          # algorithmic bytes per particle of the fused push+dep
 
 T_START = time.time()
 
+# stdout carries exactly ONE line, the JSON result: libraries that print to file descriptor 1 (NCCL's "NCCL version ..." banner
+# under NCCL_DEBUG=VERSION, for one) are sent to stderr, the result goes to the saved descriptor
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_RESULT_FD, line)
+
 
 def log(msg):
     if os.environ.get("BENCH_VERBOSE", "1") != "0":
@@ -153,13 +174,32 @@ def make_particles_device(torch, n, seed, mpw, dev, zrange=None):
         t[c].mul_(hi[c] - lo[c]).add_(lo[c])
     (cx, cy, cz), r, _ = SPHERE
     d2 = (t[0] - cx) ** 2 + (t[1] - cy) ** 2 + (t[2] - cz) ** 2
-    t[2][d2 <= (1.001 * r) ** 2] += 0.2          # out of the sphere, still inside the box
+    if zrange is None:
+        t[2][d2 <= (1.001 * r) ** 2] += 0.2          # out of the sphere, still inside the box
+    else:
+        for _ in range(64):                          # slab-local: redraw the points that fell into the sphere (uniform outside it)
+            bad = torch.nonzero(d2 <= (1.001 * r) ** 2).flatten()
+            if bad.numel() == 0:
+                break
+            for c in range(3):
+                t[c][bad] = torch.rand(bad.numel(), generator=g, dtype=torch.float64, device=dev) * (hi[c] - lo[c]) + lo[c]
+            d2[bad] = (t[0][bad] - cx) ** 2 + (t[1][bad] - cy) ** 2 + (t[2][bad] - cz) ** 2
     del d2
     for c in range(3, 6):
         t[c].normal_(0.0, 300.0, generator=g)
     t[5].add_(7000.0)
     t[6].fill_(mpw)
     return t
+
+
+def free_volume_per_cell_plane(n_mesh):
+    """volume of the box outside the sphere in each cell plane k (the particle load of the synthetic case is uniform there)"""
+    dz = (XM[2] - X0[2]) / (n_mesh - 1)
+    z = X0[2] + dz * np.arange(n_mesh)
+    (cx, cy, cz), r, _ = SPHERE
+    a = np.clip(z - cz, -r, r)
+    cap = np.pi * (r * r * a - a ** 3 / 3.0)          # integral of pi (r^2 - s^2) ds
+    return (XM[0] - X0[0]) * (XM[1] - X0[1]) * dz - np.diff(cap)
 
 
 def host_particles(rng, n, mpw):
@@ -273,6 +313,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,10 +357,12 @@ def main():
     n_gen = n_local if args.impl == "ours" else min(n_local, int(2e7))   # reference arm only needs a warm field
     mpw_gen = mpw if args.impl == "ours" else N0 * box_vol / n_gen
     decomp = args.decomp and world > 1 and args.impl == "ours"
+    if decomp and args.fuse:
+        raise SystemExit("--decomp needs the separate deposit kernel (the fused scatter would run before the migration)")
     zrange = None
     if decomp:
-        kb = es.slab_bounds(n_mesh, world)
         dhz = (XM[2] - X0[2]) / (n_mesh - 1)
+        kb = es.balanced_bounds(free_volume_per_cell_plane(n_mesh), world)     # equal particle counts, not equal node counts
         zrange = (X0[2] + kb[rank] * dhz, X0[2] + kb[rank + 1] * dhz)
         e.set_domain(world, rank, kb)
         workload += "-kslab-migration"
@@ -348,7 +391,7 @@ def main():
     e.compute_ef()
 
     def pic_step(i, count):
-        e.push(sp, DT, es.WALL_ABSORB, pflags)
+        e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
         if decomp:
             e.migrate(sp)
         n_live = e.count(sp)
@@ -391,7 +434,7 @@ def main():
         pe = phase_ev[i]
         pe[0].record()
         n_before = e.count(sp)
-        e.push(sp, DT, es.WALL_ABSORB, pflags)
+        e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
         if decomp:
             migrated.append(e.migrate(sp)[0])    # inside the push phase of the timed region
         pe[1].record()
@@ -499,7 +542,7 @@ def main():
         v0.record()
         for i in range(nq):
             pushed_q += e.count(sp)
-            e.push(sp, DT, es.WALL_ABSORB, pflags)
+            e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
             if decomp:
                 e.migrate(sp)
             if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
@@ -557,7 +600,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -593,7 +636,7 @@ def reference_arm(args, e, es, sp, workload, n_total, mpw):
     """--impl reference: the reference's CPU implementation of the same step on the host cores.  The GPU engine above was
     used only to prepare the warm field state (untimed); nothing of this repo's engine is inside the timed commands."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_ch3")):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_ch3 was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_ch3 was not built (needs /root/reference at build time)"})
         return 0
     res = reference_cpu_step(args, e, es, sp, n_total, mpw, steps=args.steps, warmup=args.warmup, budget_s=240.0)
     e.close()
@@ -606,7 +649,7 @@ def reference_arm(args, e, es, sp, workload, n_total, mpw):
            "cpu_baseline": res,
            "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 

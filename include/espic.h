@@ -87,6 +87,8 @@ enum { ESPIC_WALL_ABSORB = 0,      /* ch3/ch9: kill on sphere / outside box, swa
        ESPIC_WALL_REFLECT = 1 };   /* ch2: specular reflection at the six walls, nothing removed */
 enum { ESPIC_PUSH_FUSE_DEPOSIT = 1,   /* also scatter the survivors: the next espic_deposit only finalises */
        ESPIC_PUSH_NO_COMPACT = 2,     /* leave dead particles in place with mpw=0 (kill-mask tests) */
+       ESPIC_PUSH_MIGRATE = 4,        /* spatial decomposition: also flag the survivors that left this part and postpone the removal to
+                                         the espic_migrate that must follow (one pass closes both kinds of holes) */
        ESPIC_PUSH_FIXED_POINT = 256 };/* with FUSE_DEPOSIT: accumulate in int64 fixed point */
 int espic_push(espic_ctx *ctx, int sp, double dt, int wall_mode, int flags);
 /* device time (ms) of the push kernel of the most recent espic_push alone -- CUDA events on the launching stream,
@@ -219,20 +221,23 @@ int espic_allreduce_density(espic_ctx *ctx, int sp);
 int espic_domain_set(espic_ctx *ctx, int parts, int part, const int *k_bounds);
 int espic_domain_get(espic_ctx *ctx, int *parts, int *part, int *k_bounds /* parts+1 ints, may be NULL */);
 
-/* Species::transferParticles (ch9/MPI/src/Species.cpp:204-313) after a push: every particle whose cell belongs to another part
- * is sent there (any part, not only a face neighbour; nothing is discarded -- the reference drops particles that overshoot the
- * neighbour, :285-288), the holes are closed in espic_push's swap-with-last order, arrivals are appended by ascending source
- * part in the sender's particle order.  Counts travel as one all-gathered matrix, the particles in one NCCL send/recv group that
- * writes straight behind the receiver's live particles.  Needs espic_comm_init with nranks == parts and rank == part.
- * Collective: every part must call it. */
+/* Species::move's tail (ch9/MPI/src/Species.cpp:189-213): transferParticles + the removal sweep.  Every live particle whose
+ * cell belongs to another part is sent there (any part, not only a face neighbour; nothing is discarded -- the reference drops
+ * particles that overshoot the neighbour, :285-288); arrivals are appended by ascending source part in the sender's particle
+ * order; then ONE swap-with-last sweep (the order of espic_push) closes the holes of the dead and of the leavers over old
+ * particles + arrivals, as the reference does.  Call it right after espic_push(..., ESPIC_PUSH_MIGRATE), which leaves the kill
+ * and leave bits and removes nothing; without such a push (initial placement, after an injection) the leave bits are computed
+ * here.  Counts travel as one all-gathered matrix, the particles in one NCCL send/recv group that writes straight behind the
+ * receiver's particles.  Needs espic_comm_init with nranks == parts and rank == part.  Collective: every part must call it. */
 int espic_migrate(espic_ctx *ctx, int sp, long long *n_sent, long long *n_received);
 
-/* The two halves of espic_migrate for callers that move the segments themselves (several parts on one device, other
- * transports): pack removes the leavers and returns counts[parts]; segment returns the device address of the packed particles
- * bound for `dest` as SoA [7][count] doubles (valid until the next pack); the receiver appends them with
- * espic_species_upload_device(..., append=1) in ascending source order. */
+/* The pieces of espic_migrate for callers that move the segments themselves (several parts on one device, other transports):
+ * pack lists and packs the leavers (nothing is removed yet) and returns counts[parts]; segment returns the device address of
+ * the packed particles bound for `dest` as SoA [7][count] doubles (valid until the next pack); the receiver appends them with
+ * espic_species_upload_device(..., append=1) in ascending source order; finish runs the removal sweep. */
 int espic_migrate_pack(espic_ctx *ctx, int sp, long long *counts);
 int espic_migrate_segment(espic_ctx *ctx, int dest, void **dptr, long long *count);
+int espic_migrate_finish(espic_ctx *ctx, int sp);
 
 #ifdef __cplusplus
 }

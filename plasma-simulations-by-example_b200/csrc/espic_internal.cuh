@@ -41,6 +41,10 @@ struct Species {
     // particles [n_settled, np) were added since (dt = world dt)
     long long n_settled = 0;
     bool substep = false;              // the species is advanced with espic_push_surface
+    // migration in flight (espic_migrate.cuh): 0 none; 1 espic_push(ESPIC_PUSH_MIGRATE) left kill + leave bits for the first
+    // mig_n particles, nothing removed yet; 2 leavers packed, arrivals may be appended, removal still to come
+    int mig_stage = 0;
+    long long mig_n = 0;
 };
 
 struct espic_ctx {
@@ -61,6 +65,8 @@ struct espic_ctx {
     // scratch
     uint32_t *dead_words = nullptr; long long dead_words_cap = 0;
     uint32_t *hit_words = nullptr;  long long hit_words_cap = 0;    // ions that hit the sphere (espic_push_surface)
+    uint32_t *leave_words = nullptr; long long leave_words_cap = 0; // survivors that leave this part (espic_migrate.cuh)
+    int dom_klo = 0, dom_khi = 1 << 30;                             // cell planes this part owns (espic_domain_set)
     uint32_t *scan_pre = nullptr;  long long scan_cap = 0;
     uint32_t *scan_coff = nullptr; long long scan_coff_cap = 0;
     long long *lists = nullptr;    long long lists_cap = 0;   // holes | fillers

@@ -7,6 +7,8 @@
 #include <math.h>
 
 #define SP_CHECK(c, sp) do { if ((sp) < 0 || (sp) >= (c)->nsp) { espic_set_error("bad species id %d", (sp)); return -1; } } while (0)
+// between espic_push(ESPIC_PUSH_MIGRATE) / espic_migrate_pack and the end of the migration the arrays still hold the dead and the leavers
+#define MIG_GUARD(c, s, who) do { if ((s).mig_stage != 0) { espic_set_error("%s: a migration of this species is pending (call espic_migrate / espic_migrate_finish first)", who); return -1; } } while (0)
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // =====================================================================================================
@@ -466,12 +468,16 @@ __device__ __forceinline__ bool push_one(const MeshC &m, const double *__restric
     }
 }
 
-template <int WALL, bool FUSE, int MODE>
+// MIG (spatial decomposition, espic_migrate.cuh): a survivor whose new cell plane k lies outside [klo, khi) leaves this part;
+// its bit goes to leave_words AND to dead_words (the removal after the exchange closes both kinds of holes in one pass, as
+// ch9/MPI does: moveKernel clears `alive` for both, ch9/MPI/src/Species.cpp:66,185-188).
+template <int WALL, bool FUSE, int MODE, bool MIG = false>
 __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const double *__restrict__ ef4,
                                               double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                                               double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
                                               double *__restrict__ pmpw, long long n, double s, double dt,
-                                              uint32_t *__restrict__ dead_words, double *acc, double scale, int ahead)
+                                              uint32_t *__restrict__ dead_words, double *acc, double scale, int ahead,
+                                              uint32_t *__restrict__ leave_words, int klo, int khi)
 {
     const int lane = threadIdx.x & 31;
     const long long i0 = 2 * (blockIdx.x * 256ll + threadIdx.x);
@@ -509,8 +515,22 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
     if (WALL == ESPIC_WALL_ABSORB) {
         if (dead0 && w0_in != 0) pmpw[i0] = 0;               // part.mpw = 0 (Species.cpp:31)
         if (dead1 && w1_in != 0) pmpw[i0 + 1] = 0;
+        bool gone0 = dead0, gone1 = dead1;
+        if (MIG) {
+            int k; double dk;
+            cell_frac(Z.x, m.x0[2], m.dh[2], m.rdh[2], m.nk, k, dk);
+            const bool lv0 = v0 && !dead0 && (k < klo || k >= khi);
+            cell_frac(Z.y, m.x0[2], m.dh[2], m.rdh[2], m.nk, k, dk);
+            const bool lv1 = v1 && !dead1 && (k < klo || k >= khi);
+            const uint32_t l0 = __ballot_sync(0xffffffffu, lv0), l1 = __ballot_sync(0xffffffffu, lv1);
+            if (lane == 0) {
+                leave_words[wbase >> 5] = spread16(l0) | (spread16(l1) << 1);
+                if (wbase + 32 < n) leave_words[(wbase >> 5) + 1] = spread16(l0 >> 16) | (spread16(l1 >> 16) << 1);
+            }
+            gone0 = dead0 || lv0; gone1 = dead1 || lv1;
+        }
         // kill bit of particle wbase + b is bit (b & 31) of word (wbase + b) >> 5: interleave the two ballots
-        const uint32_t b0 = __ballot_sync(0xffffffffu, dead0), b1 = __ballot_sync(0xffffffffu, dead1);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, gone0), b1 = __ballot_sync(0xffffffffu, gone1);
         if (lane == 0) {
             const uint32_t lo = spread16(b0) | (spread16(b1) << 1);
             const uint32_t hi = spread16(b0 >> 16) | (spread16(b1 >> 16) << 1);
@@ -628,23 +648,32 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     const long long n = s.np;
     const bool fuse = (flags & ESPIC_PUSH_FUSE_DEPOSIT) != 0;
     const int mode = (flags & ESPIC_PUSH_FIXED_POINT) ? ESPIC_DEPOSIT_FIXED : ESPIC_DEPOSIT_FP64;
+    MIG_GUARD(c, s, "espic_push");
+    const bool mig = (flags & ESPIC_PUSH_MIGRATE) != 0;
+    if (mig && (!c->mig || wall_mode != ESPIC_WALL_ABSORB || fuse || (flags & ESPIC_PUSH_NO_COMPACT))) {
+        espic_set_error("espic_push: ESPIC_PUSH_MIGRATE needs espic_domain_set, ESPIC_WALL_ABSORB and neither FUSE_DEPOSIT nor NO_COMPACT");
+        return -1;
+    }
     s.acc_fresh = false;
     if (fuse) { int r = prepare_acc(c, s, mode); if (r) return r; }
-    if (n == 0) { if (fuse) s.acc_fresh = true; return 0; }
+    if (n == 0) { if (fuse) s.acc_fresh = true; if (mig) { s.mig_stage = 1; s.mig_n = 0; } return 0; }
     const double sfac = dt * s.charge / s.mass;     // Species.cpp:22, evaluated as the reference does
     const double scale = ldexp(1.0, s.acc_shift);
     const long long nw = (n + 31) / 32;
     int r;
-    if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw, c->stream))) return r; }
+    // with MIGRATE the words must also cover the arrivals appended before the removal: leave headroom so they rarely regrow
+    if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, mig ? nw + nw / 16 + 1024 : nw, c->stream))) return r; }
+    if (mig) { if ((r = ensure_buf(&c->leave_words, &c->leave_words_cap, nw, c->stream))) return r; }
     const unsigned grid = nblk((n + 1) / 2, 256);
     if (!c->push_ev0) { CK(cudaEventCreate(&c->push_ev0)); CK(cudaEventCreate(&c->push_ev1)); }
     CK(cudaEventRecord(c->push_ev0, c->stream));
     static const int ahead_env = getenv("ESPIC_PUSH_PREFETCH") ? atoi(getenv("ESPIC_PUSH_PREFETCH")) : -1;
     // default distance: two blocks per SM (measured plateau: 1-3 blocks per SM)
     const int ahead = ahead_env >= 0 ? ahead_env : 2 * c->sm_count;
-#define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale, ahead
+#define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale, ahead, c->leave_words, c->dom_klo, c->dom_khi
     if (wall_mode == ESPIC_WALL_ABSORB) {
-        if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        if (mig) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64, true><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FIXED><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
     } else if (wall_mode == ESPIC_WALL_REFLECT) {
@@ -659,6 +688,7 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     if (fuse) s.acc_fresh = true;
     if (s.pushes_since_sort < (1 << 20)) s.pushes_since_sort++;
     if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) { s.n_settled = s.np; return 0; }
+    if (mig) { s.mig_stage = 1; s.mig_n = n; return 0; }     // removal happens in espic_migrate, after the exchange
 
     int rr = compact_dead(c, s, n);
     s.n_settled = s.np;
@@ -684,6 +714,7 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
     if (mode != ESPIC_DEPOSIT_FP64 && mode != ESPIC_DEPOSIT_FIXED) { espic_set_error("espic_deposit: bad mode %d", mode); return -1; }
+    MIG_GUARD(c, s, "espic_deposit");
     if (!(s.acc_fresh && s.acc_mode == mode)) {
         int r = prepare_acc(c, s, mode);
         if (r) return r;
@@ -922,6 +953,7 @@ extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
+    MIG_GUARD(c, s, "espic_sort_by_cell");
     const long long n = s.np;
     if (n < 2) return 0;
     if (s.substep && s.n_settled < n) {

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libespic_cuda.so")
 
 PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM, NVV_SUM, NWW_SUM, MPC = range(15)
 WALL_ABSORB, WALL_REFLECT = 0, 1
-PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_FIXED_POINT = 1, 2, 256
+PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_MIGRATE, PUSH_FIXED_POINT = 1, 2, 4, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
 SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF, SOLVE_PCG_MG, SOLVE_PCG_MG_SLAB = 0, 1, 2, 3, 4, 5, 6
 
@@ -25,7 +25,7 @@ EXPORTS = [
     "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
-    "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment",
+    "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment", "espic_migrate_finish",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     L.espic_migrate.argtypes = [vp, C.c_int, llp, llp]
     L.espic_migrate_pack.argtypes = [vp, C.c_int, llp]
     L.espic_migrate_segment.argtypes = [vp, C.c_int, C.POINTER(vp), llp]
+    L.espic_migrate_finish.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -352,6 +353,9 @@ class Engine:
         self._ck(self.L.espic_migrate_pack(self.h, sp, counts))
         return [int(v) for v in counts]
 
+    def migrate_finish(self, sp):
+        self._ck(self.L.espic_migrate_finish(self.h, sp))
+
     def migrate_segment(self, dest):
         """(device address, count) of the packed SoA [7][count] segment bound for part `dest`"""
         p, n = C.c_void_p(), C.c_longlong(0)
@@ -363,3 +367,21 @@ def slab_bounds(nk, parts):
     """k_bounds of `parts` equal slabs of cells (the last one takes the remainder), the default cut of bench.py"""
     cells = nk - 1
     return [cells * r // parts for r in range(parts)] + [cells]
+
+
+def balanced_bounds(weights, parts):
+    """k_bounds that give every part about the same share of `weights` (one non-negative number per cell plane, e.g. the free
+    volume or a particle histogram): the load balance of the decomposition (ch9/MPI cuts into equal node counts,
+    World.h:96-99, whatever the particles do).  Every part keeps at least one cell plane."""
+    w = np.asarray(weights, dtype=np.float64)
+    cells = w.size
+    assert 1 <= parts <= cells
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    kb = [0]
+    for r in range(1, parts):
+        k = int(np.searchsorted(cum, cum[-1] * r / parts, side="left"))
+        if k > 0 and abs(cum[k - 1] - cum[-1] * r / parts) <= abs(cum[k] - cum[-1] * r / parts):
+            k -= 1
+        k = min(max(k, kb[-1] + 1), cells - (parts - r))
+        kb.append(k)
+    return kb + [cells]

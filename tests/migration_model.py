@@ -2,8 +2,9 @@
 World::initMPIDomain + Species::transferParticles, ch9/MPI/include/World.h:73-128, ch9/MPI/src/Species.cpp:204-313).
 
 Test infrastructure: it states, independently of the CUDA code, which part owns a particle and in which ORDER every part holds its
-particles after a migration -- stayers in the reference's swap-with-last removal order (ch3/ver2/Species.cpp:36-46), then the
-arrivals by ascending source part, each source in its own particle order.  The GPU path must reproduce that order bit for bit.
+particles after a migration -- the arrivals are appended by ascending source part, each source in its own particle order, and
+then one swap-with-last removal sweep (ch3/ver2/Species.cpp:36-46; ch9/MPI/src/Species.cpp:205-210) closes the holes of the
+dead and of the leavers.  The GPU path must reproduce that order bit for bit.
 """
 import numpy as np
 
@@ -28,20 +29,31 @@ def swap_remove(part, dead):
     return out
 
 
-def migrate(parts, z0, dhz, nk, kb):
-    """parts: list of (7, n_r) arrays (after push + removal).  Returns (new parts, counts[src][dst])."""
+def migrate(parts, z0, dhz, nk, kb, dead=None):
+    """parts: list of (7, n_r) arrays; dead: optional list of boolean masks (particles the push killed but has not removed
+    yet: espic_push(ESPIC_PUSH_MIGRATE) / Species::moveKernel leave them in place).  The sequence of ch9/MPI Species::move
+    (Species.cpp:189-213): leavers are packed per destination in particle order, arrivals are appended by ascending source,
+    then ONE swap-with-last sweep closes the holes of the dead and of the leavers -- arrivals are the first fillers.
+    Returns (new parts, counts[src][dst])."""
     R = len(parts)
-    own = [owner_of(p[2], z0, dhz, nk, kb) for p in parts]
     counts = np.zeros((R, R), dtype=np.int64)
     seg = [[None] * R for _ in range(R)]
-    stay = []
+    gone = []
     for r, p in enumerate(parts):
+        dmask = np.zeros(p.shape[1], dtype=bool) if dead is None else np.asarray(dead[r], dtype=bool)
+        own = owner_of(p[2], z0, dhz, nk, kb)
+        leave = (own != r) & ~dmask
         for d in range(R):
             if d != r:
-                seg[r][d] = p[:, own[r] == d]
+                seg[r][d] = p[:, leave & (own == d)]
                 counts[r, d] = seg[r][d].shape[1]
-        stay.append(swap_remove(p, own[r] != r))
-    out = [np.concatenate([stay[r]] + [seg[s][r] for s in range(R) if s != r], axis=1) for r in range(R)]
+        gone.append(dmask | leave)
+    out = []
+    for r, p in enumerate(parts):
+        arrivals = [seg[s][r] for s in range(R) if s != r]
+        full = np.concatenate([p] + arrivals, axis=1)
+        mask = np.concatenate([gone[r], np.zeros(full.shape[1] - p.shape[1], dtype=bool)])
+        out.append(swap_remove(full, mask))
     return out, counts
 
 

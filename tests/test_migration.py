@@ -32,28 +32,34 @@ def _oracle_parts(w, sp_all, kb):
     return sps
 
 
-def _oracle_decomposed_steps(w, sps, kb, dt, steps):
-    """push every part with the oracle, migrate with the model; returns per-step lists of part arrays"""
+def _oracle_decomposed_steps(w, sps, kb, dt, steps, fused=False):
+    """push every part with the oracle, migrate with the model; returns per-step lists of part arrays.
+    fused: the push leaves its dead in place (mpw = 0) and the migration's single sweep removes them together with the leavers
+    (espic_push(ESPIC_PUSH_MIGRATE) + espic_migrate); otherwise the push removes its dead first (espic_push + espic_migrate)."""
     hist = []
     for _ in range(steps):
+        dead = None
         for s in sps:
-            s.advance(dt)
-        new, counts = mm.migrate([s.particles() for s in sps], w.x0[2], w.dh[2], w.nk, kb)
+            s.push_nocompact(dt) if fused else s.advance(dt)
+        if fused:
+            dead = [s.particles()[6] == 0 for s in sps]
+        new, counts = mm.migrate([s.particles() for s in sps], w.x0[2], w.dh[2], w.nk, kb, dead)
         for s, p in zip(sps, new):
             s.set_particles(p)
         hist.append(([p.copy() for p in new], counts))
     return hist
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("kb,dt", [([0, 3, 9, 13], 1e-7), ([0, 2, 4, 13], 2e-5), ([0, 13], 1e-7)])
-def test_decomposed_oracle_run_is_the_single_domain_run(kb, dt):
+def test_decomposed_oracle_run_is_the_single_domain_run(kb, dt, fused):
     w, sp = cases.sphere_case(seed=77, ni=9, nj=8, nk=14, n=6000, near_walls=0.1)
     one = orc.Species(w, sp.mass, sp.charge, 50.0, cap=4 * 6000)
     one.set_particles(sp.particles())
     sps = _oracle_parts(w, sp, kb)
     assert sum(s.particles().shape[1] for s in sps) == 6000
     moved, skipped = 0, 0
-    for parts, counts in _oracle_decomposed_steps(w, sps, kb, dt, 4):
+    for parts, counts in _oracle_decomposed_steps(w, sps, kb, dt, 4, fused):
         one.advance(dt)
         moved += int(counts.sum())
         skipped += int(counts[0, 2]) if len(kb) > 3 else 0
@@ -96,6 +102,25 @@ def test_swap_remove_is_the_reference_loop():
             assert np.array_equal(mm.swap_remove(part, dead), ref)
 
 
+def test_slab_bounds_helpers():
+    """espic.slab_bounds / balanced_bounds: valid cuts (0 .. nk-1, strictly increasing), balanced shares"""
+    es = __import__("engines")._espic()
+    for nk, parts in ((14, 3), (128, 8), (9, 8), (3, 2)):
+        kb = es.slab_bounds(nk, parts)
+        assert kb[0] == 0 and kb[-1] == nk - 1 and all(b > a for a, b in zip(kb, kb[1:])) and len(kb) == parts + 1
+    rng = np.random.default_rng(5)
+    for cells, parts in ((127, 8), (127, 2), (13, 13), (40, 7)):
+        w = rng.uniform(0.5, 1.5, cells)
+        kb = es.balanced_bounds(w, parts)
+        assert kb[0] == 0 and kb[-1] == cells and all(b > a for a, b in zip(kb, kb[1:])) and len(kb) == parts + 1
+        share = np.array([w[a:b].sum() for a, b in zip(kb, kb[1:])]) / w.sum()
+        assert np.abs(share - 1.0 / parts).max() <= 1.6 * w.max() / w.sum()
+    assert es.balanced_bounds([0, 0, 0, 5, 0, 0], 3) == [0, 3, 4, 6]       # every part keeps a cell plane
+    import bench
+    w = bench.free_volume_per_cell_plane(128)
+    assert abs(w.sum() - (0.2 * 0.2 * 0.4 - 4.0 / 3.0 * np.pi * 0.05 ** 3)) < 1e-12
+
+
 # ---- the exchange protocol of espic_migrate over gloo, world size 2 ------------------------------------------------------
 
 def _gloo_worker(rank, world, port, path):
@@ -117,9 +142,8 @@ def _gloo_worker(rank, world, port, path):
         s.advance(dt)
         p = s.particles()
         own = mm.owner_of(p[2], w.x0[2], w.dh[2], w.nk, kb)
-        # pack: one SoA segment per destination, leavers in particle order; holes closed in swap-with-last order
+        # pack: one SoA segment per destination, leavers in particle order
         segs = {dst: np.ascontiguousarray(p[:, own == dst]) for dst in range(world) if dst != rank}
-        stay = mm.swap_remove(p, own != rank)
         # counts matrix M[src][dst]: every rank contributes its row, the all-gather returns all rows
         row = torch.zeros(world, dtype=torch.int64)
         for dst, sg in segs.items():
@@ -127,7 +151,7 @@ def _gloo_worker(rank, world, port, path):
         rows = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(rows, row)
         M = torch.stack(rows).numpy()
-        # one send and one matching receive per peer with a non-zero count; arrivals land behind the stayers by ascending source
+        # one send and one matching receive per peer with a non-zero count; arrivals land behind the old particles by ascending source
         recv = {src: torch.zeros((7, int(M[src, rank])), dtype=torch.float64) for src in range(world) if src != rank}
         reqs = []
         for peer in range(world):
@@ -139,7 +163,10 @@ def _gloo_worker(rank, world, port, path):
                 reqs.append(dist.irecv(recv[peer], peer))
         for q in reqs:
             q.wait()
-        s.set_particles(np.concatenate([stay] + [recv[src].numpy() for src in sorted(recv)], axis=1))
+        # arrivals behind the last slot, then ONE swap-with-last sweep over old + new closes the leavers' holes
+        full = np.concatenate([p] + [recv[src].numpy() for src in sorted(recv)], axis=1)
+        gone = np.concatenate([own != rank, np.zeros(full.shape[1] - p.shape[1], dtype=bool)])
+        s.set_particles(mm.swap_remove(full, gone))
     np.save(path + ".rank%d.npy" % rank, s.particles())
     dist.barrier()
     dist.destroy_process_group()
@@ -178,7 +205,7 @@ def _gpu_parts(st, kb):
 
 
 def _gpu_migrate_on_one_device(engines):
-    """espic_migrate with the transport done by hand: pack everywhere, then append the segments by ascending source"""
+    """espic_migrate with the transport done by hand: pack everywhere, append the segments by ascending source, removal sweep"""
     R = len(engines)
     counts = [g.e.migrate_pack(g.species[0]) for g in engines]
     for g in engines:
@@ -191,24 +218,30 @@ def _gpu_migrate_on_one_device(engines):
             assert cnt == counts[src][dst]
             engines[dst].e.upload_device(engines[dst].species[0], [ptr + 8 * q * cnt for q in range(7)], cnt, 0.0, append=True)
     for g in engines:
+        g.e.migrate_finish(g.species[0])
         g.e.sync()
     return np.array(counts)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kb,dt,n", [([0, 3, 9, 13], 1e-7, 40000), ([0, 2, 4, 13], 2e-5, 20011), ([0, 1, 2, 3, 5, 8, 11, 12, 13], 4e-6, 30000)])
-def test_gpu_parts_on_one_device_match_the_model(kb, dt, n):
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("kb,dt,n", [([0, 3, 9, 13], 1e-7, 40000), ([0, 2, 4, 13], 2e-5, 20011), ([0, 1, 2, 3, 5, 8, 11, 12, 13], 4e-6, 30000),
+                                     ([0, 5, 13], 3e-6, 300001)])
+def test_gpu_parts_on_one_device_match_the_model(kb, dt, n, fused):
     es = __import__("engines")._espic()
     w, sp = cases.sphere_case(seed=79, ni=9, nj=8, nk=14, n=n, near_walls=0.1)
     st = sf.state_from_oracle(w, [sp], dt)
     engines = _gpu_parts(st, kb)
     sps = _oracle_parts(w, sp, kb)
-    hist = _oracle_decomposed_steps(w, sps, kb, dt, 4)
+    hist = _oracle_decomposed_steps(w, sps, kb, dt, 4, fused)
     one = __import__("engines").GpuEngine(st)
     total = 0
     for step, (want, want_counts) in enumerate(hist):
         for g in engines:
-            g.e.push(g.species[0], dt, es.WALL_ABSORB, 0)
+            g.e.push(g.species[0], dt, es.WALL_ABSORB, es.PUSH_MIGRATE if fused else 0)
+            if fused:
+                with pytest.raises(es.EspicError):          # dead and leavers are still in the arrays
+                    g.e.deposit(g.species[0], es.DEPOSIT_FP64)
         counts = _gpu_migrate_on_one_device(engines)
         assert np.array_equal(counts, want_counts), step
         total += int(counts.sum())

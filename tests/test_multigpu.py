@@ -139,12 +139,12 @@ def _migrate_worker(rank, world, port, path):
     out = {}
     moved = 0
     for step in range(3):                       # frozen field: order and bits against the model
-        g.e.push(sp, st.dt, es.WALL_ABSORB, 0)
+        g.e.push(sp, st.dt, es.WALL_ABSORB, es.PUSH_MIGRATE if step != 1 else 0)
         sent, recv = g.e.migrate(sp)
         moved += sent
         out["frozen%d" % step] = g.e.download(sp)
     for step in range(2):                       # full cycle: the decomposed run is the single-domain run
-        g.e.push(sp, st.dt, es.WALL_ABSORB, 0)
+        g.e.push(sp, st.dt, es.WALL_ABSORB, es.PUSH_MIGRATE)
         sent, recv = g.e.migrate(sp)
         moved += sent
         res = g.run(["deposit", "rho", "solve_mg:2000:1e-8", "ef"])
@@ -172,7 +172,9 @@ def test_two_rank_migration_matches_single_gpu(tmp_path):
     mp.spawn(_migrate_worker, args=(2, 29800 + os.getpid() % 1000, path), nprocs=2, join=True)
     r = [np.load(path + ".rank%d.npz" % q) for q in range(2)]
     kb = es.slab_bounds(st.nk, 2)
-    hist = _oracle_decomposed_steps(w, _oracle_parts(w, sp, kb), kb, st.dt, 3)
+    sps = _oracle_parts(w, sp, kb)             # steps 0 and 2: leave bits from the push kernel, one removal sweep; step 1: push removes first
+    hist = _oracle_decomposed_steps(w, sps, kb, st.dt, 1, True) + _oracle_decomposed_steps(w, sps, kb, st.dt, 1, False) \
+        + _oracle_decomposed_steps(w, sps, kb, st.dt, 1, True)
     for step in range(3):
         for q in range(2):
             got, want = r[q]["frozen%d" % step], hist[step][0][q]
