@@ -9,8 +9,9 @@
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on at 1/2/4/8 B200): 128^3 mesh,
 sphere (0,0,0.15) r=0.05 at -100 V + inlet, O+ ions at n0=1e12 with v=(0,0,7000)+300*N(0,1) m/s, 2e8
 macroparticles PER GPU (weak scaling: particles are sharded by index, each rank deposits its shard, the density
-is summed with one NCCL all-reduce, the field solve is replicated), Boltzmann electrons, Newton + Jacobi-PCG
-Poisson solve (ch3/ver2 SolverType::PCG, tol 1e-4) warm-started from the previous step, dt=1e-7.
+is summed with one NCCL all-reduce, the field solve is replicated), Boltzmann electrons, Newton + multigrid-preconditioned CG
+Poisson solve (ch3/ver2 SolverType::PCG, tol 1e-4; --solver pcg = the reference's Jacobi preconditioner) warm-started from the
+previous step, dt=1e-7.
 Injection and diagnostics are outside the timed region; the periodic cell sort is inside it.
 Prints ONE JSON line (rank 0).
 """
