@@ -478,6 +478,7 @@ struct MgPcgArgs {
     StencilC s;
     int nlev;
     int coarse_sweeps;            // Jacobi sweeps on the coarsest level (even)
+    int first_redundant;          // slab mode: first level that every rank solves in full (<= nlev-1, >= 1); unused on one GPU
     MgLevel L[MG_MAX_LEVELS];     // L[0]: dims, diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
     const uint8_t *nbmask;
     double *delta, *r, *z, *d0, *d1, *q;     // r enters holding the right-hand side; d0/d1 ping-pong search directions
@@ -513,21 +514,29 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
         }
         return acc;
     }
-    // The coarsest level is tiny: in slab mode its right-hand side is stored to EVERY rank and every rank sweeps the whole
-    // level redundantly with grid-local barriers only (identical arithmetic -> identical result everywhere); that removes
-    // coarse_sweeps+1 inter-GPU barriers per V-cycle.
+    // The coarse levels are tiny: in slab mode the right-hand side of level `lr` (a.first_redundant; by default the coarsest
+    // level) is stored to EVERY rank, and every rank runs the levels lr .. coarsest redundantly in full with grid-local
+    // barriers only (identical arithmetic -> identical result everywhere).  That removes 2 inter-GPU barriers per redundant
+    // level and coarse_sweeps+1 for the coarsest from every V-cycle.
     const int lc = a.nlev - 1;
     const MgLevel &Lc = a.L[lc];
-    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride, lc == 1);
+    int lr = lc;
+    if constexpr (Own::slab) lr = a.first_redundant;
+    OwnAll whole;
+    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride, lr == 1);
     own.barrier(grid);
     MG_TICK(0);
     for (int l = 1; l + 1 < a.nlev; l++) {
-        mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lc);
-        own.barrier(grid);
+        if (Own::slab && l >= lr) {
+            mg_down(whole, a.L[l], l, a.L[l + 1], t0, stride, false);
+            grid.sync();
+        } else {
+            mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lr);
+            own.barrier(grid);
+        }
     }
     MG_TICK(1);
     {
-        OwnAll whole;
         for (long long u = t0; u < Lc.nn; u += stride) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
         grid.sync();
         for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
@@ -540,8 +549,13 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
     MG_TICK(2);
     const double *e = Lc.x;
     for (int l = a.nlev - 2; l >= 1; l--) {
-        mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
-        own.barrier(grid);
+        if (Own::slab && l >= lr) {
+            mg_up(whole, a.L[l], l, a.L[l + 1], e, t0, stride);
+            grid.sync();
+        } else {
+            mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
+            own.barrier(grid);
+        }
         e = a.L[l].xn;
     }
     MG_TICK(3);
@@ -779,7 +793,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
             LAUNCH_CHECK(c);
         }
         MgPcgArgs a;
-        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps; a.nbmask = H->nbmask;
+        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps; a.nbmask = H->nbmask; a.first_redundant = H->nlev - 1;
         a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = diagJ; a.L[0].minv = minv; a.L[0].x = x0;
@@ -973,6 +987,13 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         CK(cudaMemsetAsync(S->d0, 0, (size_t)s.nn * sizeof(double), c->stream));
         MgPcgArgs a;
         a.s = s; a.nlev = H->nlev; a.coarse_sweeps = MG_COARSE_SWEEPS; a.nbmask = H->nbmask;
+        // Levels with at most ESPIC_MG_SLAB_REDUNDANT_NODES nodes are solved by every rank in full instead of by slabs
+        // (trades 2 inter-GPU barriers per level and V-cycle for redundant work on a small level); default: only the coarsest.
+        a.first_redundant = H->nlev - 1;
+        if (const char *ev = getenv("ESPIC_MG_SLAB_REDUNDANT_NODES")) {
+            const long long limit = atoll(ev);
+            while (a.first_redundant > 1 && H->L[a.first_redundant - 1].nn <= limit) a.first_redundant--;
+        }
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;
         a.delta = S->delta; a.r = S->R; a.z = S->z; a.d0 = S->d0; a.d1 = S->d1; a.q = S->q;

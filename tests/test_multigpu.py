@@ -69,8 +69,10 @@ def test_two_rank_deposit_matches_single_gpu(tmp_path):
     assert np.abs(out["fp64"] - one).max() <= 1e-12 * np.abs(one).max()
 
 
-def _slab_worker(rank, world, port, path):
+def _slab_worker(rank, world, port, path, redundant_nodes=None):
     import torch.distributed as dist
+    if redundant_nodes is not None:
+        os.environ["ESPIC_MG_SLAB_REDUNDANT_NODES"] = str(redundant_nodes)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -89,11 +91,14 @@ def _slab_worker(rank, world, port, path):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("dims,n0", [((32, 32, 64), 1e12), ((40, 24, 48), 1e11)])
-def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0):
+@pytest.mark.parametrize("dims,n0,redundant_nodes", [((32, 32, 64), 1e12, None), ((40, 24, 48), 1e11, None),
+                                                     ((32, 32, 64), 1e12, 20000), ((64, 64, 128), 1e12, 40000)])
+def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0, redundant_nodes):
     """ESPIC_SOLVE_PCG_MG_SLAB on two ranks (k-slabs, halo planes and dot products through peer memory) must give the
     potential of the single-GPU multigrid solve: same iteration counts, phi within 1e-10 (summation order of the dot
-    products differs), and both ranks must end with identical fields."""
+    products differs), and both ranks must end with identical fields.  `redundant_nodes` = ESPIC_MG_SLAB_REDUNDANT_NODES:
+    every level with at most that many nodes is solved by each rank in full (32x32x64: all coarse levels, i.e. the fine down
+    pass stores to every rank; 64x64x128: levels 2.. of 4, the transition sits between two coarse levels)."""
     import torch.multiprocessing as mp
     n = 200000
     w, sp = cases.sphere_case(seed=91, ni=dims[0], nj=dims[1], nk=dims[2], n=n, amp=0.0, mpw=n0 * 0.016 / n)
@@ -104,7 +109,7 @@ def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0):
     st = sf.state_from_oracle(w, [sp], 1e-7)
     path = str(tmp_path / "in.npz")
     np.savez(path, **sf.state_to_dict(st, "in_"))
-    mp.spawn(_slab_worker, args=(2, 29700 + os.getpid() % 1000, path), nprocs=2, join=True)
+    mp.spawn(_slab_worker, args=(2, 29700 + os.getpid() % 1000, path, redundant_nodes), nprocs=2, join=True)
     r0, r1 = np.load(path + ".rank0.npz"), np.load(path + ".rank1.npz")
     one = GpuEngine(st)
     one.e.nr_tol = 1e-10
