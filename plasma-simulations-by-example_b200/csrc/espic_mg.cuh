@@ -19,6 +19,7 @@
 #define MG_OMEGA 0.9
 #define MG_COARSE_SWEEPS 6
 #define MG_COARSEST_NODES 4096      // stop coarsening once a level is this small
+#define MG_SLAB_REDUNDANT_NODES 65536   // slab mode: levels up to this size are solved by every rank in full
 
 struct MgLevel {
     int ni, nj, nk;
@@ -987,11 +988,14 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         CK(cudaMemsetAsync(S->d0, 0, (size_t)s.nn * sizeof(double), c->stream));
         MgPcgArgs a;
         a.s = s; a.nlev = H->nlev; a.coarse_sweeps = MG_COARSE_SWEEPS; a.nbmask = H->nbmask;
-        // Levels with at most ESPIC_MG_SLAB_REDUNDANT_NODES nodes are solved by every rank in full instead of by slabs
-        // (trades 2 inter-GPU barriers per level and V-cycle for redundant work on a small level); default: only the coarsest.
+        // Levels with at most MG_SLAB_REDUNDANT_NODES nodes (override: ESPIC_MG_SLAB_REDUNDANT_NODES, 0 = only the coarsest)
+        // are solved by every rank in full instead of by slabs: 2 inter-GPU barriers less per level and V-cycle for redundant
+        // work on a small level.  Measured on 4 B200, 256^3 (profiles/r1_slab_redundant_levels_n4.txt): 530 us per CG
+        // iteration with only the coarsest level redundant, 508 with <= 8192 nodes, 493 with <= 65536, 492 with <= 524288.
         a.first_redundant = H->nlev - 1;
-        if (const char *ev = getenv("ESPIC_MG_SLAB_REDUNDANT_NODES")) {
-            const long long limit = atoll(ev);
+        {
+            const char *ev = getenv("ESPIC_MG_SLAB_REDUNDANT_NODES");
+            const long long limit = ev ? atoll(ev) : MG_SLAB_REDUNDANT_NODES;
             while (a.first_redundant > 1 && H->L[a.first_redundant - 1].nn <= limit) a.first_redundant--;
         }
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];

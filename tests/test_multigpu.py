@@ -92,13 +92,15 @@ def _slab_worker(rank, world, port, path, redundant_nodes=None):
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("dims,n0,redundant_nodes", [((32, 32, 64), 1e12, None), ((40, 24, 48), 1e11, None),
-                                                     ((32, 32, 64), 1e12, 20000), ((64, 64, 128), 1e12, 40000)])
+                                                     ((32, 32, 64), 1e12, 0), ((40, 24, 48), 1e11, 0),
+                                                     ((64, 64, 128), 1e12, 40000), ((64, 64, 128), 1e12, None)])
 def test_slab_multigrid_matches_single_gpu(tmp_path, dims, n0, redundant_nodes):
     """ESPIC_SOLVE_PCG_MG_SLAB on two ranks (k-slabs, halo planes and dot products through peer memory) must give the
     potential of the single-GPU multigrid solve: same iteration counts, phi within 1e-10 (summation order of the dot
     products differs), and both ranks must end with identical fields.  `redundant_nodes` = ESPIC_MG_SLAB_REDUNDANT_NODES:
-    every level with at most that many nodes is solved by each rank in full (32x32x64: all coarse levels, i.e. the fine down
-    pass stores to every rank; 64x64x128: levels 2.. of 4, the transition sits between two coarse levels)."""
+    every level with at most that many nodes is solved by each rank in full.  Default (None) 65536: on these meshes all coarse
+    levels, i.e. the fine down pass stores to every rank; 0: only the coarsest level; 64x64x128 with 40000: levels 2.. of
+    0..3, the transition sits between two coarse levels."""
     import torch.multiprocessing as mp
     n = 200000
     w, sp = cases.sphere_case(seed=91, ni=dims[0], nj=dims[1], nk=dims[2], n=n, amp=0.0, mpw=n0 * 0.016 / n)
