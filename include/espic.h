@@ -197,6 +197,14 @@ typedef struct {
 } espic_solve_info;
 
 int espic_solve(espic_ctx *ctx, const espic_solve_params *p, espic_solve_info *info);
+/* Planning query, host only (no context, no device work): the multigrid hierarchy ESPIC_SOLVE_PCG_MG / _PCG_MG_SLAB build for a
+ * mesh of ni x nj x nk nodes with spacings dh.  Returns the number of levels (<= 8) or a negative error; dims[l] = nodes per
+ * dimension of level l (0 beyond the last level); *first_redundant = with nranks > 1 the first level every rank solves in full
+ * (levels before it are split into k-slabs), else the coarsest level; *slab_plane_unit = fine k-planes per coarsest plane: the slab
+ * solver needs nk to be a multiple of nranks * slab_plane_unit.  Replaces nothing in the reference (its PCG has no hierarchy,
+ * PotentialSolver.cpp:299-331); it exposes the host logic of the preconditioner that replaces the Jacobi one. */
+int espic_mg_plan(int ni, int nj, int nk, const double dh[3], int nranks, long long dims[8][3], int *first_redundant,
+                  int *slab_plane_unit);
 /* PotentialSolver::computeEF (PotentialSolver.cpp:465-504) */
 int espic_compute_ef(espic_ctx *ctx);
 /* World::getPE (World.cpp:72-84) */

@@ -709,6 +709,52 @@ static long long mg_coarse_doubles(const StencilC &s)
     return total;
 }
 
+// slab mode: first level that every rank solves in full -- the largest run of trailing levels whose node counts are all
+// <= limit (the coarsest level always is; level 0 never)
+static int mg_first_redundant(int nlev, const long long dims[MG_MAX_LEVELS][3], long long limit)
+{
+    int lr = nlev - 1;
+    while (lr > 1 && dims[lr - 1][0] * dims[lr - 1][1] * dims[lr - 1][2] <= limit) lr--;
+    return lr;
+}
+
+static long long mg_slab_redundant_limit()
+{
+    const char *ev = getenv("ESPIC_MG_SLAB_REDUNDANT_NODES");
+    return ev ? atoll(ev) : MG_SLAB_REDUNDANT_NODES;
+}
+
+// fine planes per coarsest plane: slab boundaries must be multiples of it so that no aggregate straddles two ranks
+static int mg_slab_plane_unit(int nlev, const int shifts[MG_MAX_LEVELS][3])
+{
+    int kshift = 0;
+    for (int l = 1; l < nlev; l++) kshift += shifts[l][2];
+    return 1 << kshift;
+}
+
+// Host-side planning only (no device work, callable without a GPU): the hierarchy ESPIC_SOLVE_PCG_MG(_SLAB) builds for a mesh.
+extern "C" int espic_mg_plan(int ni, int nj, int nk, const double dh[3], int nranks, long long dims_out[8][3], int *first_redundant,
+                             int *slab_plane_unit)
+{
+    if (ni < 2 || nj < 2 || nk < 2 || !dh || !(dh[0] > 0) || !(dh[1] > 0) || !(dh[2] > 0) || nranks < 1) {
+        espic_set_error("espic_mg_plan: bad mesh");
+        return -1;
+    }
+    StencilC s;
+    memset(&s, 0, sizeof(s));
+    s.ni = ni; s.nj = nj; s.nk = nk; s.nn = (long long)ni * nj * nk; s.sj = ni; s.sk = (long long)ni * nj;
+    s.gdx2 = 1.0 / (dh[0] * dh[0]); s.gdy2 = 1.0 / (dh[1] * dh[1]); s.gdz2 = 1.0 / (dh[2] * dh[2]);
+    long long dims[MG_MAX_LEVELS][3];
+    int shifts[MG_MAX_LEVELS][3];
+    const int nlev = mg_level_dims(s, dims, shifts);
+    for (int l = 0; l < 8; l++)
+        for (int a = 0; a < 3; a++)
+            if (dims_out) dims_out[l][a] = l < nlev ? dims[l][a] : 0;
+    if (first_redundant) *first_redundant = nranks > 1 ? mg_first_redundant(nlev, dims, mg_slab_redundant_limit()) : nlev - 1;
+    if (slab_plane_unit) *slab_plane_unit = mg_slab_plane_unit(nlev, shifts);
+    return nlev;
+}
+
 // (re)build the hierarchy H for the current geometry; coarse-level arrays go to `external` if given (slab mode: a pool
 // that the other ranks map), else to an allocation owned by H
 static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *external)
@@ -888,9 +934,7 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     long long dims[MG_MAX_LEVELS][3];
     int shifts[MG_MAX_LEVELS][3];
     const int nlev = mg_level_dims(s, dims, shifts);
-    int kshift = 0;
-    for (int l = 1; l < nlev; l++) kshift += shifts[l][2];
-    const int unit = 1 << kshift;                     // fine planes per coarsest plane
+    const int unit = mg_slab_plane_unit(nlev, shifts);        // fine planes per coarsest plane
     if (s.nk % (c->nranks * unit) != 0) {
         espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: nk=%d must be a multiple of nranks*2^(k-coarsenings) = %d", s.nk, c->nranks * unit);
         return -1;
@@ -992,11 +1036,10 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
         // are solved by every rank in full instead of by slabs: 2 inter-GPU barriers less per level and V-cycle for redundant
         // work on a small level.  Measured on 4 B200, 256^3 (profiles/r1_slab_redundant_levels_n4.txt): 530 us per CG
         // iteration with only the coarsest level redundant, 508 with <= 8192 nodes, 493 with <= 65536, 492 with <= 524288.
-        a.first_redundant = H->nlev - 1;
         {
-            const char *ev = getenv("ESPIC_MG_SLAB_REDUNDANT_NODES");
-            const long long limit = ev ? atoll(ev) : MG_SLAB_REDUNDANT_NODES;
-            while (a.first_redundant > 1 && H->L[a.first_redundant - 1].nn <= limit) a.first_redundant--;
+            long long dims[MG_MAX_LEVELS][3];
+            for (int l = 0; l < H->nlev; l++) { dims[l][0] = H->L[l].ni; dims[l][1] = H->L[l].nj; dims[l][2] = H->L[l].nk; }
+            a.first_redundant = mg_first_redundant(H->nlev, dims, mg_slab_redundant_limit());
         }
         for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
         a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;

@@ -23,7 +23,7 @@ EXPORTS = [
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
     "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
-    "espic_charge_density", "espic_solve", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
+    "espic_charge_density", "espic_solve", "espic_mg_plan", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init", "espic_allreduce_density",
     "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment", "espic_migrate_finish",
 ]
@@ -102,6 +102,7 @@ def load():
     L.espic_clear_samples.argtypes = [vp, C.c_int]
     L.espic_charge_density.argtypes = [vp]
     L.espic_solve.argtypes = [vp, C.POINTER(SolveParams), C.POINTER(SolveInfo)]
+    L.espic_mg_plan.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.espic_compute_ef.argtypes = [vp]
     L.espic_field_pe.argtypes = [vp, dp]
     L.espic_comm_unique_id.argtypes = [vp]
@@ -120,6 +121,19 @@ def load():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def mg_plan(ni, nj, nk, dh, nranks=1):
+    """espic_mg_plan: (level dimensions, first level solved redundantly by every rank, fine k-planes per coarsest plane).
+    Host-side planning only: works without a GPU."""
+    L = load()
+    dims = (C.c_longlong * 24)()
+    fr, unit = C.c_int(0), C.c_int(0)
+    d = (C.c_double * 3)(*[float(x) for x in dh])
+    nlev = L.espic_mg_plan(int(ni), int(nj), int(nk), d, int(nranks), dims, C.byref(fr), C.byref(unit))
+    if nlev < 0:
+        raise EspicError(L.espic_last_error().decode())
+    return [tuple(dims[3 * l + a] for a in range(3)) for l in range(nlev)], fr.value, unit.value
 
 
 def _comp(arr7):

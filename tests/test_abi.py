@@ -50,3 +50,33 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "liboracle" not in txt and "espic_oracle" not in txt and "from oracle" not in txt, os.path.join(root, f)
+
+
+def test_multigrid_plan_host_logic(monkeypatch):
+    """espic_mg_plan (host-only planning of the multigrid preconditioner): semi-coarsening on the reference's dz = 2 dx meshes,
+    the coarsest-level size bound, and which levels the slab-decomposed solver runs redundantly on every rank."""
+    es = _espic()
+    monkeypatch.delenv("ESPIC_MG_SLAB_REDUNDANT_NODES", raising=False)
+
+    def dh(n):
+        return (0.2 / (n[0] - 1), 0.2 / (n[1] - 1), 0.4 / (n[2] - 1))
+    # bench mesh (BASELINE configs[2..3]): z is not coarsened on the first level
+    dims, fr, unit = es.mg_plan(128, 128, 128, dh((128, 128, 128)))
+    assert dims == [(128, 128, 128), (64, 64, 128), (32, 32, 64), (16, 16, 32), (8, 8, 16)]
+    assert fr == 4 and unit == 8                      # one rank: nothing is redundant but the coarsest level by construction
+    # configs[4] on 8 ranks: levels of <= 65536 nodes are solved by every rank in full, 256 planes split 8 x 32 (unit 16)
+    dims, fr, unit = es.mg_plan(256, 256, 256, dh((256, 256, 256)), nranks=8)
+    assert dims[:4] == [(256, 256, 256), (128, 128, 256), (64, 64, 128), (32, 32, 64)] and len(dims) == 6
+    assert fr == 3 and unit == 16 and 256 % (8 * unit) == 0
+    monkeypatch.setenv("ESPIC_MG_SLAB_REDUNDANT_NODES", "0")
+    assert es.mg_plan(256, 256, 256, dh((256, 256, 256)), nranks=8)[1] == 5
+    monkeypatch.setenv("ESPIC_MG_SLAB_REDUNDANT_NODES", "100000000")
+    assert es.mg_plan(256, 256, 256, dh((256, 256, 256)), nranks=8)[1] == 1        # level 0 is never redundant
+    monkeypatch.delenv("ESPIC_MG_SLAB_REDUNDANT_NODES")
+    # the shipped ch3 mesh (21 x 21 x 41, isotropic spacing): full coarsening, two levels
+    dims, fr, unit = es.mg_plan(21, 21, 41, (0.01, 0.01, 0.01), nranks=2)
+    assert dims == [(21, 21, 41), (11, 11, 21)] and fr == 1 and unit == 2
+    # a mesh below the coarsest-level bound has no hierarchy (the solver falls back to the Jacobi preconditioner)
+    assert es.mg_plan(9, 9, 9, (1.0, 1.0, 1.0))[0] == [(9, 9, 9)]
+    with pytest.raises(es.EspicError):
+        es.mg_plan(1, 9, 9, (1.0, 1.0, 1.0))
