@@ -87,3 +87,47 @@ void Output::diagOutput(World &world, std::vector<Species> &species)
     f_diag << "," << PE << "," << (tot_KE + PE) << "\n";
     if (world.getTs() % 25 == 0) f_diag.flush();
 }
+
+// ch4/Output.cpp:175-229.  The selection rule is the reference's: a counter grows by num_parts/np per particle, a particle is
+// written when it exceeds 1 and the counter restarts at -1 (so about num_parts/2 particles are written).
+void Output::particlesVTP(std::ostream &out, const std::string &species_name, std::vector<Particle> &parts, int num_parts)
+{
+    const double dp = num_parts / (double)parts.size();
+    double counter = 0;
+    std::vector<Particle *> to_output;
+    for (Particle &part : parts) {
+        counter += dp;
+        if (counter > 1) { to_output.emplace_back(&part); counter = -1; }
+    }
+    out << "<?xml version=\"1.0\"?>\n";
+    out << "<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
+    out << "<PolyData>\n";
+    out << "<Piece NumberOfPoints=\"" << to_output.size() << "\" NumberOfVerts=\"0\" NumberOfLines=\"0\" ";
+    out << "NumberOfStrips=\"0\" NumberOfCells=\"0\">\n";
+    out << "<Points>\n";
+    out << "<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+    for (Particle *part : to_output) out << part->pos << "\n";
+    out << "</DataArray>\n";
+    out << "</Points>\n";
+    out << "<PointData>\n";
+    out << "<DataArray Name=\"vel." << species_name << "\" type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+    for (Particle *part : to_output) out << part->vel << "\n";
+    out << "</DataArray>\n";
+    out << "</PointData>\n";
+    out << "</Piece>\n";
+    out << "</PolyData>\n";
+    out << "</VTKFile>\n";
+}
+
+void Output::particles(World &world, std::vector<Species> &species, int num_parts)
+{
+    for (Species &sp : species) {
+        std::stringstream name;
+        name << "results/parts_" << sp.name << "_" << std::setfill('0') << std::setw(5) << world.getTs() << ".vtp";
+        std::ofstream out(name.str());
+        if (!out.is_open()) { std::cerr << "Could not open " << name.str() << std::endl; return; }
+        std::vector<Particle> snapshot = sp.downloadParticles();     // particles live on the GPU: one device-to-host copy per file
+        particlesVTP(out, sp.name, snapshot, num_parts);
+        out.close();
+    }
+}

@@ -5,9 +5,12 @@
 //   shim_check box <n> <ions_grid> <eles_grid> <steps> <out.state>             ch2/Main.cpp:14-75 flow
 //   shim_check surface <steps> <QN|PCG> <out.state>                               ch4/Main.cpp:19-110 flow (ions + neutrals)
 //   shim_check fieldio <out.state>                                             host writes to Field mirrors reach the GPU
+//   shim_check vtp <in.bin> <num_parts> <out.vtp>                              Output::particlesVTP on a particle snapshot from a file
+//                                                                              (int64 np; double part[7][np]); host only, no GPU needed
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -231,6 +234,24 @@ int run_fieldio(int argc, char **args)
 
 }  // namespace
 
+int run_vtp(int argc, char **args)
+{
+    if (argc < 5) return 1;
+    FILE *f = fopen(args[2], "rb");
+    if (!f) { perror(args[2]); return 2; }
+    long long np = 0;
+    if (fread(&np, 8, 1, f) != 1) return 2;
+    std::vector<double> p((size_t)7 * np);
+    if (fread(p.data(), 8, p.size(), f) != p.size()) return 2;
+    fclose(f);
+    std::vector<Particle> parts;
+    for (long long i = 0; i < np; i++)
+        parts.emplace_back(double3(p[i], p[np + i], p[2 * np + i]), double3(p[3 * np + i], p[4 * np + i], p[5 * np + i]), p[6 * np + i]);
+    std::ofstream out(args[4]);
+    Output::particlesVTP(out, "O+", parts, atoi(args[3]));
+    return 0;
+}
+
 int main(int argc, char **args)
 {
     int rc = 1;
@@ -239,10 +260,11 @@ int main(int argc, char **args)
         else if (argc > 1 && !strcmp(args[1], "box")) rc = run_box(argc, args);
         else if (argc > 1 && !strcmp(args[1], "surface")) rc = run_surface(argc, args);
         else if (argc > 1 && !strcmp(args[1], "fieldio")) rc = run_fieldio(argc, args);
+        else if (argc > 1 && !strcmp(args[1], "vtp")) rc = run_vtp(argc, args);
     } catch (const std::exception &e) {
         std::cerr << "shim_check: " << e.what() << std::endl;
         return 3;
     }
-    if (rc == 1) std::cerr << "usage: shim_check sphere|box|surface|fieldio ... (see the header of shim_check.cpp)" << std::endl;
+    if (rc == 1) std::cerr << "usage: shim_check sphere|box|surface|fieldio|vtp ... (see the header of shim_check.cpp)" << std::endl;
     return rc;
 }

@@ -343,6 +343,28 @@ def test_surface_flow_through_class_api(tmp_path):
     close(st.phi, w.phi, 1e-9, "phi")
 
 
+@pytest.mark.parametrize("case", ["thin", "dense", "single", "exact"])
+def test_particle_file_matches_reference_bytes(tmp_path, case):
+    """Output::particles (ch4/Output.cpp:175-229: running-counter thinning, ASCII VTK PolyData): the shim's writer must produce the
+    reference's file byte for byte from the same particle snapshot.  Golden: tests/golden/ch4/parts_vtp.npz, written by the
+    compiled reference (tests/golden/make_vtp_golden.py); where oracle/_ref is present the reference is also run live."""
+    import sys
+    sys.path.insert(0, os.path.join(sf.ROOT, "tests", "golden"))
+    import make_vtp_golden as mk
+    if not os.path.exists(os.path.join(BIN, "shim_check")):
+        pytest.skip("bin/shim_check not built (python __graft_entry__.py)")
+    g = np.load(os.path.join(sf.ROOT, "tests", "golden", "ch4", "parts_vtp.npz"))
+    part, num_parts, want = g[case + "_part"], int(g[case + "_num_parts"]), g[case + "_vtp"].tobytes()
+    mk.write_input(str(tmp_path / "in.bin"), part)
+    subprocess.run([os.path.join(BIN, "shim_check"), "vtp", "in.bin", str(num_parts), "out.vtp"], cwd=str(tmp_path), check=True)
+    got = open(str(tmp_path / "out.vtp"), "rb").read()
+    assert got == want
+    npts = int(got.split(b'NumberOfPoints="')[1].split(b'"')[0])
+    assert got.count(b"\n") == 2 * npts + 15          # 15 markup lines, one position and one velocity line per point
+    if os.path.exists(mk.REF):
+        assert mk.reference_file(part, num_parts) == want
+
+
 def _check_ch4_statistics(got, ref):
     """Observables of ch4/Main.cpp against the reference run.  Observed on three B200 runs with different seeds against the one
     reference run (scripts/ch4_compare.py): diagnostics 7e-4, steady state 551 vs 552-553, plane profiles of density / stream
