@@ -50,6 +50,10 @@ LINK = ["-L" + os.path.join(HERE, "lib"), "-lespic_host", "-lespic_cuda", "-Wl,-
 # the book's drivers that must compile UNCHANGED against host/*.h; read from the reference tree where it lies
 REF_MAINS = {"main_ch2": "ch2/Main.cpp", "main_ch3": "ch3/ver2/Main.cpp", "main_ch4": "ch4/Main.cpp", "main_ch9": "ch9/Main.cpp",
              "main_ch9mt": "ch9/MT/Main.cpp", "main_ch9cuda": "ch9/CUDA/Main.cpp"}
+# BASELINE configs[1] names the ch3 sphere program with the nonlinear PCG solver; the shipped Main.cpp constructs
+# PotentialSolver(world, SolverType::GS, 20000, 1e-4) (ch3/ver2/Main.cpp:42).  main_ch3_pcg is that file with exactly this one
+# expression replaced on its way to the compiler ("C2 additionally with SolverType::PCG,1000,1e-4"); nothing is copied.
+REF_MAIN_VARIANTS = {"main_ch3_pcg": ("ch3/ver2/Main.cpp", b"SolverType::GS,20000,1e-4", b"SolverType::PCG,1000,1e-4")}
 
 
 def build_host(force=False, reference="/root/reference"):
@@ -86,6 +90,18 @@ def build_host(force=False, reference="/root/reference"):
         if force or not os.path.exists(exe) or os.path.getmtime(exe) < deps:
             with open(main, "rb") as f:
                 subprocess.check_call([CXX] + CXXFLAGS + ["-w", "-x", "c++", "-", "-x", "none", "-o", exe] + LINK, stdin=f, cwd=BIN)
+        built.append(exe)
+    for name, (rel, token, repl) in REF_MAIN_VARIANTS.items():
+        main = os.path.join(reference, rel)
+        exe = os.path.join(BIN, name)
+        if not os.path.exists(main):
+            continue
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < deps:
+            text = open(main, "rb").read()
+            if text.count(token) != 1:
+                raise RuntimeError("%s: expected exactly one %r in %s" % (name, token, main))
+            subprocess.run([CXX] + CXXFLAGS + ["-w", "-x", "c++", "-", "-x", "none", "-o", exe] + LINK, input=text.replace(token, repl),
+                           cwd=BIN, check=True)
         built.append(exe)
     return built
 

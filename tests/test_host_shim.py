@@ -244,7 +244,10 @@ def test_reference_ch3_main_steady_state_statistics(tmp_path):
     with open(str(tmp_path / "run.log"), "w") as log:
         subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=900, check=True,
                        env=dict(os.environ, ESPIC_SEED="4242"))
-    got = summarise(str(tmp_path))
+    _check_ch3_statistics(summarise(str(tmp_path)), ref)
+
+
+def _check_ch3_statistics(got, ref):
     # scalar observables at ts = 400 (reference run-to-run scatter is ~0.1 %)
     for key, tol in (("mp_count", 0.01), ("real_count", 0.01), ("pz", 0.01), ("KE", 0.01), ("PE", 0.005)):
         assert abs(got[key] / ref[key] - 1) < tol, (key, got[key], ref[key])
@@ -257,6 +260,32 @@ def test_reference_ch3_main_steady_state_statistics(tmp_path):
         assert np.abs(a - b).max() <= tol * b.max(), (key, np.abs(a - b).max() / b.max())
     a, b = np.array(got["phi_k_profile"]), np.array(ref["phi_k_profile"])
     assert np.abs(a - b).max() <= 0.02 * np.abs(b).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run on a B200 pending "
+                                        "(an XPASS is the expected outcome; remove this marker after it)")
+def test_reference_ch3_main_with_pcg_solver_statistics(tmp_path):
+    """BASELINE configs[1]: the ch3 sphere program with the nonlinear PCG Poisson solver on the shipped mesh.  bin/main_ch3_pcg is the
+    reference's ch3/ver2/Main.cpp with the one expression `SolverType::GS,20000,1e-4` replaced by `SolverType::PCG,1000,1e-4` on its
+    way to the compiler (build.py REF_MAIN_VARIANTS; SURVEY 8d); the shim maps SolverType::PCG to Newton + multigrid-PCG on the SPD
+    form of the same discrete equations.  Golden: the reference's run with its shipped GS solver (both solve the same equations to
+    1e-4) -- the reference build of the PCG variant is no usable pin: its CG on the non-symmetric matrix breaks down ("PCG failed to
+    converge" -> linear-GS fall-back -> NaN from time step ~140 on, observed here in a run of the compiled variant; DESIGN.md section 3)."""
+    import json
+    import sys
+    exe = os.path.join(BIN, "main_ch3_pcg")
+    gold = os.path.join(sf.ROOT, "tests", "golden", "ch3_sphere_statistics.json")
+    if not os.path.exists(exe):
+        pytest.skip("bin/main_ch3_pcg is built only where the reference tree is present")
+    sys.path.insert(0, os.path.join(sf.ROOT, "tests", "golden"))
+    from make_ch3_statistics import summarise
+    ref = json.load(open(gold))
+    os.makedirs(str(tmp_path / "results"))
+    with open(str(tmp_path / "run.log"), "w") as log:
+        subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=900, check=True,
+                       env=dict(os.environ, ESPIC_SEED="4242"))
+    _check_ch3_statistics(summarise(str(tmp_path)), ref)
 
 
 def _run_main(exe_name, tmp_path, args=(), timeout=900):
