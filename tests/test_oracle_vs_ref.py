@@ -1,5 +1,5 @@
 """Pins the C restatement (oracle/espic_oracle.c) against the UNMODIFIED reference compiled into
-oracle/_ref (ref_ch3 = ch3/ver2 sources, ref_ch2 = ch2 sources).  Bit-exact unless stated.
+oracle/_ref (ref_ch3 = ch3/ver2 sources, ref_ch2 = ch2 sources, ref_mt = ch9/MT sources).  Bit-exact unless stated.
 Skipped where oracle/_ref was never built (it is built by __graft_entry__.build() / oracle/Makefile
 whenever /root/reference is present, and travels to the GPU box)."""
 import numpy as np
@@ -81,6 +81,34 @@ def test_advance_deposit_rho(tmp_path, seed, near):
     assert_bits(r.species[0]["den"], sp.den, "den")
     assert_bits(r.rho, w.rho, "rho")
     assert_bits(r.diag[2:7], np.concatenate([[sp.real_count()], sp.momentum(), [sp.ke()]]), "diag")
+
+
+refmt = pytest.mark.skipif(not sf.have_ref("ref_mt"), reason="oracle/_ref/ref_mt not built")
+
+
+@refmt
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_threaded_reference_build_gives_the_serial_particles(tmp_path, threads):
+    """ch9/MT (std::thread advance and density scatter, ch9/MT/Species.cpp:9-123): whatever the thread count, the particles after
+    advance + removal equal the serial algorithm's bit for bit -- values AND order (the removal sweep stays serial) -- and the density
+    differs only by the order in which the per-thread buffers are added (1e-13 of the maximum).  This is the build the CPU baseline
+    of bench.py times on all host cores."""
+    w, sp = cases.sphere_case(seed=5, n=5000, near_walls=0.3)
+    dt = 2e-6
+    st = sf.state_from_oracle(w, [sp], dt)
+    r = sf.run_ref("ref_mt", st, ["threads:%d" % threads, "advance", "deposit", "rho", "advance", "advance", "deposit", "rho"], tmp_path)
+    n0 = sp.np
+    for _ in range(3):
+        sp.advance(dt)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    assert sp.np < n0 - 50 and r.species[0]["part"].shape[1] == sp.np
+    assert_bits(r.species[0]["part"], sp.particles(), "particles (order included)")
+    scale = np.abs(sp.den).max()
+    assert np.abs(r.species[0]["den"] - sp.den).max() <= 1e-13 * scale
+    assert np.abs(r.rho - w.rho).max() <= 1e-13 * np.abs(w.rho).max()
+    if threads == 1:
+        assert_bits(r.species[0]["den"], sp.den, "den, one thread")
 
 
 @ref3
