@@ -283,7 +283,7 @@ def test_reference_ch3_main_with_pcg_solver_statistics(tmp_path):
     ref = json.load(open(gold))
     os.makedirs(str(tmp_path / "results"))
     with open(str(tmp_path / "run.log"), "w") as log:
-        subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=900, check=True,
+        subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=240, check=True,
                        env=dict(os.environ, ESPIC_SEED="4242"))
     _check_ch3_statistics(summarise(str(tmp_path)), ref)
 
