@@ -308,6 +308,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra QN-solver measurement")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
+    ap.add_argument("--dump-warm", default=None, metavar="PATH",
+                    help="after the timed region write phi of the last step and rho of the next one to PATH (.npz): the warm-started "
+                         "Poisson problem of one full-size step, for the offline reference-solver convergence run (scripts/ref_gs_convergence.py)")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -493,6 +496,16 @@ def main():
             traffic = tj["dram_bytes_per_particle"] * (pushed_local / args.steps)
         except Exception:
             traffic = None
+
+    if args.dump_warm and rank == 0:
+        phi_n = e.field(es.PHI)
+        e.push(sp, DT, es.WALL_ABSORB, pflags)
+        e.deposit(sp, dmode)
+        e.compute_charge_density()
+        np.savez(args.dump_warm, phi=phi_n, rho_next=e.field(es.RHO), mesh=n_mesh, particles=e.count(sp))
+        inf = e.solve(solver, max_it, tol)
+        e.compute_ef()
+        log("warm state dumped to %s (next solve: %s)" % (args.dump_warm, inf))
 
     # ---------------------------------------------------------------- e2e: same steps through the API with host buffers
     e2e = None

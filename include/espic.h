@@ -214,9 +214,10 @@ int espic_field_pe(espic_ctx *ctx, double *pe);
 
 int espic_comm_unique_id(void *id128);                                  /* ncclGetUniqueId */
 int espic_comm_init(espic_ctx *ctx, int rank, int nranks, const void *id128);
-/* sum the species' deposited density over all ranks (FP64, or int64 when deposited in fixed point).
- * Replaces ch9/MPI Field::updateBoundaries (ch9/MPI/include/Field.h:122-179). */
-int espic_allreduce_density(espic_ctx *ctx, int sp);
+/* Once a communicator exists, espic_deposit itself sums the scatter ACCUMULATOR over all ranks (FP64, or int64 when deposited
+ * in fixed point: identical bits for any rank count) before dividing by the node volumes -- that replaces ch9/MPI
+ * Field::updateBoundaries (ch9/MPI/include/Field.h:122-179).  There is deliberately no separate "all-reduce the density" entry:
+ * called after espic_deposit it would count every rank's particles nranks times. */
 
 /* ---- multi-GPU: spatial decomposition with particle migration ------------------- */
 

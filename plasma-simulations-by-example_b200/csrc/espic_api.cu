@@ -154,8 +154,9 @@ extern "C" void espic_destroy(espic_ctx *c)
     for (int s = 0; s < c->nsp; s++) {
         for (int q = 0; q < 7; q++) { cudaFree(c->sp[s].p[q]); cudaFree(c->sp[s].alt[q]); }
         cudaFree(c->sp[s].den); cudaFree(c->sp[s].den_ave); cudaFree(c->sp[s].acc); cudaFree(c->sp[s].mom); cudaFree(c->sp[s].mpc);
+        cudaFree(c->sp[s].kill_words); cudaFree(c->sp[s].leave_words);
     }
-    cudaFree(c->dead_words); cudaFree(c->hit_words); cudaFree(c->leave_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
+    cudaFree(c->dead_words); cudaFree(c->hit_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
     cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
     for (int q = 0; q < 8; q++) cudaFree(c->sv[q]);
     if (c->push_ev0) { cudaEventDestroy(c->push_ev0); cudaEventDestroy(c->push_ev1); }
@@ -352,6 +353,7 @@ extern "C" int espic_species_upload(espic_ctx *c, int sp, const double *const co
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
+    MIG_GUARD(c, s, "espic_species_upload");
     long long base = append ? s.np : 0;
     int r = espic_species_reserve(c, sp, base + n);
     if (r) return r;
@@ -371,6 +373,8 @@ extern "C" int espic_species_upload_device(espic_ctx *c, int sp, const double *c
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
+    // appending behind a packed migration is how arrivals come in (espic_migrate_pack -> upload_device(append) -> espic_migrate_finish)
+    if (!(append && s.mig_stage == 2)) MIG_GUARD(c, s, "espic_species_upload_device");
     long long base = append ? s.np : 0;
     int r = espic_species_reserve(c, sp, base + n);
     if (r) return r;

@@ -156,6 +156,7 @@ extern "C" int espic_dsmc_mex(espic_ctx *c, int sp, double dt, double *sigma_cr_
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
     if (num_cols) *num_cols = 0;
+    MIG_GUARD(c, s, "espic_dsmc_mex");
     const long long n = s.np;
     if (n < 2) return 0;
     if (n >= (1ll << 32)) { espic_set_error("espic_dsmc_mex: more than 2^32 particles in one species"); return -1; }

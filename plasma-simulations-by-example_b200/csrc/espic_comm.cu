@@ -140,11 +140,3 @@ int espic_comm_exchange_segments(espic_ctx *c, int parts, int me, const double *
     return 0;
 }
 
-extern "C" int espic_allreduce_density(espic_ctx *c, int sp)
-{
-    if (sp < 0 || sp >= c->nsp) { espic_set_error("bad species id %d", sp); return -1; }
-    if (c->nranks <= 1 || !c->nccl) return 0;
-    CK(cudaSetDevice(c->device));
-    NCK(g_nccl.AllReduce(c->sp[sp].den, c->sp[sp].den, (size_t)c->m.nn, ncclFloat64, ncclSum, (ncclComm_t)c->nccl, c->stream));
-    return 0;
-}

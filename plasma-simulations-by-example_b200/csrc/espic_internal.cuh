@@ -45,6 +45,10 @@ struct Species {
     // mig_n particles, nothing removed yet; 2 leavers packed, arrivals may be appended, removal still to come
     int mig_stage = 0;
     long long mig_n = 0;
+    // kill bits (one per particle) written by the push kernels and consumed by the removal; leave bits of a MIGRATE push.
+    // Per species: after espic_push(A, ESPIC_PUSH_MIGRATE) they must survive calls on other species until espic_migrate(A).
+    uint32_t *kill_words = nullptr;  long long kill_cap = 0;
+    uint32_t *leave_words = nullptr; long long leave_cap = 0;
 };
 
 struct espic_ctx {
@@ -63,9 +67,8 @@ struct espic_ctx {
     cudaEvent_t push_ev0 = nullptr, push_ev1 = nullptr;
     bool push_timed = false;
     // scratch
-    uint32_t *dead_words = nullptr; long long dead_words_cap = 0;
+    uint32_t *dead_words = nullptr; long long dead_words_cap = 0;   // per-cell fill cursors of espic_dsmc_mex (transient scratch)
     uint32_t *hit_words = nullptr;  long long hit_words_cap = 0;    // ions that hit the sphere (espic_push_surface)
-    uint32_t *leave_words = nullptr; long long leave_words_cap = 0; // survivors that leave this part (espic_migrate.cuh)
     int dom_klo = 0, dom_khi = 1 << 30;                             // cell planes this part owns (espic_domain_set)
     uint32_t *scan_pre = nullptr;  long long scan_cap = 0;
     uint32_t *scan_coff = nullptr; long long scan_coff_cap = 0;
@@ -92,6 +95,9 @@ int  espic_cuda_fail(cudaError_t e, const char *what, const char *file, int line
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return espic_cuda_fail(e_, #call, __FILE__, __LINE__); } while (0)
 #define LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return espic_cuda_fail(e_, "kernel launch", __FILE__, __LINE__); } while (0)
+
+// between espic_push(ESPIC_PUSH_MIGRATE) / espic_migrate_pack and the end of the migration the arrays still hold the dead and the leavers
+#define MIG_GUARD(c, s, who) do { if ((s).mig_stage != 0) { espic_set_error("%s: a migration of this species is pending (call espic_migrate / espic_migrate_finish first)", who); return -1; } } while (0)
 
 int espic_ensure(void **ptr, long long *cap, long long need, size_t elem, cudaStream_t s);
 template <typename T> static inline int ensure_buf(T **ptr, long long *cap, long long need, cudaStream_t s)

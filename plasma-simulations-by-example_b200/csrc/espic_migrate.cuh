@@ -244,6 +244,9 @@ static int mig_pack_enqueue(espic_ctx *c, int sp)
     MigState *g = (MigState *)c->mig;
     Species &s = c->sp[sp];
     const int P = g->dom.parts;
+    // the packed segments live in ONE staging buffer per context: a second species may only be packed once the first is finished
+    for (int q = 0; q < c->nsp; q++)
+        if (q != sp && c->sp[q].mig_stage == 2) { espic_set_error("espic_migrate_pack: species %d is packed and not finished (espic_migrate_finish) -- its segments would be overwritten", q); return -1; }
     g->L = 0;
     g->counts_on_host = false;
     for (int r = 0; r < P; r++) { g->counts[r] = 0; g->offs[r] = 0; }
@@ -254,9 +257,9 @@ static int mig_pack_enqueue(espic_ctx *c, int sp)
         s.mig_n = s.np;
         const long long nw = (s.mig_n + 31) / 32;
         if (nw > 0) {
-            if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw + nw / 16 + 1024, c->stream))) return r;
-            if ((r = ensure_buf(&c->leave_words, &c->leave_words_cap, nw, c->stream))) return r;
-            k_mig_flags<<<nblk(nw * 32, 256), 256, 0, c->stream>>>(c->m, g->dom, s.p[2], s.mig_n, c->leave_words, c->dead_words);
+            if ((r = ensure_buf(&s.kill_words, &s.kill_cap, nw + nw / 16 + 1024, c->stream))) return r;
+            if ((r = ensure_buf(&s.leave_words, &s.leave_cap, nw, c->stream))) return r;
+            k_mig_flags<<<nblk(nw * 32, 256), 256, 0, c->stream>>>(c->m, g->dom, s.p[2], s.mig_n, s.leave_words, s.kill_words);
             LAUNCH_CHECK(c);
         }
     }
@@ -264,7 +267,7 @@ static int mig_pack_enqueue(espic_ctx *c, int sp)
     const long long n = s.mig_n, nw = (n + 31) / 32;
     if (n == 0 || P == 1) return 0;
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
-    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->leave_words, nw, c->cell_cnt);
+    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(s.leave_words, nw, c->cell_cnt);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
     unsigned long long *h = (unsigned long long *)c->hpin;
@@ -281,7 +284,7 @@ static int mig_pack_enqueue(espic_ctx *c, int sp)
     if ((r = ensure_buf(&g->dest, &g->dest_cap, Lcap, c->stream))) return r;
     if ((r = ensure_buf(&g->hist, &g->hist_cap, ccap * P, c->stream))) return r;
     if ((r = ensure_buf(&g->send, &g->send_cap, 7 * Lcap, c->stream))) return r;
-    k_mig_list<<<nblk(nw, 256), 256, 0, c->stream>>>(c->m, g->dom, s.p[2], nw, c->leave_words, c->scan_pre, c->scan_coff, g->idx, g->dest);
+    k_mig_list<<<nblk(nw, 256), 256, 0, c->stream>>>(c->m, g->dom, s.p[2], nw, s.leave_words, c->scan_pre, c->scan_coff, g->idx, g->dest);
     LAUNCH_CHECK(c);
 #define MIG_PART_ARGS L, P, g->dest, g->idx, g->hist, g->dcnt, g->dcnt + P, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], g->send
     k_mig_partition<false><<<(unsigned)nchunks, MIG_CHUNK, 0, c->stream>>>(MIG_PART_ARGS);
@@ -346,17 +349,17 @@ extern "C" int espic_migrate_finish(espic_ctx *c, int sp)
     Species &s = c->sp[sp];
     if (s.mig_stage != 2) { espic_set_error("espic_migrate_finish: species %d has no packed migration", sp); return -1; }
     const long long nw_old = (s.mig_n + 31) / 32, nw_new = (s.np + 31) / 32;
-    if (nw_new > c->dead_words_cap) {            // grow, keeping the kill bits
+    if (nw_new > s.kill_cap) {            // grow, keeping the kill bits
         uint32_t *nb = nullptr;
         const long long ncap = 2 * nw_new;
         CK(cudaMalloc(&nb, (size_t)ncap * sizeof(uint32_t)));
-        if (nw_old > 0) CK(cudaMemcpyAsync(nb, c->dead_words, (size_t)nw_old * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        if (nw_old > 0) CK(cudaMemcpyAsync(nb, s.kill_words, (size_t)nw_old * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        CK(cudaFree(c->dead_words));
-        c->dead_words = nb;
-        c->dead_words_cap = ncap;
+        CK(cudaFree(s.kill_words));
+        s.kill_words = nb;
+        s.kill_cap = ncap;
     }
-    if (nw_new > nw_old) CK(cudaMemsetAsync(c->dead_words + nw_old, 0, (size_t)(nw_new - nw_old) * sizeof(uint32_t), c->stream));
+    if (nw_new > nw_old) CK(cudaMemsetAsync(s.kill_words + nw_old, 0, (size_t)(nw_new - nw_old) * sizeof(uint32_t), c->stream));
     s.mig_stage = 0;
     int r = 0;
     if (s.np > 0) r = compact_dead(c, s, s.np);

@@ -7,8 +7,6 @@
 #include <math.h>
 
 #define SP_CHECK(c, sp) do { if ((sp) < 0 || (sp) >= (c)->nsp) { espic_set_error("bad species id %d", (sp)); return -1; } } while (0)
-// between espic_push(ESPIC_PUSH_MIGRATE) / espic_migrate_pack and the end of the migration the arrays still hold the dead and the leavers
-#define MIG_GUARD(c, s, who) do { if ((s).mig_stage != 0) { espic_set_error("%s: a migration of this species is pending (call espic_migrate / espic_migrate_finish first)", who); return -1; } } while (0)
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // =====================================================================================================
@@ -606,7 +604,7 @@ static int prepare_acc(espic_ctx *c, Species &s, int mode)
     return 0;
 }
 
-// count the dead of dead_words (one bit per particle of [0,n)), then remove them in the reference's order
+// count the dead of the species' kill words (one bit per particle of [0,n)), then remove them in the reference's order
 static int compact_dead(espic_ctx *c, Species &s, long long n)
 {
     const long long nw = (n + 31) / 32;
@@ -615,7 +613,7 @@ static int compact_dead(espic_ctx *c, Species &s, long long n)
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_a = trace ? now() : 0;
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nw, c->stream))) return r;
-    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, c->cell_cnt);
+    k_dead_popc<<<nblk(nw, 256), 256, 0, c->stream>>>(s.kill_words, nw, c->cell_cnt);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nw, c->dscal))) return r;
     unsigned long long *h = (unsigned long long *)c->hpin;
@@ -628,7 +626,7 @@ static int compact_dead(espic_ctx *c, Species &s, long long n)
     if (D < n) {
         if ((r = ensure_buf(&c->lists, &c->lists_cap, std::max(2 * D, n / 64), c->stream))) return r;
         CK(cudaMemsetAsync(c->lists, 0xff, (size_t)D * sizeof(long long), c->stream));
-        k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(c->dead_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
+        k_fill_lists<<<nblk(nw, 256), 256, 0, c->stream>>>(s.kill_words, nw, n, c->scan_pre, c->scan_coff, c->dscal,
                                                            c->lists, c->lists + D);
         LAUNCH_CHECK(c);
         k_move<<<nblk(D, 256), 256, 0, c->stream>>>(D, c->lists, c->lists + D, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6]);
@@ -662,15 +660,15 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     const long long nw = (n + 31) / 32;
     int r;
     // with MIGRATE the words must also cover the arrivals appended before the removal: leave headroom so they rarely regrow
-    if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, mig ? nw + nw / 16 + 1024 : nw, c->stream))) return r; }
-    if (mig) { if ((r = ensure_buf(&c->leave_words, &c->leave_words_cap, nw, c->stream))) return r; }
+    if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&s.kill_words, &s.kill_cap, mig ? nw + nw / 16 + 1024 : nw, c->stream))) return r; }
+    if (mig) { if ((r = ensure_buf(&s.leave_words, &s.leave_cap, nw, c->stream))) return r; }
     const unsigned grid = nblk((n + 1) / 2, 256);
     if (!c->push_ev0) { CK(cudaEventCreate(&c->push_ev0)); CK(cudaEventCreate(&c->push_ev1)); }
     CK(cudaEventRecord(c->push_ev0, c->stream));
     static const int ahead_env = getenv("ESPIC_PUSH_PREFETCH") ? atoi(getenv("ESPIC_PUSH_PREFETCH")) : -1;
     // default distance: two blocks per SM (measured plateau: 1-3 blocks per SM)
     const int ahead = ahead_env >= 0 ? ahead_env : 2 * c->sm_count;
-#define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, c->dead_words, s.acc, scale, ahead, c->leave_words, c->dom_klo, c->dom_khi
+#define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, s.kill_words, s.acc, scale, ahead, s.leave_words, c->dom_klo, c->dom_khi
     if (wall_mode == ESPIC_WALL_ABSORB) {
         if (mig) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64, true><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
@@ -1086,6 +1084,7 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
 {
     Species &s = c->sp[sp];
     if (n_added) *n_added = 0;
+    MIG_GUARD(c, s, "espic_species_add / espic_inject_*");
     if (n <= 0) return 0;
     int r;
     if ((r = espic_species_reserve(c, sp, s.np + n))) return r;

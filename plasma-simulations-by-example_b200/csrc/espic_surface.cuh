@@ -257,6 +257,7 @@ extern "C" int espic_push_surface(espic_ctx *c, int sp, double dt, int neutrals_
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
     if (emitted) emitted[0] = emitted[1] = 0;
+    MIG_GUARD(c, s, "espic_push_surface");
     const bool charged = s.charge != 0;
     if (charged) {
         SP_CHECK(c, neutrals_sp);
@@ -265,6 +266,8 @@ extern "C" int espic_push_surface(espic_ctx *c, int sp, double dt, int neutrals_
             espic_set_error("espic_push_surface: an ion species cannot emit into itself (species %d)", sp);
             return -1;
         }
+        MIG_GUARD(c, c->sp[neutrals_sp], "espic_push_surface (emission target)");
+        MIG_GUARD(c, c->sp[sput_sp], "espic_push_surface (emission target)");
         if (!(c->sp[neutrals_sp].mpw0 > 0) || !(c->sp[sput_sp].mpw0 > 0) || s.mpw0 / c->sp[neutrals_sp].mpw0 > 1e5) {
             espic_set_error("espic_push_surface: bad macroparticle weight ratio between species %d and its emission targets", sp);
             return -1;
@@ -276,7 +279,7 @@ extern "C" int espic_push_surface(espic_ctx *c, int sp, double dt, int neutrals_
     if (n == 0) { s.n_settled = 0; return 0; }
     const long long nw = (n + 31) / 32;
     int r;
-    if ((r = ensure_buf(&c->dead_words, &c->dead_words_cap, nw, c->stream))) return r;
+    if ((r = ensure_buf(&s.kill_words, &s.kill_cap, nw, c->stream))) return r;
     if (charged && (r = ensure_buf(&c->hit_words, &c->hit_words_cap, nw, c->stream))) return r;
     SurfPar p;
     p.charge = s.charge; p.mass = s.mass; p.dt = dt;
@@ -285,10 +288,10 @@ extern "C" int espic_push_surface(espic_ctx *c, int sp, double dt, int neutrals_
     p.seed = seed; p.stream = stream; p.step = step;
     if (charged)
         k_push_surface<true><<<nblk(n, 256), 256, 0, c->stream>>>(c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
-                                                                  n, p, c->dead_words, c->hit_words);
+                                                                  n, p, s.kill_words, c->hit_words);
     else
         k_push_surface<false><<<nblk(n, 256), 256, 0, c->stream>>>(c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
-                                                                   n, p, c->dead_words, nullptr);
+                                                                   n, p, s.kill_words, nullptr);
     LAUNCH_CHECK(c);
     if (s.pushes_since_sort < (1 << 20)) s.pushes_since_sort++;
     if (charged) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
     "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_mg_plan", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
-    "espic_comm_init", "espic_allreduce_density",
+    "espic_comm_init",
     "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment", "espic_migrate_finish",
 ]
 
@@ -107,7 +107,6 @@ def load():
     L.espic_field_pe.argtypes = [vp, dp]
     L.espic_comm_unique_id.argtypes = [vp]
     L.espic_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
-    L.espic_allreduce_density.argtypes = [vp, C.c_int]
     ip, llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
     L.espic_domain_set.argtypes = [vp, C.c_int, C.c_int, ip]
     L.espic_domain_get.argtypes = [vp, ip, ip, ip]
@@ -347,8 +346,6 @@ class Engine:
     def comm_init(self, rank, nranks, uid):
         self._ck(self.L.espic_comm_init(self.h, rank, nranks, C.c_char_p(uid)))
 
-    def allreduce_density(self, sp):
-        self._ck(self.L.espic_allreduce_density(self.h, sp))
 
     # ---- spatial decomposition with particle migration (ch9/MPI initMPIDomain / transferParticles)
     def set_domain(self, parts, part, k_bounds):

@@ -308,3 +308,85 @@ def test_gpu_migrate_edge_cases():
         g.e.migrate(g.species[0])               # no communicator of that shape
     for x in engines + [g]:
         x.e.close()
+
+
+def _gpu_migrate_species_on_one_device(engines, q):
+    """as _gpu_migrate_on_one_device, for species index q of every part"""
+    R = len(engines)
+    counts = [g.e.migrate_pack(g.species[q]) for g in engines]
+    for dst in range(R):
+        for src in range(R):
+            if src == dst or counts[src][dst] == 0:
+                continue
+            ptr, cnt = engines[src].e.migrate_segment(dst)
+            engines[dst].e.upload_device(engines[dst].species[q], [ptr + 8 * c * cnt for c in range(7)], cnt, 0.0, append=True)
+    for g in engines:
+        g.e.migrate_finish(g.species[q])
+    return np.array(counts)
+
+
+@pytest.mark.gpu
+def test_gpu_two_species_push_all_then_migrate_all():
+    """the kill / leave bits of a MIGRATE push belong to the SPECIES.  The natural loop
+    `for sp: push(MIGRATE)` then `for sp: migrate` must give, per species, exactly the run that pushes and migrates one
+    species at a time; calls that would clobber a pending migration of the same species fail instead of corrupting it."""
+    es = __import__("engines")._espic()
+    from engines import GpuEngine
+    kb, dt = [0, 3, 9, 13], 2e-6
+    w, spa = cases.sphere_case(seed=81, ni=9, nj=8, nk=14, n=30000, near_walls=0.1)
+    _, spb = cases.sphere_case(seed=82, ni=9, nj=8, nk=14, n=17001, near_walls=0.2, v_drift=9000.0)
+    st = sf.state_from_oracle(w, [spa, spb], dt)
+    z0, dhz = st.x0[2], (st.xm[2] - st.x0[2]) / (st.nk - 1)
+    full = [r["part"] for r in st.species]
+    split = [mm.split_by_owner(p, z0, dhz, st.nk, kb) for p in full]
+
+    def make_parts():
+        out = []
+        for r in range(len(kb) - 1):
+            for q in range(2):
+                st.species[q]["part"] = split[q][r]
+            g = GpuEngine(st)
+            g.e.set_domain(len(kb) - 1, r, kb)
+            out.append(g)
+        for q in range(2):
+            st.species[q]["part"] = full[q]
+        return out
+
+    inter, seq = make_parts(), make_parts()
+    moved = 0
+    for step in range(4):
+        # interleaved: every species pushed first, then every species migrated
+        for g in inter:
+            for q in range(2):
+                g.e.push(g.species[q], dt, es.WALL_ABSORB, es.PUSH_MIGRATE)
+        for g in inter[:1]:        # guards: the pending species refuses anything that would move or overwrite its particles
+            for call in (lambda: g.e.push(g.species[0], dt, es.WALL_ABSORB, 0),
+                         lambda: g.e.add_particles(g.species[0], full[0][:, :5].copy(), dt),
+                         lambda: g.e.upload(g.species[0], full[0][:, :5].copy()),
+                         lambda: g.e.sort_by_cell(g.species[0]),
+                         lambda: g.e.inject_cold_beam(g.species[0], 7000.0, 1e10, dt, 1, 0, step)):
+                with pytest.raises(es.EspicError):
+                    call()
+        for q in range(2):
+            moved += int(_gpu_migrate_species_on_one_device(inter, q).sum())
+        # sequential: one species at a time
+        for q in range(2):
+            for g in seq:
+                g.e.push(g.species[q], dt, es.WALL_ABSORB, es.PUSH_MIGRATE)
+            _gpu_migrate_species_on_one_device(seq, q)
+        for r, (a, b) in enumerate(zip(inter, seq)):
+            for q in range(2):
+                pa, pb = a.e.download(a.species[q]), b.e.download(b.species[q])
+                assert pa.shape == pb.shape, (step, r, q, pa.shape, pb.shape)
+                assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64)), "step %d part %d species %d" % (step, r, q)
+    assert moved > 0
+    # and both equal the single-domain run, species by species
+    one = GpuEngine(st)
+    for step in range(4):
+        for q in range(2):
+            one.e.push(one.species[q], dt, es.WALL_ABSORB, 0)
+    for q in range(2):
+        allp = np.concatenate([g.e.download(g.species[q]) for g in inter], axis=1)
+        assert np.array_equal(mm.canonical(allp).view(np.uint64), mm.canonical(one.e.download(one.species[q])).view(np.uint64))
+    for g in inter + seq + [one]:
+        g.e.close()
