@@ -216,74 +216,376 @@ def host_particles(rng, n, mpw):
     return p
 
 
-def run_ref(which, state, cmds, tmpdir, timeout):
+def run_ref(which, state_path, cmds, timeout):
     """Run an oracle/_ref harness binary (compiled from the unmodified reference) with per-command timing."""
-    import statefile as sf
-    fin = os.path.join(tmpdir, "in.state")
-    sf.write_state(fin, state)
     env = dict(os.environ, ESPIC_REF_TIMING="1", ESPIC_REF_NODUMP="1")
-    out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", which), fin, os.path.join(tmpdir, "out.state")] + cmds,
+    out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", which), state_path, "/dev/null"] + cmds,
                          check=True, capture_output=True, text=True, env=env, timeout=timeout)
     return [(line.split()[1], float(line.split()[2])) for line in out.stdout.splitlines() if line.startswith("T ")]
 
 
-def reference_cpu_step(args, e, es, sp, n_total, mpw, steps, warmup, budget_s):
-    """Time the reference's own CPU implementation of one full step of THIS workload on a bounded sample.
+GS_RECORD = os.path.join(ROOT, "profiles", "r2_reference_gs_convergence.json")
 
-    particle phases  Species::advance + computeNumberDensity on `cpu_sample` particles (uniform sample of the same
-                     distribution, E from the warm GPU state), `warmup`+`steps` repetitions, scaled linearly to the full
-                     population; serial ch3/ver2 build and, if built, the ch9/MT std::thread build on all host cores.
-    mesh phases      computeChargeDensity + computeEF as measured; the Poisson solve is the reference's solveGS
-                     (the solver ch3/ver2/Main.cpp ships with; its Newton-PCG breaks down at n0=1e12)
-                     run ONCE to its own tolerance from the previous step's phi on the next step's rho -- exactly the
-                     warm-started solve a full-size reference step performs.
+
+def reference_cpu_step(mesh, n_total, steps, warmup, n_sample, gs_sweeps, budget_s=1500.0):
+    """Time the reference's own CPU implementation (oracle/_ref, the unmodified ch3/ver2 and ch9/MT sources, g++ -O2) of one
+    full step of THIS workload on the host cores.  Pure CPU: no CUDA, none of this repo's engine -- the fields the particles
+    move in are produced by the reference itself (deposit -> rho -> solveQN -> computeEF on the sample).
+
+    particle phases  Species::advance + computeNumberDensity on `n_sample` particles of the workload's distribution (weight
+                     scaled so the density is the workload's), `warmup`+`steps` repetitions, mean of the timed ones, scaled
+                     linearly to the full population (`sample_factor`; both loops are O(N) with no N-dependent state).
+                     Serial ch3/ver2 build and the ch9/MT std::thread build on all host cores; the faster one counts.
+    mesh phases      computeChargeDensity, computeEF, solveQN: measured at full size, no scaling.
+    Poisson          the solver ch3/ver2/Main.cpp ships with, solveGS (its Newton-PCG breaks down at n0 = 1e12):
+                     `gs_sweeps` sweeps are timed live (max_it = gs_sweeps, tolerance 0 so it cannot stop early); the number
+                     of sweeps one warm-started solve needs to reach the shipped tolerance 1e-4 is read from the committed
+                     record of a run of the same binary to convergence on this workload's own warm state
+                     (profiles/r2_reference_gs_convergence.json, scripts/ref_gs_convergence.py).
     """
     import statefile as sf
     t_begin = time.time()
-    n_sample = int(args.cpu_sample)
-    nn = args.mesh ** 3
-    # fields of step n, then rho of step n+1 from the GPU engine (the reference's solve input at full statistics)
-    st = sample_state(args, e, es, n_sample, mpw, n_total)
-    e.push(sp, DT, es.WALL_ABSORB, es.PUSH_FUSE_DEPOSIT)
-    e.deposit(sp, es.DEPOSIT_FP64)
-    e.compute_charge_density()
-    rho_next = e.field(es.RHO)
-    res = {"cores": 1, "kind": "reference", "unit": "particle-pushes/s"}
+    nn = mesh ** 3
+    box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
+    st = sf.State()
+    st.ni = st.nj = st.nk = mesh
+    st.flags = 3 | 4                      # addSphere + addInlet, keep the potential they set
+    st.x0, st.xm, st.dt = np.array(X0), np.array(XM), DT
+    st.sphere_c, st.sphere_r, st.sphere_phi = np.array(SPHERE[0]), SPHERE[1], SPHERE[2]
+    st.phi0, st.Te0, st.n0 = PHI0, TE0, N0
+    part = host_particles(np.random.default_rng(4242), n_sample, N0 * box_vol / n_sample)
+    st.species = [dict(mass=16 * AMU, charge=QE, mpw0=part[6, 0], den=np.zeros(nn), den_ave=np.zeros(nn), part=part)]
+    res = {"cores": 1, "kind": "reference", "unit": "particle-pushes/s", "extrapolated": True,
+           "sample_factor": n_total / n_sample, "sample_particles": n_sample}
+    prep = ["deposit", "rho", "solve_qn", "ef"]
+    reps = warmup + steps
     with tempfile.TemporaryDirectory() as tmp:
-        t = run_ref("ref_ch3", st, ["advance", "deposit", "rho", "ef"] * (warmup + steps), tmp, timeout=budget_s)
-        tt = np.array([x[1] for x in t]).reshape(warmup + steps, 4)[warmup:]
-        t_adv, t_dep, t_rho, t_ef = tt.mean(axis=0)
+        fin = os.path.join(tmp, "in.state")
+        sf.write_state(fin, st)
+        del part, st
+        left = lambda: max(30.0, budget_s - (time.time() - t_begin))
+        t = run_ref("ref_ch3", fin, prep + ["advance", "deposit", "rho", "ef", "solve_qn"] * reps + ["solve_gs:%d:0" % gs_sweeps], left())
+        body = t[len(prep):]
+        tt = np.array([x[1] for x in body[:5 * reps]]).reshape(reps, 5)[warmup:]
+        t_adv, t_dep, t_rho, t_ef, t_qn = tt.mean(axis=0)
+        t_sweep = body[5 * reps][1] / gs_sweeps
         res["ns_per_particle_serial"] = {"advance": t_adv / n_sample * 1e9, "deposit": t_dep / n_sample * 1e9}
+        res["spread"] = {"advance": float(tt[:, 0].std() / t_adv), "deposit": float(tt[:, 1].std() / t_dep)}
         cores = 1
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_mt")):
             try:
                 nc = os.cpu_count() or 1
-                t = run_ref("ref_mt", st, ["threads:%d" % nc] + ["advance", "deposit"] * (warmup + steps), tmp, timeout=budget_s)
-                tm = np.array([x[1] for x in t if x[0] in ("advance", "deposit")]).reshape(warmup + steps, 2)[warmup:].mean(axis=0)
+                t = run_ref("ref_mt", fin, prep + ["threads:%d" % nc] + ["advance", "deposit"] * reps, left())
+                tm = np.array([x[1] for x in t if x[0] in ("advance", "deposit")][1:]).reshape(reps, 2)[warmup:].mean(axis=0)
                 res["ns_per_particle_threads"] = {"advance": tm[0] / n_sample * 1e9, "deposit": tm[1] / n_sample * 1e9, "threads": nc}
                 if tm.sum() < t_adv + t_dep:
                     t_adv, t_dep, cores = tm[0], tm[1], nc
             except Exception as ex:
                 res["ns_per_particle_threads"] = {"error": repr(ex)}
-        # one warm-started full solve
-        st2 = sample_state(args, e, es, 0, mpw, n_total)
-        st2.phi, st2.rho = st.phi, rho_next
-        left = max(30.0, budget_s - (time.time() - t_begin))
-        solver_note = "solveGS(20000,1e-4) warm-started, run once"
-        try:
-            t = run_ref("ref_ch3", st2, ["solve_gs:20000:1e-4"], tmp, timeout=left)
-            t_solve = t[0][1]
-        except subprocess.TimeoutExpired:
-            t_solve = left
-            solver_note = "solveGS did not reach its tolerance within the %.0f s budget: lower bound used" % left
     scale = n_total / n_sample
-    t_step = (t_adv + t_dep) * scale + t_rho + t_ef + t_solve
-    res.update({"value": n_total / t_step, "cores": cores, "s_per_step_full_size": t_step,
-                "phases_s": {"advance(sample)": t_adv, "deposit(sample)": t_dep, "rho": t_rho, "solve": t_solve, "ef": t_ef},
-                "sample": "unmodified reference sources (oracle/_ref, g++ -O2): %d^3 mesh; advance+deposit on %d of %d particles "
-                          "(x%.0f, %d core%s), rho+ef measured, Poisson = %s" % (args.mesh, n_sample, n_total, scale, cores,
-                                                                                "s" if cores > 1 else "", solver_note)})
+    t_particles = (t_adv + t_dep) * scale
+    res["cores"] = cores
+    res["phases_s"] = {"advance(sample)": t_adv, "deposit(sample)": t_dep, "rho": t_rho, "ef": t_ef, "solveQN": t_qn,
+                       "solveGS per sweep": t_sweep, "solveGS sweeps timed": gs_sweeps}
+    # the same step with the solver ch9/Main.cpp ships (SolverType::QN): nothing but the particle count is extrapolated
+    t_step_qn = t_particles + t_rho + t_qn + t_ef
+    res["qn_step"] = {"value": n_total / t_step_qn, "s_per_step_full_size": t_step_qn}
+    rec = None
+    if os.path.exists(GS_RECORD):
+        try:
+            rec = json.load(open(GS_RECORD))
+            if int(rec["mesh"]) != mesh:
+                rec = None
+        except Exception:
+            rec = None
+    if rec is None:
+        res.update({"value": None, "s_per_step_full_size": None,
+                    "reason": "no committed convergence record of the reference's solveGS for a %d^3 mesh: the Poisson phase of its "
+                              "shipped solver is not extrapolated from a guess; see qn_step for the fully measured variant" % mesh})
+    else:
+        sweeps = float(rec["sweeps_to_converge"])
+        t_step = t_particles + t_rho + t_ef + t_sweep * sweeps
+        res.update({"value": n_total / t_step, "s_per_step_full_size": t_step,
+                    "poisson": {"solver": "solveGS(20000, 1e-4), warm-started", "per_sweep_s": t_sweep, "sweeps_to_converge": sweeps,
+                                "solve_s": t_sweep * sweeps, "record": os.path.relpath(GS_RECORD, ROOT),
+                                "record_note": rec.get("note", "")}})
+    res["sample"] = ("unmodified reference sources (oracle/_ref, g++ -O2), %d^3 mesh: advance+deposit measured on %d of %d particles "
+                     "(x%.0f, %d core%s); rho, computeEF, solveQN measured at full size; Poisson = solveGS per-sweep time measured over %d "
+                     "sweeps x %s sweeps to its tolerance" % (mesh, n_sample, n_total, scale, cores, "s" if cores > 1 else "", gs_sweeps,
+                                                               "%.0f recorded" % rec["sweeps_to_converge"] if rec else "(no record)"))
+    res["wall_s"] = time.time() - t_begin
     return res
+
+
+class Case:
+    """One engine + one ion species for a configuration of the sphere case, warm-started (untimed), with the timed PIC step."""
+
+    def __init__(self, ctx, mesh, n_local, n_total, solver_name, sort_every=8, fixed_point=False, fuse=False, decomp=False, seed=12345):
+        es, torch, dist = ctx["es"], ctx["torch"], ctx["dist"]
+        rank, world, local_rank, dev = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dev"]
+        self.ctx, self.es, self.mesh, self.n_local, self.n_total = ctx, es, mesh, n_local, n_total
+        self.solver_name, self.sort_every, self.fuse = solver_name, sort_every, fuse
+        box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
+        self.mpw = mpw = N0 * box_vol / n_total
+        solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "mgslab": es.SOLVE_PCG_MG_SLAB, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[solver_name]
+        if solver_name == "mgslab" and world == 1:
+            solver = es.SOLVE_PCG_MG
+        self.solver, self.max_it, self.tol = solver, 5000, 1e-4
+        e = es.Engine(mesh, mesh, mesh, X0, XM, device=local_rank)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        e.add_sphere(*SPHERE)
+        e.add_inlet()
+        e.set_reference_values(PHI0, TE0, N0)
+        self.e = e
+        self.sp = sp = e.add_species(16 * AMU, QE, mpw, capacity=int(n_local * 1.02) + 1024)
+        if world > 1:
+            uid = [e.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            e.comm_init(rank, world, uid[0])
+        self.decomp = decomp and world > 1
+        if self.decomp and fuse:
+            raise SystemExit("--decomp needs the separate deposit kernel (the fused scatter would run before the migration)")
+        zrange = None
+        if self.decomp:
+            dhz = (XM[2] - X0[2]) / (mesh - 1)
+            kb = es.balanced_bounds(free_volume_per_cell_plane(mesh), world)     # equal particle counts, not equal node counts
+            zrange = (X0[2] + kb[rank] * dhz, X0[2] + kb[rank + 1] * dhz)
+            e.set_domain(world, rank, kb)
+        # generated in pieces of at most 5e7 so that the temporaries stay small next to a 1e9-particle population
+        done = 0
+        while done < n_local:
+            m = min(n_local - done, 50_000_000)
+            t = make_particles_device(torch, m, seed + 1000 * rank + done // 50_000_000, mpw, dev, zrange)
+            e.upload_device(sp, [t[c].data_ptr() for c in range(7)], m, mpw, append=done > 0)
+            e.sync()
+            del t
+            done += m
+        if self.decomp:
+            log("initial migration: sent %d, received %d" % e.migrate(sp))     # particles moved out of the sphere change slab
+        torch.cuda.empty_cache()
+        self.dmode = es.DEPOSIT_FIXED if fixed_point else es.DEPOSIT_FP64
+        self.pflags = ((es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if fixed_point else 0)) if fuse else 0) | (es.PUSH_MIGRATE if self.decomp else 0)
+        log("particles resident: %d on rank %d (%d^3 mesh)" % (n_local, rank, mesh))
+        e.sort_by_cell(sp)
+        e.deposit(sp, self.dmode)
+        e.compute_charge_density()
+        e.solve(es.SOLVE_QN, 1, 1.0)                     # the reference's own initial guess (ctor -> solveQN)
+        info0 = e.solve(es.SOLVE_GS, 20000, 1e-2)        # robust nonlinear SOR to get near the solution
+        log("initial SOR: %s" % (info0,))
+        if solver_name != "qn":
+            info0 = e.solve(solver, self.max_it, self.tol)
+            log("initial %s: %s" % (solver_name, info0))
+        e.compute_ef()
+        self.step_no = 0
+
+    def step(self, solver=None, rec=None, ev=None):
+        """push (+ migration) | sort when due | deposit + rho | Poisson | E; ev: six CUDA events recorded at the phase boundaries"""
+        e, es, sp = self.e, self.es, self.sp
+        i = self.step_no
+        self.step_no += 1
+        if ev:
+            ev[0].record()
+        n_before = e.count(sp)
+        e.push(sp, DT, es.WALL_ABSORB, self.pflags)
+        sent = e.migrate(sp)[0] if self.decomp else 0     # inside the push phase
+        if ev:
+            ev[1].record()
+        k_ms = e.last_push_ms() if rec is not None else 0.0    # CUDA events around the k_push launch itself, on the launching stream
+        if self.sort_every > 0 and i % self.sort_every == 0 and not self.fuse:
+            e.sort_by_cell(sp)       # between push and deposit: the scatter sees perfectly ordered particles
+        if ev:
+            ev[2].record()
+        e.deposit(sp, self.dmode)
+        e.compute_charge_density()
+        if ev:
+            ev[3].record()
+        inf = e.solve(self.solver if solver is None else solver, self.max_it, self.tol)
+        if ev:
+            ev[4].record()
+        e.compute_ef()
+        if ev:
+            ev[5].record()
+        if rec is not None:
+            rec.append((n_before, inf, k_ms, sent))
+
+    def timed(self, steps, warmup, solver=None, profile_range=False):
+        """`warmup` untimed steps, then exactly `steps` timed ones between barrier + synchronize; device time, max over ranks"""
+        torch, dist, world, dev = self.ctx["torch"], self.ctx["dist"], self.ctx["world"], self.ctx["dev"]
+        for i in range(warmup):
+            wc = []
+            self.step(solver, wc)
+            log("warm-up step %d: n=%d %s" % (i, wc[0][0], wc[0][1]))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
+        rec = []
+        launches0 = self.e.kernel_launches()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile_range:
+            torch.cuda.profiler.start()
+        ev0.record()
+        for i in range(steps):
+            self.step(solver, rec, phase_ev[i])
+        ev1.record()
+        torch.cuda.synchronize()
+        if profile_range:
+            torch.cuda.profiler.stop()
+        if world > 1:
+            dist.barrier()
+        launches = self.e.kernel_launches() - launches0
+        ms = ev0.elapsed_time(ev1)
+        pushed_local = float(sum(r[0] for r in rec))
+        pushed = pushed_local
+        if world > 1:
+            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+            tp = torch.tensor([pushed_local], dtype=torch.float64, device=dev)
+            dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+            pushed = float(tp.item())
+        ph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in phase_ev]).mean(axis=0)   # push, sort, dep+rho, solve, ef
+        return {"ms": ms, "ms_per_step": ms / steps, "pushed": pushed, "pushed_local": pushed_local, "value": pushed / (ms * 1e-3),
+                "phases_ms": {"sort(amortised)": float(ph[1]), "push+removal": float(ph[0]), "deposit+rho": float(ph[2]),
+                              "poisson": float(ph[3]), "ef": float(ph[4])},
+                "kernel_ms": float(np.mean([r[2] for r in rec])), "launches": int(launches),
+                "pcg_iters_per_step": float(np.mean([r[1]["lin_iters"] for r in rec])),
+                "newton_iters_per_step": float(np.mean([r[1]["nr_iters"] for r in rec])),
+                "migrated_per_step": float(np.mean([r[3] for r in rec])), "steps": steps, "warmup": warmup}
+
+    def close(self):
+        self.e.close()
+        self.ctx["torch"].cuda.empty_cache()
+
+
+# algorithmic bytes of the multigrid Newton solve (DESIGN.md 3, espic_mg.cuh), per node
+MG_FINE_BYTES_PER_IT = 97      # A: r 8 + diag 4 | B: r 8 + diag 4 + e 1, z 4 written | C: z 4 + d 8 + diag 4, d' 8 written | D: d' 8 + diag 4 + delta 8+8 + r 8+8
+MG_COARSE_BYTES_PER_IT = 62    # FP32 level: down 24 read + 5 written, up 29 read + 4 written
+MG_NEWTON_BYTES = 75           # linearise 17 read + 28 written, Galerkin 5, update 17 read + 8 written
+MG_LINEARISE_BYTES = 45        # the closing residual evaluation
+
+
+def poisson_roofline(case, res, peak):
+    """Achieved bytes/s of the Poisson phase: algorithmic bytes of every pass of the multigrid Newton kernel x the iteration
+    counts of the timed steps, over the phase time (CUDA events around espic_solve).  Per rank: a k-slab in slab mode."""
+    es = case.es
+    dh = [(XM[a] - X0[a]) / (case.mesh - 1) for a in range(3)]
+    dims, _, _ = es.mg_plan(case.mesh, case.mesh, case.mesh, dh, 1)
+    share = 1.0 / case.ctx["world"] if (case.solver_name == "mgslab" and case.ctx["world"] > 1) else 1.0
+    fine = float(np.prod(dims[0])) * share
+    coarse = float(sum(np.prod(d) for d in dims[1:])) * share
+    per_it = MG_FINE_BYTES_PER_IT * fine + MG_COARSE_BYTES_PER_IT * coarse
+    byt = per_it * res["pcg_iters_per_step"] + MG_NEWTON_BYTES * fine * res["newton_iters_per_step"] + MG_LINEARISE_BYTES * fine
+    t = res["phases_ms"]["poisson"] * 1e-3
+    ach = byt / t / 1e9 if t > 0 else 0.0
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "bytes_per_cg_iteration": per_it, "bytes_per_step": byt, "phase_ms": res["phases_ms"]["poisson"],
+            "levels": [list(d) for d in dims],
+            "note": "algorithmic bytes per rank: (%d B/fine node + %d B/coarse node) x CG iterations + %d B/fine node x Newton steps + %d B/fine node, over "
+                    "the Poisson phase time of the timed region" % (MG_FINE_BYTES_PER_IT, MG_COARSE_BYTES_PER_IT, MG_NEWTON_BYTES, MG_LINEARISE_BYTES)}
+
+
+def digest(a):
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(a).view(np.uint8)).hexdigest()
+
+
+def parity_check(ctx, head):
+    """N > 1, untimed, after the headline region: the assertions of tests/test_multigpu.py executed under torch.distributed.run.
+      slab          ESPIC_SOLVE_PCG_MG_SLAB against the replicated ESPIC_SOLVE_PCG_MG on the headline state: same start, same rho
+      deposit       fixed-point density of N index shards (all-reduced) == one rank's deposit of the gathered particles, bit for bit
+      migration     k-slab decomposition with espic_migrate for 3 steps == the single-domain run: same particle multiset, bit for bit"""
+    es, torch, dist, rank, world, dev = ctx["es"], ctx["torch"], ctx["dist"], ctx["rank"], ctx["world"], ctx["dev"]
+    out = {}
+    e, sp = head.e, head.sp
+    # ---- slab vs replicated on the live 128^3 state: perturb by one more push + deposit so both solves have work to do
+    try:
+        phi_start = e.field(es.PHI)
+        e.push(sp, DT, es.WALL_ABSORB, 0)
+        e.deposit(sp, head.dmode)
+        e.compute_charge_density()
+        i_rep = e.solve(es.SOLVE_PCG_MG, head.max_it, head.tol)
+        phi_rep = e.field(es.PHI)
+        e.set_field(es.PHI, phi_start)
+        i_slab = e.solve(es.SOLVE_PCG_MG_SLAB, head.max_it, head.tol)
+        phi_slab = e.field(es.PHI)
+        e.compute_ef()
+        rel = float(np.abs(phi_slab - phi_rep).max() / np.abs(phi_rep).max())
+        dg = [None] * world
+        dist.all_gather_object(dg, digest(phi_slab))
+        out["slab_vs_replicated"] = {"max_rel_diff_phi": rel, "newton": [i_rep["nr_iters"], i_slab["nr_iters"]],
+                                     "cg_iterations": [i_rep["lin_iters"], i_slab["lin_iters"]],
+                                     "phi_identical_on_all_ranks": len(set(dg)) == 1,
+                                     "ok": bool(rel <= 1e-10 and len(set(dg)) == 1 and i_slab["converged"] == 1 and i_rep["converged"] == 1)}
+    except Exception as ex:
+        out["slab_vs_replicated"] = {"ok": False, "error": repr(ex)}
+    # ---- small case: 33 x 33 x 65 mesh, 2e5 particles per rank
+    try:
+        ni, nj, nk, n_loc = 33, 33, 65, 200_000
+        rng = np.random.default_rng(777 + rank)
+        part = host_particles(rng, n_loc, 50.0)
+        part[5] += rng.normal(0, 3000.0, n_loc)          # fast enough that particles cross slabs within 3 steps of 2e-6
+        small_dt = 2e-6
+
+        def engine(comm):
+            g = es.Engine(ni, nj, nk, X0, XM, device=ctx["local_rank"])
+            g.add_sphere(*SPHERE)
+            g.add_inlet()
+            s = g.add_species(16 * AMU, QE, 50.0, capacity=4 * n_loc * (1 if comm else world))
+            if comm:
+                uid = [g.unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                g.comm_init(rank, world, uid[0])
+            return g, s
+
+        g, s = engine(True)
+        g.upload(s, part)
+        g.deposit(s, es.DEPOSIT_FIXED)
+        den = g.field(es.DEN, s)
+        dg = [None] * world
+        dist.all_gather_object(dg, digest(den))
+        allp = [None] * world
+        dist.all_gather_object(allp, part)
+        full = np.concatenate(allp, axis=1)
+        one, s1 = engine(False)
+        one.upload(s1, full)
+        one.deposit(s1, es.DEPOSIT_FIXED)
+        den1 = one.field(es.DEN, s1)
+        out["fixed_point_deposit"] = {"identical_on_all_ranks": len(set(dg)) == 1, "equals_single_rank_deposit_bitwise": bool(np.array_equal(den.view(np.uint64), den1.view(np.uint64))),
+                                      "ok": bool(len(set(dg)) == 1 and np.array_equal(den.view(np.uint64), den1.view(np.uint64)))}
+        g.close()
+        # migration: every rank owns a k-slab; particles start on their owner
+        kb = es.slab_bounds(nk, world)
+        dhz = (XM[2] - X0[2]) / (nk - 1)
+        kcell = np.minimum(((full[2] - X0[2]) / dhz).astype(np.int64), nk - 2)
+        mine = full[:, (kcell >= kb[rank]) & (kcell < kb[rank + 1])]
+        g, s = engine(True)
+        g.set_domain(world, rank, kb)
+        g.upload(s, np.ascontiguousarray(mine))
+        moved = 0
+        for _ in range(3):
+            g.push(s, small_dt, es.WALL_ABSORB, es.PUSH_MIGRATE)
+            moved += g.migrate(s)[0]
+            one.push(s1, small_dt, es.WALL_ABSORB, 0)
+        parts = [None] * world
+        dist.all_gather_object(parts, g.download(s))
+        union = np.concatenate(parts, axis=1)
+        ref = one.download(s1)
+
+        def canon(a):
+            return a[:, np.lexsort(a[::-1])]
+        same = union.shape == ref.shape and bool(np.array_equal(canon(union).view(np.uint64), canon(ref).view(np.uint64)))
+        mv = torch.tensor([moved], dtype=torch.float64, device=dev)
+        dist.all_reduce(mv)
+        out["migration"] = {"union_of_parts_equals_single_domain_bitwise": same, "particles": int(ref.shape[1]), "migrated_total": int(mv.item()),
+                            "ok": bool(same and mv.item() > 0)}
+        g.close()
+        one.close()
+    except Exception as ex:
+        out.setdefault("fixed_point_deposit", {"ok": False, "error": repr(ex)})
+        out.setdefault("migration", {"ok": False, "error": repr(ex)})
+    out["ok"] = all(v.get("ok", False) for v in out.values() if isinstance(v, dict))
+    return out
 
 
 def main():
@@ -303,10 +605,11 @@ def main():
                     help="N>1: spatial decomposition into k-slabs with particle migration (espic_migrate, ch9/MPI's scheme) "
                          "instead of sharding the particles by index")
     ap.add_argument("--fuse", action="store_true", help="scatter inside the push kernel instead of the tiled deposit kernel")
-    ap.add_argument("--cpu-sample", type=float, default=2e6, help="particles of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=float, default=1e7, help="particles of the reference arm's bounded sample (the in-line cpu_baseline uses at most 2e6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra QN-solver measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra records (configs[2], strong scaling, configs[4], parity check)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     ap.add_argument("--dump-warm", default=None, metavar="PATH",
                     help="after the timed region write phi of the last step and rho of the next one to PATH (.npz): the warm-started "
@@ -322,8 +625,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        return 0 if rank != 0 else reference_arm(args)
 
     import torch
     if not torch.cuda.is_available():
@@ -331,179 +634,60 @@ def main():
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world > 1 and args.impl == "ours":
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
     es = load_espic()
+    ctx = {"es": es, "torch": torch, "dist": dist, "rank": rank, "world": world, "local_rank": local_rank, "dev": dev}
     n_mesh = args.mesh
     n_local = int(args.particles)
-    n_total = n_local * (world if args.impl == "ours" else args.gpus)
-    box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
-    mpw = N0 * box_vol / n_total
-    solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "mgslab": es.SOLVE_PCG_MG_SLAB, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[args.solver]
-    if args.solver == "mgslab" and world == 1:
-        solver = es.SOLVE_PCG_MG
-    max_it, tol = 5000, 1e-4
+    n_total = n_local * world
     workload = "sphere-%d^3-mesh-%.0e-ions-per-gpu-%s" % (n_mesh, n_local, args.solver)
-
-    # ---------------------------------------------------------------- engine + warm state (untimed)
-    e = es.Engine(n_mesh, n_mesh, n_mesh, X0, XM, device=local_rank)
-    e.set_stream(torch.cuda.current_stream().cuda_stream)
-    e.add_sphere(*SPHERE)
-    e.add_inlet()
-    e.set_reference_values(PHI0, TE0, N0)
-    sp = e.add_species(16 * AMU, QE, mpw, capacity=int(n_local * 1.02) + 1024)
-    if world > 1 and args.impl == "ours":
-        uid = [e.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        e.comm_init(rank, world, uid[0])
-    n_gen = n_local if args.impl == "ours" else min(n_local, int(2e7))   # reference arm only needs a warm field
-    mpw_gen = mpw if args.impl == "ours" else N0 * box_vol / n_gen
-    decomp = args.decomp and world > 1 and args.impl == "ours"
-    if decomp and args.fuse:
-        raise SystemExit("--decomp needs the separate deposit kernel (the fused scatter would run before the migration)")
-    zrange = None
-    if decomp:
-        dhz = (XM[2] - X0[2]) / (n_mesh - 1)
-        kb = es.balanced_bounds(free_volume_per_cell_plane(n_mesh), world)     # equal particle counts, not equal node counts
-        zrange = (X0[2] + kb[rank] * dhz, X0[2] + kb[rank + 1] * dhz)
-        e.set_domain(world, rank, kb)
+    if args.decomp and world > 1:
         workload += "-kslab-migration"
-    t = make_particles_device(torch, n_gen, 12345 + rank, mpw_gen, dev, zrange)
-    e.upload_device(sp, [t[c].data_ptr() for c in range(7)], n_gen, mpw_gen)
-    e.sync()
-    del t
-    if decomp:
-        log("initial migration: sent %d, received %d" % e.migrate(sp))     # particles moved out of the sphere change slab
-    torch.cuda.empty_cache()
-    dmode = es.DEPOSIT_FIXED if args.fixed_point else es.DEPOSIT_FP64
-    pflags = (es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if args.fixed_point else 0)) if args.fuse else 0
 
-    log("particles resident: %d on rank %d" % (n_gen, rank))
-    e.sort_by_cell(sp)
-    e.deposit(sp, dmode)
-    e.compute_charge_density()
-    e.sync()
-    log("sorted + deposited")
-    e.solve(es.SOLVE_QN, 1, 1.0)                     # the reference's own initial guess (ctor -> solveQN)
-    info0 = e.solve(es.SOLVE_GS, 20000, 1e-2)        # robust nonlinear SOR to get near the solution
-    log("initial SOR: %s" % (info0,))
-    if args.solver != "qn":
-        info0 = e.solve(solver, max_it, tol)
-        log("initial %s: %s" % (args.solver, info0))
-    e.compute_ef()
-
-    def pic_step(i, count):
-        e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
-        if decomp:
-            e.migrate(sp)
-        n_live = e.count(sp)
-        if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
-            e.sort_by_cell(sp)       # between push and deposit: the scatter sees perfectly ordered particles
-        e.deposit(sp, dmode)
-        e.compute_charge_density()
-        inf = e.solve(solver, max_it, tol)
-        e.compute_ef()
-        if count is not None:
-            count.append((n_live, inf))
-
-    # ---------------------------------------------------------------- reference arm
-    if args.impl == "reference":
-        return reference_arm(args, e, es, sp, workload, n_total, mpw)
-
-    # ---------------------------------------------------------------- timed region (device resident)
+    # ---------------------------------------------------------------- headline: BASELINE configs[3], weak scaling
+    head = Case(ctx, n_mesh, n_local, n_total, args.solver, args.sort_every, args.fixed_point, args.fuse, args.decomp)
+    e, sp = head.e, head.sp
+    # warm-up first, then sample clocks over the timed steps only
     for i in range(args.warmup):
         wc = []
-        pic_step(i, wc)
+        head.step(None, wc)
         log("warm-up step %d: n=%d %s" % (i, wc[0][0], wc[0][1]))
     sampler = ClockSampler(local_rank)
     if not args.no_clocks:
         sampler.start()
         time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    push_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
-    counts = []
-    kernel_ms = []
-    migrated = []
-    launches0 = e.kernel_launches()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if args.profile_range:
-        torch.cuda.profiler.start()
-    ev0.record()
-    for i in range(args.steps):
-        pe = phase_ev[i]
-        pe[0].record()
-        n_before = e.count(sp)
-        e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
-        if decomp:
-            migrated.append(e.migrate(sp)[0])    # inside the push phase of the timed region
-        pe[1].record()
-        kernel_ms.append(e.last_push_ms())       # CUDA events around the k_push launch itself, on the launching stream
-        n_live = e.count(sp)
-        if args.sort_every > 0 and (i + args.warmup) % args.sort_every == 0 and not args.fuse:
-            e.sort_by_cell(sp)
-        pe[2].record()
-        e.deposit(sp, dmode)
-        e.compute_charge_density()
-        pe[3].record()
-        inf = e.solve(solver, max_it, tol)
-        pe[4].record()
-        e.compute_ef()
-        pe[5].record()
-        counts.append((n_before, n_live, inf))
-    ev1.record()
-    torch.cuda.synchronize()
-    if args.profile_range:
-        torch.cuda.profiler.stop()
-    if world > 1:
-        dist.barrier()
-    launches = e.kernel_launches() - launches0
+    res = head.timed(args.steps, 0, profile_range=args.profile_range)
     sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    pushed_local = sum(c[0] for c in counts)
-    if world > 1:
-        tp = torch.tensor([pushed_local], dtype=torch.float64, device=dev)
-        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
-        pushed = float(tp.item())
-    else:
-        pushed = float(pushed_local)
-    value = pushed / (ms * 1e-3)
-    log("timed region done: %.2f ms/step" % (ms / args.steps))
-    ph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in phase_ev])     # push, sort, dep+rho, solve, ef
-    ph = ph[:, [1, 0, 2, 3, 4]]
-    phase_ms = ph.mean(axis=0)
+    log("timed region done: %.2f ms/step" % res["ms_per_step"])
+    value, ms = res["value"], res["ms"]
+    pushed_local = res["pushed_local"]
 
     # dominant kernel: k_push (Species::advance).  Its duration is the mean over the timed steps of the CUDA-event time of
     # the kernel launch alone (events recorded by the library on the launching stream); the push PHASE additionally holds
     # the removal bookkeeping (popcount, scan, hole filling, one D2H count)
-    push_ms = float(phase_ms[1])
-    k_ms = float(np.mean(kernel_ms))
+    k_ms = res["kernel_ms"]
     peak, peak_src = measured_peak_gbs()
     achieved = PUSH_BYTES * (pushed_local / args.steps) / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "push_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic = tj["dram_bytes_per_particle"] * (pushed_local / args.steps)
+            traffic_note = "ncu constant (profiles/push_traffic.json: %.1f DRAM bytes per particle from one `ncu --set full` capture) x particles per launch; not measured in this run" % tj["dram_bytes_per_particle"]
         except Exception:
             traffic = None
 
     if args.dump_warm and rank == 0:
         phi_n = e.field(es.PHI)
-        e.push(sp, DT, es.WALL_ABSORB, pflags)
-        e.deposit(sp, dmode)
+        e.push(sp, DT, es.WALL_ABSORB, head.pflags)
+        e.deposit(sp, head.dmode)
         e.compute_charge_density()
         np.savez(args.dump_warm, phi=phi_n, rho_next=e.field(es.RHO), mesh=n_mesh, particles=e.count(sp))
-        inf = e.solve(solver, max_it, tol)
+        inf = e.solve(head.solver, head.max_it, head.tol)
         e.compute_ef()
         log("warm state dumped to %s (next solve: %s)" % (args.dump_warm, inf))
 
@@ -512,7 +696,7 @@ def main():
     if not args.no_e2e:
         rng = np.random.default_rng(99 + rank)
         n_inj = max(1, int(0.003 * n_local))
-        batches = [host_particles(rng, n_inj, mpw) for _ in range(2)]
+        batches = [host_particles(rng, n_inj, head.mpw) for _ in range(2)]
         pinned = [torch.from_numpy(b).pin_memory() for b in batches]
         pb = [p.numpy() for p in pinned]
         h2d = 7 * 8 * n_inj
@@ -527,7 +711,7 @@ def main():
         for i in range(args.steps):
             e.add_particles(sp, pb[i % 2], DT)                 # host -> device: this step's injected particles
             pushed_e2e += e.count(sp)
-            pic_step(i + 1, None)
+            head.step()
             dg = e.diag(sp)                                    # device -> host: the step's diagnostics ...
             phi_host = e.field(es.PHI, out=phi_pinned)         # ... and the potential (what Output::fields reads)
             d2h = dg.nbytes + phi_host.nbytes + 8
@@ -547,120 +731,127 @@ def main():
     # ---------------------------------------------------------------- the same step with ch9's own default field solver (QN)
     variants = None
     if not args.no_variants and args.solver != "qn":
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nq = max(3, min(args.steps, 5))
-        pushed_q = 0
-        v0.record()
-        for i in range(nq):
-            pushed_q += e.count(sp)
-            e.push(sp, DT, es.WALL_ABSORB, pflags | (es.PUSH_MIGRATE if decomp else 0))
-            if decomp:
-                e.migrate(sp)
-            if args.sort_every > 0 and i % args.sort_every == 0 and not args.fuse:
-                e.sort_by_cell(sp)
-            e.deposit(sp, dmode)
-            e.compute_charge_density()
-            e.solve(es.SOLVE_QN, 1, 1.0)
-            e.compute_ef()
-        v1.record()
-        torch.cuda.synchronize()
-        ms_q = v0.elapsed_time(v1)
-        if world > 1:
-            tq = torch.tensor([ms_q, pushed_q], dtype=torch.float64, device=dev)
-            mq = tq.clone()
-            dist.all_reduce(mq, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tq, op=dist.ReduceOp.SUM)
-            ms_q, pushed_q = float(mq[0].item()), float(tq[1].item())
-        variants = {"qn": {"value": pushed_q / (ms_q * 1e-3), "unit": "particle-pushes/s", "ms_per_step": ms_q / nq, "steps": nq,
+        rq = head.timed(max(3, min(args.steps, 5)), 0, solver=es.SOLVE_QN)
+        variants = {"qn": {"value": rq["value"], "unit": "particle-pushes/s", "ms_per_step": rq["ms_per_step"], "steps": rq["steps"],
                            "note": "same workload with SolverType::QN, the solver ch9/Main.cpp ships with (ch9/Main.cpp:40); "
                                    "run after the timed region, not part of `value`"}}
+
+    # ---------------------------------------------------------------- N > 1: multi-GPU correctness, executed where the driver runs
+    parity = None
+    if world > 1 and not args.no_extra and args.solver in ("mg", "mgslab") and not args.decomp:
+        parity = parity_check(ctx, head)
+        log("parity check: %s" % (parity,))
+    head.close()
+
+    # ---------------------------------------------------------------- extra records (same timing contract, fewer steps)
+    extra = {}
+    if not args.no_extra and args.mesh == 128 and args.solver == "mg" and not args.decomp:
+        ks = max(3, min(args.steps, 6))
+
+        def record(tag, mesh, n_loc, n_tot, solver_name, note):
+            try:
+                free = torch.cuda.mem_get_info(dev)[0]
+                need = 2 * 56 * n_loc * 1.03 + 40 * 8 * mesh ** 3 + (2 << 30)     # particles + sort double buffer, ~40 node arrays
+                if need > free:
+                    extra[tag] = {"skipped": "needs %.0f GB of device memory, %.0f GB free" % (need / 1e9, free / 1e9)}
+                    return
+                cs = Case(ctx, mesh, n_loc, n_tot, solver_name, args.sort_every)
+                r = cs.timed(ks, 3)
+                pk = r["kernel_ms"]
+                extra[tag] = {"value": r["value"], "unit": "particle-pushes/s", "ms_per_step": r["ms_per_step"], "steps": ks, "warmup": 3,
+                              "n_gpus": world, "mesh": [mesh] * 3, "particles_total": n_tot, "particles_per_gpu": n_loc, "solver": solver_name,
+                              "phases_ms": r["phases_ms"], "pcg_iters_per_step": r["pcg_iters_per_step"],
+                              "newton_iters_per_step": r["newton_iters_per_step"],
+                              "push_roofline_frac": PUSH_BYTES * (r["pushed_local"] / ks) / (pk * 1e-3) / 1e9 / peak if pk > 0 else None,
+                              "roofline_poisson": poisson_roofline(cs, r, peak), "note": note}
+                cs.close()
+            except Exception as ex:       # an extra record never takes the headline line down
+                extra[tag] = {"error": repr(ex)}
+            log("%s: %s" % (tag, extra[tag]))
+
+        if world == 1:
+            record("config2", 128, 50_000_000, 50_000_000, "mg", "BASELINE configs[2]: 128^3 mesh, 5e7 ions, one B200")
+        else:
+            record("strong", 128, 200_000_000 // world, 200_000_000, "mg",
+                   "BASELINE configs[3] read as strong scaling: 2e8 ions in total, sharded by index over the ranks, replicated field solve")
+        record("config5", 256, 1_000_000_000 // world, 1_000_000_000, "mgslab" if world > 1 else "mg",
+               "BASELINE configs[4]: 256^3 mesh, 1e9 ions in total (strong scaling in N); N>1: k-slab multigrid solve over peer memory, "
+               "N=1: the same solver on one GPU -- the denominator of the 8-GPU speed-up")
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline(args, e, es, sp, n_total, mpw)
+            cpu = cpu_baseline(args, n_total)
         except Exception as ex:       # the baseline is reporting, never the product
             cpu = {"value": None, "unit": "particle-pushes/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
-        lin = [c[2]["lin_iters"] for c in counts]
         out = {
             "metric": "particle-pushes/sec per full PIC step", "value": value, "unit": "particle-pushes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "mesh": [n_mesh] * 3, "particles_per_gpu": n_local, "solver": args.solver,
-                       "solver_tol": tol, "dt": DT, "sort_every": args.sort_every,
+                       "solver_tol": head.tol, "dt": DT, "sort_every": args.sort_every,
                        "deposit": "fixed-point int64" if args.fixed_point else "fp64 atomics",
                        "parallelism": "%s x%d, NCCL density all-reduce, %s" % (
-                           "k-slab spatial decomposition with particle migration (%.3g particles sent per rank per step)" % np.mean(migrated)
-                           if decomp else "particle-index sharding", world, "k-slab multigrid Poisson solve over peer memory" if (args.solver == "mgslab" and world > 1) else "replicated field solve"),
+                           "k-slab spatial decomposition with particle migration (%.3g particles sent per rank per step)" % res["migrated_per_step"]
+                           if head.decomp else "particle-index sharding", world, "k-slab multigrid Poisson solve over peer memory" if (args.solver == "mgslab" and world > 1) else "replicated field solve"),
                        "l2": "inputs (%.1f GB of particles per GPU) are larger than L2" % (56 * n_local / 1e9),
-                       "pcg_iters_per_step": float(np.mean(lin)), "newton_iters_per_step": float(np.mean([c[2]["nr_iters"] for c in counts]))},
-            "phases_ms": {"sort(amortised)": float(phase_ms[0]), "push+removal": push_ms, "deposit+rho": float(phase_ms[2]),
-                          "poisson": float(phase_ms[3]), "ef": float(phase_ms[4])},
+                       "pcg_iters_per_step": res["pcg_iters_per_step"], "newton_iters_per_step": res["newton_iters_per_step"]},
+            "phases_ms": res["phases_ms"],
             "roofline": {"bound": "hbm", "kernel": "k_push<ABSORB%s> (Species::advance: gather + leapfrog + kill flags%s)" % (
                              (",FUSE", " + fused deposit") if args.fuse else ("", "")),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "peak_source": peak_src, "bytes_per_particle": PUSH_BYTES, "kernel_ms": k_ms,
                          "particles_per_launch": pushed_local / args.steps,
                          "note": "duration = CUDA events around the kernel launch on its stream, mean over the timed steps"},
+            "roofline_poisson": poisson_roofline(head, res, peak) if args.solver in ("mg", "mgslab") else None,
             "cpu_baseline": cpu,
             "solver_variants": variants,
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": res["launches"],
             "clocks": sampler.summary(),
         }
+        if parity is not None:
+            out["parity_check"] = parity
+        out.update(extra)
         emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def sample_state(args, e, es, n_sample, mpw_full, n_full):
-    """State file for the CPU runs: the GPU engine's warm fields + an independent uniform particle sample whose weight is
-    scaled so the deposited density matches the full population."""
-    import statefile as sf
-    st = sf.State()
-    st.ni = st.nj = st.nk = args.mesh
-    st.flags = 3
-    st.x0, st.xm, st.dt = np.array(X0), np.array(XM), DT
-    st.sphere_c, st.sphere_r, st.sphere_phi = np.array(SPHERE[0]), SPHERE[1], SPHERE[2]
-    st.phi0, st.Te0, st.n0 = PHI0, TE0, N0
-    st.phi, st.rho, st.ef = e.field(es.PHI), e.field(es.RHO), e.field(es.EF)
-    st.node_vol, st.object_id = e.field(es.NODE_VOL), e.field(es.OBJECT_ID)
-    rng = np.random.default_rng(4242)
-    nn = args.mesh ** 3
-    if n_sample > 0:
-        part = host_particles(rng, n_sample, mpw_full * n_full / n_sample)
-        st.species = [dict(mass=16 * AMU, charge=QE, mpw0=part[6, 0], den=np.zeros(nn), den_ave=np.zeros(nn), part=part)]
-    return st
-
-
-def cpu_baseline(args, e, es, sp, n_total, mpw):
+def cpu_baseline(args, n_total):
+    """bounded sample of the reference on the host cores beside the GPU number (about 20-30 s)"""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_ch3")):
         return {"value": None, "unit": "particle-pushes/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
-    return reference_cpu_step(args, e, es, sp, n_total, mpw, steps=2, warmup=1, budget_s=150.0)
+    return reference_cpu_step(args.mesh, n_total, steps=2, warmup=1, n_sample=int(min(args.cpu_sample, 2e6)), gs_sweeps=10, budget_s=300.0)
 
 
-def reference_arm(args, e, es, sp, workload, n_total, mpw):
-    """--impl reference: the reference's CPU implementation of the same step on the host cores.  The GPU engine above was
-    used only to prepare the warm field state (untimed); nothing of this repo's engine is inside the timed commands."""
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the same step on the host cores.  No CUDA context, no library
+    of this repo is loaded by this process or by the binaries it runs."""
+    workload = "sphere-%d^3-mesh-%.0e-ions-per-gpu-%s" % (args.mesh, int(args.particles), args.solver)
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_ch3")):
         emit({"impl": "reference", "unavailable": "oracle/_ref/ref_ch3 was not built (needs /root/reference at build time)"})
         return 0
-    res = reference_cpu_step(args, e, es, sp, n_total, mpw, steps=args.steps, warmup=args.warmup, budget_s=240.0)
-    e.close()
+    n_total = int(args.particles) * args.gpus
+    res = reference_cpu_step(args.mesh, n_total, steps=args.steps, warmup=args.warmup, n_sample=int(args.cpu_sample), gs_sweeps=40)
     value = res["value"]
     out = {"impl": "reference", "metric": "particle-pushes/sec per full PIC step", "value": value, "unit": "particle-pushes/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_step_full_size"] * 1e3,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": None if value is None else res["s_per_step_full_size"] * 1e3,
+           "extrapolated": True, "sample_factor": res["sample_factor"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "mesh": [args.mesh] * 3, "particles_per_gpu": int(args.particles),
-                      "solver": "gs (the reference's shipped solver; its PCG diverges on this case)"},
+                      "solver": "gs (the reference's shipped solver, PotentialSolver.cpp:334-430; its Newton-PCG diverges on this case) -- "
+                                "the repo's arm solves the same equations to the same tolerance with Newton + multigrid-PCG",
+                      "same_config": "same mesh, particles, dt, equations and tolerance; different iterative solver (see DESIGN.md 7)"},
            "cpu_baseline": res,
+           "solver_variants": {"qn": dict(res["qn_step"], unit="particle-pushes/s",
+                                          note="same step with SolverType::QN (ch9/Main.cpp:40); compare with the repo arm's solver_variants.qn")},
            "e2e": {"value": value, "unit": "particle-pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)

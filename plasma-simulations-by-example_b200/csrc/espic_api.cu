@@ -128,14 +128,14 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
     CK(cudaMalloc(&c->ef4, 4 * nb));
     CK(cudaMalloc(&c->node_vol, nb));
     CK(cudaMalloc(&c->object_id, (size_t)m.nn * sizeof(int32_t)));
-    CK(cudaMalloc(&c->dscal, 64 * sizeof(unsigned long long)));
-    CK(cudaMallocHost(&c->hpin, 64 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->dscal, 128 * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&c->hpin, 128 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->phi, 0, nb, c->stream));
     CK(cudaMemsetAsync(c->rho, 0, nb, c->stream));
     CK(cudaMemsetAsync(c->ef, 0, 3 * nb, c->stream));
     CK(cudaMemsetAsync(c->ef4, 0, 4 * nb, c->stream));
     CK(cudaMemsetAsync(c->object_id, 0, (size_t)m.nn * sizeof(int32_t), c->stream));
-    CK(cudaMemsetAsync(c->dscal, 0, 64 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->dscal, 0, 128 * sizeof(unsigned long long), c->stream));
     k_node_volumes<<<nblk(m.nn, 256), 256, 0, c->stream>>>(m, c->node_vol);
     LAUNCH_CHECK(c);
     *out = c;

@@ -834,8 +834,7 @@ void espic_mg_destroy(espic_ctx *c)
     slab_destroy(c);
     if (!c->mg) return;
     MgHierarchy *H = static_cast<MgHierarchy *>(c->mg);
-    cudaFree(H->pool);
-    cudaFree(H->nbmask);
+    if (H->own_pool) cudaFree(H->pool);
     delete H;
     c->mg = nullptr;
 }

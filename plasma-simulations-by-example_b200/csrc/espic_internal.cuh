@@ -74,8 +74,8 @@ struct espic_ctx {
     uint32_t *scan_coff = nullptr; long long scan_coff_cap = 0;
     long long *lists = nullptr;    long long lists_cap = 0;   // holes | fillers
     double *red = nullptr;         long long red_cap = 0;     // reduction partials
-    unsigned long long *dscal = nullptr;                      // small device scalars (64 x 8 B)
-    void *hpin = nullptr;                                     // pinned host mirror of dscal (64 x 8 B)
+    unsigned long long *dscal = nullptr;                      // small device scalars (128 x 8 B)
+    void *hpin = nullptr;                                     // pinned host mirror of dscal (128 x 8 B)
     uint32_t *cell_cnt = nullptr;  long long cell_cap = 0;
     // solver work vectors
     double *sv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

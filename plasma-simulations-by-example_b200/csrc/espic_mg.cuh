@@ -1,66 +1,61 @@
-// espic_mg.cuh -- aggregation-multigrid preconditioned CG for the Newton systems of the Boltzmann-electron Poisson solve.
-// Textually included by espic_fields.cu (it uses StencilC, the node types and the SPD Newton kernels defined there).
+// espic_mg.cuh -- inexact Newton + aggregation-multigrid preconditioned CG for the Boltzmann-electron Poisson solve,
+// the WHOLE nonlinear solve in one persistent cooperative kernel.  Textually included by espic_fields.cu (it uses
+// StencilC, the node types and the reductions defined there).
 //
-// The reference preconditions CG with the matrix diagonal (PotentialSolver::solvePCGLinear, PotentialSolver.cpp:299-331);
-// on the 128^3 mesh that takes ~300 iterations per Newton step and is >60 % of a PIC step.  ESPIC_SOLVE_PCG_MG keeps the
-// Newton iteration, the SPD system K = -(L - diag P) on the REG nodes, the stopping tests (sqrt(sum r^2 / n) < tol for
-// CG, sqrt(sum y^2 / n) < nr_tol for Newton) and replaces only the preconditioner by one multigrid V(1,1) cycle:
-//   * coarsening by 2x2x2 aggregation of nodes, piecewise-constant prolongation P, restriction P^T, Galerkin coarse
-//     operators P^T K P -- for a 7-point stencil these are again 7-point stencils (diagonal + three link arrays);
-//   * damped-Jacobi smoothing (w = 0.9), one sweep before and one after the coarse correction; both are fused with the
-//     grid transfer (down pass: smooth from zero + residual + restriction; up pass: prolongation + smooth), so a
-//     level costs two passes and two grid-wide barriers per V-cycle;
-//   * a few Jacobi sweeps on the coarsest level.
-// The cycle is a symmetric positive definite operator (self-adjoint smoother, R = P^T), which CG requires.
-// Everything runs in ONE persistent cooperative kernel per linear solve; convergence is tested on the device.
+// The reference runs Newton-Raphson with a Jacobi-preconditioned CG per step (PotentialSolver::solveNRPCG / solvePCGLinear,
+// PotentialSolver.cpp:225-331): ~300 CG iterations per Newton step on the 128^3 mesh.  ESPIC_SOLVE_PCG_MG keeps the
+// Newton iteration on the same discrete equations (the SPD system K = -(L - diag P) on the REG nodes, espic_fields.cu) and
+// the reference's stopping tests, and changes how the work is done:
+//   * preconditioner: one multigrid V(1,1) cycle instead of the matrix diagonal (:304) -- 2x2x2 node aggregation (a
+//     direction whose spacing exceeds sqrt(2) x the smallest is not coarsened), piecewise-constant prolongation P,
+//     restriction P^T, Galerkin coarse operators (7-point again: a diagonal and three link arrays per level), damped-Jacobi
+//     smoothing (w = 0.9) fused with the grid transfers; the coarsest level (<= 4096 nodes) is solved redundantly by EVERY
+//     block in its own shared memory (no grid barrier inside it).  The cycle is a fixed SPD operator, which CG requires.
+//     Everything the preconditioner alone touches (z, the smoother's copy of the diagonal, all coarse levels) is stored in
+//     FP32: it only has to be a fixed operator close to K^-1; r, d, delta and the operator itself stay FP64.
+//   * inexact Newton: the linear solve of Newton step k stops at eta_k |R_k| with the Eisenstat-Walker forcing term
+//     eta_k = gamma (|R_k| / |R_{k-1}|)^2 (eta_0 fixed) -- every quantity comes from THIS solve, the result is a pure
+//     function of (rho, phi).  The solve ends when the reference's test holds (update norm sqrt(sum y^2 / n) < nr_tol,
+//     :282-285) AND the nonlinear residual of the equations the reference's solveGS tests (:389-421) is below tol,
+//     sqrt(sum R^2 / n) < tol (or, at the rounding floor of that residual, after a linear solve that went to tol/2): at
+//     least as strict as the reference, which stops on the update alone.
+//   * fine-level passes march along k with the column's values in registers (each vector is read once per pass, the x/y
+//     neighbours come from L1); the pre-smoothed iterate x0 = w D^-1 r and q = K d are recomputed instead of stored:
+//     96 B per node and CG iteration instead of 170.
+//   * one launch and one host synchronisation per solve (the round-1 version: 3 synchronisations per Newton step).
 #pragma once
 
 #define MG_MAX_LEVELS 8
 #define MG_OMEGA 0.9
 #define MG_COARSE_SWEEPS 6
-#define MG_COARSEST_NODES 4096      // stop coarsening once a level is this small
+#define MG_COARSEST_NODES 4096          // stop coarsening once a level is this small; it must fit 3 FP32 vectors in shared memory
 #define MG_SLAB_REDUNDANT_NODES 65536   // slab mode: levels up to this size are solved by every rank in full
+#define MG_THREADS 256                  // one 32 x 8 tile of columns per block and marching step
+#define MG_TX 32
+#define MG_TY 8
+
+typedef float mgf;                      // storage type of everything only the preconditioner reads
 
 struct MgLevel {
     int ni, nj, nk;
-    int fi, fj, fk;           // log2 of the coarsening factor from the next finer level to this one, per dimension (0 or 1):
-                              // a direction whose spacing is already > sqrt(2) x the smallest one is not coarsened (semi-
-                              // coarsening: the reference mesh has dz = 2 dx, a 4:4:1 anisotropic stencil on which point
-                              // smoothers with full coarsening converge ~1.4x slower)
+    int fi, fj, fk;           // log2 of the coarsening factor from the next finer level to this one, per dimension (0 or 1)
     long long nn;
-    double *diag, *minv;      // Galerkin diagonal and its inverse (0 on nodes without unknowns)
-    double *cx, *cy, *cz;     // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
-    double *x, *xn, *b;       // pre-smoothed iterate, post-smoothed iterate, right-hand side
+    mgf *diag, *minv;         // Galerkin diagonal and its inverse (0 on nodes without unknowns)
+    mgf *cx, *cy, *cz;        // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
+    mgf *x, *xn, *b;          // pre-smoothed iterate, post-smoothed iterate, right-hand side
 };
 
 struct MgHierarchy {
     int nlev = 0;
     MgLevel L[MG_MAX_LEVELS];
     long long geom_version = -1;
-    double *pool = nullptr;   // one allocation for all coarse-level arrays
-    uint8_t *nbmask = nullptr; // per fine node: bit b set iff neighbour b (-x,+x,-y,+y,-z,+z) is an unknown (REG)
-    // |R after the first Newton update| / |R before it| seen in the previous solve: the first linear solve of the next
-    // solve is stopped a decade below the nonlinear residual it cannot remove anyway (inexact Newton forcing term)
-    double newton_ratio = 0;
+    mgf *pool = nullptr;      // one allocation for all coarse-level arrays
+    bool own_pool = false;
 };
 
 static MgHierarchy *g_mg_of(espic_ctx *c);   // stored in the context (espic_internal.cuh: void *mg)
 
-// ---- setup kernels -------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) k_mg_nbmask(StencilC s, const uint8_t *__restrict__ type, uint8_t *__restrict__ nbmask)
-{
-    long long u = blockIdx.x * 256ll + threadIdx.x;
-    if (u >= s.nn) return;
-    unsigned m = 0;
-    if (type[u] == NT_REG) {         // REG nodes are interior: all six neighbours exist
-        m |= (type[u - 1] == NT_REG) << 0;    m |= (type[u + 1] == NT_REG) << 1;
-        m |= (type[u - s.sj] == NT_REG) << 2; m |= (type[u + s.sj] == NT_REG) << 3;
-        m |= (type[u - s.sk] == NT_REG) << 4; m |= (type[u + s.sk] == NT_REG) << 5;
-        m |= 64;                              // bit 6: the node itself is an unknown
-    }
-    nbmask[u] = (uint8_t)m;
-}
+// ---- setup kernels (geometry only: links never change with phi) --------------------------------------------------------
 
 // links of level 1 from the fine node types: a fine link (u, u+e) exists iff both ends are REG; its weight is g = 1/dh^2
 __global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const uint8_t *__restrict__ type, MgLevel C)
@@ -80,7 +75,7 @@ __global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const u
                 if (dj == C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) ly += s.gdy2;
                 if (dk == C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) lz += s.gdz2;
             }
-    C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
+    C.cx[I] = (mgf)lx; C.cy[I] = (mgf)ly; C.cz[I] = (mgf)lz;
 }
 
 // links of level l+1 from the links of level l (l >= 1)
@@ -100,58 +95,14 @@ __global__ void __launch_bounds__(256) k_mg_links_from_links(MgLevel F, MgLevel 
                 if (dj == C.fj) ly += F.cy[u];
                 if (dk == C.fk) lz += F.cz[u];
             }
-    C.cx[I] = lx; C.cy[I] = ly; C.cz[I] = lz;
-}
-
-// Galerkin diagonal of level 1: sum of the fine diagonals minus twice the fine links inside the aggregate
-__global__ void __launch_bounds__(256) k_mg_diag_from_fine(StencilC s, const uint8_t *__restrict__ type, const double *__restrict__ diagJ, MgLevel C)
-{
-    long long I = blockIdx.x * 256ll + threadIdx.x;
-    if (I >= C.nn) return;
-    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-    double d = 0;
-    for (int dk = 0; dk <= C.fk; dk++)
-        for (int dj = 0; dj <= C.fj; dj++)
-            for (int di = 0; di <= C.fi; di++) {
-                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
-                if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
-                const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
-                if (type[u] != NT_REG) continue;
-                d += diagJ[u];
-                if (di < C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
-                if (dj < C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
-                if (dk < C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
-            }
-    C.diag[I] = d;
-    C.minv[I] = d > 0 ? 1.0 / d : 0.0;
-}
-
-__global__ void __launch_bounds__(256) k_mg_diag_from_level(MgLevel F, MgLevel C)
-{
-    long long I = blockIdx.x * 256ll + threadIdx.x;
-    if (I >= C.nn) return;
-    const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-    double d = 0;
-    for (int dk = 0; dk <= C.fk; dk++)
-        for (int dj = 0; dj <= C.fj; dj++)
-            for (int di = 0; di <= C.fi; di++) {
-                const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
-                if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
-                const long long u = ((long long)k * F.nj + j) * F.ni + i;
-                d += F.diag[u];
-                if (di < C.fi && i + 1 < F.ni) d -= 2 * F.cx[u];
-                if (dj < C.fj && j + 1 < F.nj) d -= 2 * F.cy[u];
-                if (dk < C.fk && k + 1 < F.nk) d -= 2 * F.cz[u];
-            }
-    C.diag[I] = d;
-    C.minv[I] = d > 0 ? 1.0 / d : 0.0;
+    C.cx[I] = (mgf)lx; C.cy[I] = (mgf)ly; C.cz[I] = (mgf)lz;
 }
 
 // ---- who owns what: single GPU, or one k-slab per rank with peer-mapped pools -----------------------------------------
-// Every pass below is written once and instantiated twice.  `Own` tells a pass which flat index range of a level this
-// rank computes and what a store has to do besides writing locally:
+// Every pass below is written once and instantiated twice.  `Own` tells a pass which planes of a level this rank computes
+// and what a store has to do besides writing locally:
 //   OwnAll   one GPU: the whole level, plain stores, grid-wide barrier.
-//   OwnSlab  rank r of R owns planes [k0,k1) of every level (boundaries are multiples of 2^(levels-1) fine planes, so an
+//   OwnSlab  rank r of R owns planes [k0,k1) of every level (boundaries are multiples of 2^(k-coarsenings) fine planes, so an
 //            aggregate never straddles two ranks).  All solver vectors live at the same offset of a pool that every rank
 //            maps from every other rank (CUDA IPC over NVLink).  A value written on the first / last plane of the slab is
 //            ALSO stored straight into the lower / upper neighbour's copy (peer store fused into the producing pass: the
@@ -159,53 +110,68 @@ __global__ void __launch_bounds__(256) k_mg_diag_from_level(MgLevel F, MgLevel C
 //            ranks add the same numbers in the same order; the barrier is a grid barrier plus one flag per peer.
 struct OwnAll {
     static constexpr bool slab = false;
+    __device__ __forceinline__ int klo(const MgLevel &, int) const { return 0; }
+    __device__ __forceinline__ int khi(const MgLevel &L, int) const { return L.nk; }
     __device__ __forceinline__ long long lo(const MgLevel &L, int) const { return 0; }
     __device__ __forceinline__ long long hi(const MgLevel &L, int) const { return L.nn; }
-    __device__ __forceinline__ void st(double *A, long long u, const MgLevel &, int, double v) const { A[u] = v; }
-    __device__ __forceinline__ void st_all(double *A, long long u, double v) const { A[u] = v; }
+    template <typename T> __device__ __forceinline__ void st(T *A, long long u, const MgLevel &, int, T v) const { A[u] = v; }
+    template <typename T> __device__ __forceinline__ void st_all(T *A, long long u, T v) const { A[u] = v; }
     __device__ __forceinline__ int nparts(int nb) const { return nb; }
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const { base[blockIdx.x] = v; }
-    __device__ __forceinline__ void barrier(cg::grid_group &grid) { grid.sync(); }
+    __device__ __forceinline__ bool barrier(cg::grid_group &grid) { grid.sync(); return true; }
+    __device__ __forceinline__ bool lbarrier(cg::grid_group &grid) { grid.sync(); return true; }
 };
 
 #define MG_MAX_RANKS 8
+// A barrier that waits longer than this many polls (~ seconds) gives up: it raises the abort word on every rank, every
+// later barrier returns at once and the kernel unwinds with an error code instead of hanging 8 GPUs on one faulted peer.
+#define MG_SPIN_BUDGET (1ull << 31)
 struct OwnSlab {
     static constexpr bool slab = true;
     int rank, nranks;
     int k0[MG_MAX_LEVELS], k1[MG_MAX_LEVELS];
     long long peer[MG_MAX_RANKS];        // byte distance from an address in this rank's pool to the same address in rank p's pool
     unsigned long long *flags;           // in the pool: flags[p] = last barrier epoch rank p has reached (written by rank p)
+    unsigned long long *abort_word;      // in the pool: non-zero once any rank gave up waiting (written by that rank to every pool)
     unsigned long long epoch;            // barriers passed so far (identical on every rank)
+    unsigned long long *arrive, *release;     // in the local pool
+    unsigned long long *larrive, *lrelease;   // the same pair for the barrier among this rank's blocks only
+    unsigned long long lepoch;
+    __device__ __forceinline__ int klo(const MgLevel &, int l) const { return k0[l]; }
+    __device__ __forceinline__ int khi(const MgLevel &, int l) const { return k1[l]; }
     __device__ __forceinline__ long long lo(const MgLevel &L, int l) const { return (long long)k0[l] * L.ni * L.nj; }
     __device__ __forceinline__ long long hi(const MgLevel &L, int l) const { return (long long)k1[l] * L.ni * L.nj; }
-    __device__ __forceinline__ void st(double *A, long long u, const MgLevel &L, int l, double v) const
+    template <typename T> __device__ __forceinline__ T *at(T *p, int r) const
+    {
+        return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + peer[r]);
+    }
+    template <typename T> __device__ __forceinline__ void st(T *A, long long u, const MgLevel &L, int l, T v) const
     {
         A[u] = v;
         const long long plane = (long long)L.ni * L.nj;
-        if (rank > 0 && u < lo(L, l) + plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank - 1]) = v;
-        if (rank + 1 < nranks && u >= hi(L, l) - plane) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[rank + 1]) = v;
+        if (rank > 0 && u < lo(L, l) + plane) *at(A + u, rank - 1) = v;
+        if (rank + 1 < nranks && u >= hi(L, l) - plane) *at(A + u, rank + 1) = v;
     }
-    // store into every rank's copy (the right-hand side of the coarsest level: that level is solved by every rank in full)
-    __device__ __forceinline__ void st_all(double *A, long long u, double v) const
+    // store into every rank's copy (the right-hand side of the first level that every rank solves in full)
+    template <typename T> __device__ __forceinline__ void st_all(T *A, long long u, T v) const
     {
-        for (int p = 0; p < nranks; p++) *reinterpret_cast<double *>(reinterpret_cast<char *>(A + u) + peer[p]) = v;
+        for (int p = 0; p < nranks; p++) *at(A + u, p) = v;
     }
     __device__ __forceinline__ int nparts(int nb) const { return nb * nranks; }
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const
     {
-        for (int p = 0; p < nranks; p++)
-            *reinterpret_cast<double *>(reinterpret_cast<char *>(base + rank * nb + blockIdx.x) + peer[p]) = v;
+        for (int p = 0; p < nranks; p++) *at(base + rank * nb + blockIdx.x, p) = v;
     }
     // All blocks of all ranks.  Local arrival (one atomic per block on a cumulative counter), then block 0 exchanges one
     // flag with every peer over NVLink, then it releases the local blocks: one local round trip plus one remote one.
     // Ordering: every block's thread 0 issues a system-scope fence after the block barrier and before arriving, block 0
     // fences again (system scope) between seeing all arrivals and signalling the peers, so a peer that sees the flag also
-    // sees every halo value and partial sum stored before this barrier.
-    unsigned long long *arrive, *release;     // in the local pool
-    __device__ __forceinline__ void barrier(cg::grid_group &)
+    // sees every halo value and partial sum stored before this barrier.  Returns false once the abort word is up.
+    __device__ __forceinline__ bool barrier(cg::grid_group &)
     {
         __syncthreads();
         epoch++;
+        volatile unsigned long long *ab = abort_word;
         if (blockIdx.x == 0) {
             if (threadIdx.x < 32) {          // first warp: lane 0 collects the local arrivals, lane p talks to peer p
                 const int lane = threadIdx.x;
@@ -213,14 +179,21 @@ struct OwnSlab {
                     __threadfence_system();
                     volatile unsigned long long *arr = arrive;
                     const unsigned long long want = (unsigned long long)(gridDim.x - 1) * epoch;
-                    while (*arr < want) { }
+                    unsigned long long spins = 0;
+                    while (*arr < want && !*ab) { if (++spins > MG_SPIN_BUDGET) break; }
                     __threadfence_system();
                 }
                 __syncwarp();
                 if (lane < nranks) {
-                    *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(flags + rank) + peer[lane]) = epoch;
+                    *reinterpret_cast<volatile unsigned long long *>(at(flags + rank, lane)) = epoch;
                     volatile unsigned long long *mine = flags + lane;
-                    while (*mine < epoch) { }
+                    unsigned long long spins = 0;
+                    while (*mine < epoch && !*ab) {
+                        if (++spins > MG_SPIN_BUDGET) {          // a peer never arrived: tell everybody and give up
+                            for (int p = 0; p < nranks; p++) *reinterpret_cast<volatile unsigned long long *>(at(abort_word, p)) = epoch;
+                            break;
+                        }
+                    }
                     __threadfence_system();
                 }
                 __syncwarp();
@@ -234,70 +207,57 @@ struct OwnSlab {
             __threadfence_system();
             atomicAdd(arrive, 1ull);
             volatile unsigned long long *rel = release;
-            while (*rel < epoch) { }
+            while (*rel < epoch && !*ab) { }
             __threadfence();
         }
         __syncthreads();
+        return *ab == 0;
+    }
+    // the blocks of THIS rank only (levels every rank solves in full): same arrive / release scheme without the peer exchange
+    __device__ __forceinline__ bool lbarrier(cg::grid_group &)
+    {
+        __syncthreads();
+        lepoch++;
+        volatile unsigned long long *ab = abort_word;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            volatile unsigned long long *rel = lrelease;
+            if (blockIdx.x == 0) {
+                volatile unsigned long long *arr = larrive;
+                const unsigned long long want = (unsigned long long)(gridDim.x - 1) * lepoch;
+                while (*arr < want && !*ab) { }
+                __threadfence();
+                *rel = lepoch;
+            } else {
+                atomicAdd(larrive, 1ull);
+                while (*rel < lepoch && !*ab) { }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        return *ab == 0;
     }
 };
 
-// ---- device pieces of the V-cycle (grid-stride; the caller separates them with barriers) ---------------------------------
+// ---- coarse-level passes (grid-stride; the caller separates them with barriers) --------------------------------------
+// The coarse levels are small: what matters there is the length of the dependent-load chain of a thread, not bandwidth.
+// The passes spread one node over 8 consecutive lanes (the 8 children of an aggregate, or the 7 stencil terms of a node)
+// and combine with three shuffles; the sum order is fixed, so results are reproducible.
 
-// off-diagonal part of K v at fine node u (level 0): neighbours outside the REG set carry v == 0
-__device__ __forceinline__ double mg_offdiag0(const StencilC &s, const double *__restrict__ v, long long u)
-{
-    return s.gdx2 * (v[u - 1] + v[u + 1]) + s.gdy2 * (v[u - s.sj] + v[u + s.sj]) + s.gdz2 * (v[u - s.sk] + v[u + s.sk]);
-}
-
-// sum over neighbours of link * f(neighbour) on a coarse level, f given as a functor of the neighbour's flat index
 template <typename F>
 __device__ __forceinline__ double mg_offdiag(const MgLevel &L, int i, int j, int k, long long u, F f)
 {
     const long long sj = L.ni, sk = (long long)L.ni * L.nj;
     double a = 0;
-    if (i > 0) a += L.cx[u - 1] * f(u - 1);
-    if (i + 1 < L.ni) a += L.cx[u] * f(u + 1);
-    if (j > 0) a += L.cy[u - sj] * f(u - sj);
-    if (j + 1 < L.nj) a += L.cy[u] * f(u + sj);
-    if (k > 0) a += L.cz[u - sk] * f(u - sk);
-    if (k + 1 < L.nk) a += L.cz[u] * f(u + sk);
+    if (i > 0) a += (double)L.cx[u - 1] * f(u - 1);
+    if (i + 1 < L.ni) a += (double)L.cx[u] * f(u + 1);
+    if (j > 0) a += (double)L.cy[u - sj] * f(u - sj);
+    if (j + 1 < L.nj) a += (double)L.cy[u] * f(u + sj);
+    if (k > 0) a += (double)L.cz[u - sk] * f(u - sk);
+    if (k + 1 < L.nk) a += (double)L.cz[u] * f(u + sk);
     return a;
 }
 
-// Down pass from the fine level: x0 = w D^-1 r is already stored (written together with r); the residual r - K x0 is
-// summed over each aggregate -> b of level 1.  One thread per COARSE node (it owns the 8 children).
-template <class Own>
-__device__ __forceinline__ void mg_down0(const Own &own, const StencilC &s, const double *__restrict__ r,
-                                         const double *__restrict__ diag, const double *__restrict__ x0, const MgLevel &C,
-                                         long long t0, long long stride, bool to_all)
-{
-    for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
-        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-        double sum = 0;
-        if (C.minv[I] != 0) {
-#pragma unroll
-            for (int dk = 0; dk < 2; dk++)
-#pragma unroll
-                for (int dj = 0; dj < 2; dj++)
-#pragma unroll
-                    for (int di = 0; di < 2; di++) {
-                        if (di > C.fi || dj > C.fj || dk > C.fk) continue;
-                        const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
-                        if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
-                        const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
-                        const double dg = diag[u];
-                        if (dg == 0) continue;                 // not an unknown
-                        sum += r[u] - (dg * x0[u] - mg_offdiag0(s, x0, u));
-                    }
-        }
-        if (to_all) own.st_all(C.b, I, sum);
-        else own.st(C.b, I, C, 1, sum);
-    }
-}
-
-// The coarse levels are small: what matters there is the length of the dependent-load chain of a thread, not bandwidth.
-// All coarse passes therefore spread one node over 8 consecutive lanes (the 8 children of an aggregate, or the 7 stencil
-// terms of a node) and combine with three shuffles; the sum order is fixed, so results are reproducible.
 __device__ __forceinline__ double mg_sum8(double v)
 {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -306,7 +266,8 @@ __device__ __forceinline__ double mg_sum8(double v)
     return v;
 }
 
-// Down pass between coarse levels F (level lf) -> C: lane c of a group handles child c of coarse node I
+// Down pass between coarse levels F (level lf) -> C: x_F = w D^-1 b_F (smoothing from zero), residual b_F - K x_F summed
+// over each aggregate -> b_C.  Lane c of a group of 8 handles child c of coarse node I.
 template <class Own>
 __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf, const MgLevel &C, long long t0, long long stride,
                                         bool to_all)
@@ -326,17 +287,18 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
                 const double mi = F.minv[u];
                 double xu = 0;
                 if (mi != 0) {
-                    xu = MG_OMEGA * F.b[u] * mi;
-                    const double off = MG_OMEGA * mg_offdiag(F, i, j, k, u, [&](long long v) { return F.b[v] * F.minv[v]; });
-                    res = F.b[u] - (F.diag[u] * xu - off);
+                    const double bu = F.b[u];
+                    xu = MG_OMEGA * bu * mi;
+                    const double off = MG_OMEGA * mg_offdiag(F, i, j, k, u, [&](long long v) { return (double)F.b[v] * (double)F.minv[v]; });
+                    res = bu - ((double)F.diag[u] * xu - off);
                 }
-                own.st(F.x, u, F, lf, xu);
+                own.st(F.x, u, F, lf, (mgf)xu);
             }
         }
         res = mg_sum8(res);
         if (c == 0 && live) {
-            if (to_all) own.st_all(C.b, I, res);
-            else own.st(C.b, I, C, lf + 1, res);
+            if (to_all) own.st_all(C.b, I, (mgf)res);
+            else own.st(C.b, I, C, lf + 1, (mgf)res);
         }
     }
 }
@@ -347,51 +309,27 @@ __device__ __forceinline__ double mg_term(const MgLevel &L, int c, int i, int j,
 {
     const long long sj = L.ni, sk = (long long)L.ni * L.nj;
     switch (c) {
-        case 0: centre = val(u, i, j, k); return L.b[u] - L.diag[u] * centre;
-        case 1: return i > 0 ? L.cx[u - 1] * val(u - 1, i - 1, j, k) : 0.0;
-        case 2: return i + 1 < L.ni ? L.cx[u] * val(u + 1, i + 1, j, k) : 0.0;
-        case 3: return j > 0 ? L.cy[u - sj] * val(u - sj, i, j - 1, k) : 0.0;
-        case 4: return j + 1 < L.nj ? L.cy[u] * val(u + sj, i, j + 1, k) : 0.0;
-        case 5: return k > 0 ? L.cz[u - sk] * val(u - sk, i, j, k - 1) : 0.0;
-        case 6: return k + 1 < L.nk ? L.cz[u] * val(u + sk, i, j, k + 1) : 0.0;
+        case 0: centre = val(u, i, j, k); return (double)L.b[u] - (double)L.diag[u] * centre;
+        case 1: return i > 0 ? (double)L.cx[u - 1] * val(u - 1, i - 1, j, k) : 0.0;
+        case 2: return i + 1 < L.ni ? (double)L.cx[u] * val(u + 1, i + 1, j, k) : 0.0;
+        case 3: return j > 0 ? (double)L.cy[u - sj] * val(u - sj, i, j - 1, k) : 0.0;
+        case 4: return j + 1 < L.nj ? (double)L.cy[u] * val(u + sj, i, j + 1, k) : 0.0;
+        case 5: return k > 0 ? (double)L.cz[u - sk] * val(u - sk, i, j, k - 1) : 0.0;
+        case 6: return k + 1 < L.nk ? (double)L.cz[u] * val(u + sk, i, j, k + 1) : 0.0;
         default: return 0.0;
-    }
-}
-
-// one damped-Jacobi sweep on level L (index l): out = in + w D^-1 (b - K in); 8 lanes per node
-template <class Own>
-__device__ __forceinline__ void mg_jacobi(const Own &own, const MgLevel &L, int l, const double *__restrict__ in,
-                                          double *__restrict__ out, long long t0, long long stride)
-{
-    const long long first = own.lo(L, l), total = (own.hi(L, l) - first) * 8;
-    for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long u = first + (w >> 3);
-        const int c = (int)(w & 7);
-        const bool live = w < total;
-        double term = 0, centre = 0, mi = 0;
-        if (live) {
-            mi = L.minv[u];
-            if (mi != 0) {
-                const int i = (int)(u % L.ni), j = (int)((u / L.ni) % L.nj), k = (int)(u / ((long long)L.ni * L.nj));
-                term = mg_term(L, c, i, j, k, u, [&](long long v, int, int, int) { return in[v]; }, centre);
-            }
-        }
-        const double tot = mg_sum8(term);
-        centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        if (c == 0 && live) own.st(out, u, L, l, (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0);
     }
 }
 
 // Up pass on a coarse level F (index lf) with the correction e of the next coarser level C:
 //   xn = (x + P e) + w D^-1 (b - K (x + P e))
 template <class Own>
-__device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, const MgLevel &C, const double *__restrict__ e,
+__device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, const MgLevel &C, const mgf *e,
                                       long long t0, long long stride)
 {
     const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
     auto val = [&](long long v, int vi, int vj, int vk) {
         // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
-        return F.x[v] + e[((long long)(vk >> C.fk) * C.nj + (vj >> C.fj)) * C.ni + (vi >> C.fi)];
+        return (double)F.x[v] + (double)e[((long long)(vk >> C.fk) * C.nj + (vj >> C.fj)) * C.ni + (vi >> C.fi)];
     };
     if (count * 2 > stride) {          // a big level: one thread per node keeps every lane busy
         for (long long u = first + t0; u < first + count; u += stride) {
@@ -404,7 +342,7 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
                 for (int c = 0; c < 7; c++) tot += mg_term(F, c, i, j, k, u, val, centre);
                 out = centre + MG_OMEGA * mi * tot;
             }
-            own.st(F.xn, u, F, lf, out);
+            own.st(F.xn, u, F, lf, (mgf)out);
         }
         return;
     }
@@ -423,73 +361,125 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
         }
         const double tot = mg_sum8(term);
         centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        if (c == 0 && live) own.st(F.xn, u, F, lf, (mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0);
+        if (c == 0 && live) own.st(F.xn, u, F, lf, (mgf)((mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0));
     }
 }
 
-// Up pass on the fine level: z = (x0 + P e) + w D^-1 (r - K (x0 + P e)).  One thread per level-1 node: it holds the
-// correction of its own aggregate and of the six neighbouring aggregates in registers and walks its 8 children, so the
-// prolongated iterate never touches memory; nbmask replaces six mask loads per node.  Returns the thread's share of r.z
-template <class Own>
-__device__ __forceinline__ double mg_up0(const Own &own, const StencilC &s, const MgLevel &L0, const double *__restrict__ r,
-                                         const double *__restrict__ diag, const double *__restrict__ minv,
-                                         const double *__restrict__ x0, const uint8_t *__restrict__ nbmask, const MgLevel &C,
-                                         const double *__restrict__ e, double *__restrict__ z, long long t0, long long stride)
+// The coarsest level, solved by every block on its own in shared memory: x = w D^-1 b, then `sweeps` damped-Jacobi sweeps.
+// Identical arithmetic in every block (and on every rank): identical result everywhere, no grid barrier.  Returns the
+// shared-memory array that holds the solution.  Ends with a __syncthreads.
+__device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, mgf *smem)
 {
-    double acc = 0;
-    const long long csj = C.ni, csk = (long long)C.ni * C.nj;
+    const int n = (int)L.nn;
+    mgf *sb = smem, *sx = smem + n, *sy = smem + 2 * n;
+    for (int u = threadIdx.x; u < n; u += blockDim.x) {
+        const mgf b = L.b[u];
+        sb[u] = b;
+        sx[u] = (mgf)(MG_OMEGA * (double)b * (double)L.minv[u]);
+    }
+    __syncthreads();
+    const int sj = L.ni, sk = L.ni * L.nj;
+    for (int sweep = 0; sweep < sweeps; sweep++) {
+        for (int u = threadIdx.x; u < n; u += blockDim.x) {
+            const double mi = L.minv[u];
+            double out = 0;
+            if (mi != 0) {
+                const int i = u % L.ni, j = (u / L.ni) % L.nj, k = u / sk;
+                const double xc = sx[u];
+                double t = (double)sb[u] - (double)L.diag[u] * xc;
+                if (i > 0) t += (double)L.cx[u - 1] * (double)sx[u - 1];
+                if (i + 1 < L.ni) t += (double)L.cx[u] * (double)sx[u + 1];
+                if (j > 0) t += (double)L.cy[u - sj] * (double)sx[u - sj];
+                if (j + 1 < L.nj) t += (double)L.cy[u] * (double)sx[u + sj];
+                if (k > 0) t += (double)L.cz[u - sk] * (double)sx[u - sk];
+                if (k + 1 < L.nk) t += (double)L.cz[u] * (double)sx[u + sk];
+                out = xc + MG_OMEGA * mi * t;
+            }
+            sy[u] = (mgf)out;
+        }
+        __syncthreads();
+        mgf *tmp = sx; sx = sy; sy = tmp;
+    }
+    return sx;
+}
+
+// ---- Galerkin diagonals (the Boltzmann term changes with phi every Newton step; the links do not) ---------------------
+
+// level 1 from the fine diagonal: sum of the children's diagonals minus twice the fine links inside the aggregate
+template <class Own>
+__device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, const uint8_t *__restrict__ type, const mgf *diagf,
+                                         const MgLevel &C, long long t0, long long stride, bool to_all)
+{
     for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
-        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / csk);
-        const double e0 = e[I];
-        const double exm = ci > 0 ? e[I - 1] : 0.0, exp_ = ci + 1 < C.ni ? e[I + 1] : 0.0;
-        const double eym = cj > 0 ? e[I - csj] : 0.0, eyp = cj + 1 < C.nj ? e[I + csj] : 0.0;
-        const double ezm = ck > 0 ? e[I - csk] : 0.0, ezp = ck + 1 < C.nk ? e[I + csk] : 0.0;
-#pragma unroll
-        for (int dk = 0; dk < 2; dk++)
-#pragma unroll
-            for (int dj = 0; dj < 2; dj++)
-#pragma unroll
-                for (int di = 0; di < 2; di++) {
-                    if (di > C.fi || dj > C.fj || dk > C.fk) continue;
+        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+        double d = 0;
+        for (int dk = 0; dk <= C.fk; dk++)
+            for (int dj = 0; dj <= C.fj; dj++)
+                for (int di = 0; di <= C.fi; di++) {
                     const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                     if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                     const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
-                    const unsigned m = nbmask[u];
-                    double zu = 0;
-                    if (m & 64u) {
-                        // the neighbour on the inner side of the aggregate shares e0, the outer one takes the next aggregate's
-                        const double vxm = (m & 1u) ? x0[u - 1] + (di > 0 ? e0 : exm) : 0.0;
-                        const double vxp = (m & 2u) ? x0[u + 1] + (di < C.fi ? e0 : exp_) : 0.0;
-                        const double vym = (m & 4u) ? x0[u - s.sj] + (dj > 0 ? e0 : eym) : 0.0;
-                        const double vyp = (m & 8u) ? x0[u + s.sj] + (dj < C.fj ? e0 : eyp) : 0.0;
-                        const double vzm = (m & 16u) ? x0[u - s.sk] + (dk > 0 ? e0 : ezm) : 0.0;
-                        const double vzp = (m & 32u) ? x0[u + s.sk] + (dk < C.fk ? e0 : ezp) : 0.0;
-                        const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
-                        const double xu = x0[u] + e0;
-                        zu = xu + MG_OMEGA * minv[u] * (r[u] - (diag[u] * xu - off));
-                        acc += r[u] * zu;
-                    }
-                    own.st(z, u, L0, 0, zu);
+                    if (type[u] != NT_REG) continue;
+                    d += (double)diagf[u];
+                    if (di < C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
+                    if (dj < C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
+                    if (dk < C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
                 }
+        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0;
+        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); }
+        else { own.st(C.diag, I, C, 1, df); own.st(C.minv, I, C, 1, mi); }
     }
-    return acc;
 }
 
-struct MgPcgArgs {
+template <class Own>
+__device__ __forceinline__ void mg_diagl(const Own &own, const MgLevel &F, const MgLevel &C, int lc, long long t0, long long stride,
+                                         bool to_all)
+{
+    for (long long I = own.lo(C, lc) + t0; I < own.hi(C, lc); I += stride) {
+        const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+        double d = 0;
+        for (int dk = 0; dk <= C.fk; dk++)
+            for (int dj = 0; dj <= C.fj; dj++)
+                for (int di = 0; di <= C.fi; di++) {
+                    const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
+                    if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
+                    const long long u = ((long long)k * F.nj + j) * F.ni + i;
+                    d += (double)F.diag[u];
+                    if (di < C.fi && i + 1 < F.ni) d -= 2 * (double)F.cx[u];
+                    if (dj < C.fj && j + 1 < F.nj) d -= 2 * (double)F.cy[u];
+                    if (dk < C.fk && k + 1 < F.nk) d -= 2 * (double)F.cz[u];
+                }
+        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0;
+        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); }
+        else { own.st(C.diag, I, C, lc, df); own.st(C.minv, I, C, lc, mi); }
+    }
+}
+
+// ---- the kernel's arguments ------------------------------------------------------------------------------------------
+
+struct MgnArgs {
     StencilC s;
     int nlev;
-    int coarse_sweeps;            // Jacobi sweeps on the coarsest level (even)
+    int coarse_sweeps;            // Jacobi sweeps on the coarsest level
     int first_redundant;          // slab mode: first level that every rank solves in full (<= nlev-1, >= 1); unused on one GPU
-    MgLevel L[MG_MAX_LEVELS];     // L[0]: dims, diag = diagJ, minv, x = x0 (= w D^-1 r, kept current with r); links unused
-    const uint8_t *nbmask;
-    double *delta, *r, *z, *d0, *d1, *q;     // r enters holding the right-hand side; d0/d1 ping-pong search directions
-    double *part;
-    int max_it;
-    double tol;
-    double rel_tol;               // stop at l2 < max(tol, rel_tol * l2_start)
-    double *out;                  // converged, iterations, l2, l2 at the start
-    unsigned long long *prof;     // optional: nanoseconds per phase as seen by block 0 (ESPIC_MG_PROFILE=1), 8 slots
+    MgLevel L[MG_MAX_LEVELS];     // L[0]: dimensions only
+    const uint8_t *type;
+    const double *rho;
+    double *phi;                  // the potential the kernel works on (slab mode: the pool copy, halos kept current by peer stores)
+    double *phi_user;             // slab mode: the context's phi (read at the start, this rank's slab written at the end); else == phi
+    mgf *diagf;                   // Jacobian diagonal as the smoother and the operator use it (FP32 storage)
+    mgf *z;
+    double *r, *d0, *d1, *delta;
+    double *part;                 // 3 x nparts partial sums
+    double phi0, Te0, n0;
+    int max_it, nr_max_it;
+    double tol, nr_tol;
+    double eta0, eta_max, gamma;  // forcing: eta_0, then min(eta_max, gamma (|R_k|/|R_k-1|)^2)
+    double *out;                  // see MGN_OUT_*
+    unsigned long long *prof;     // optional: nanoseconds per phase as seen by block 0 (ESPIC_MG_PROFILE=1), 16 slots
 };
+enum { MGN_OUT_CONVERGED = 0, MGN_OUT_NEWTON = 1, MGN_OUT_LIN = 2, MGN_OUT_YNORM = 3, MGN_OUT_RNORM = 4, MGN_OUT_RNORM0 = 5,
+       MGN_OUT_LINFAIL = 6, MGN_OUT_LINL2 = 7, MGN_OUT_ABORT = 8, MGN_OUT_HIST = 9 /* then (|R|, its) per Newton step, up to 10 */ };
 
 __device__ __forceinline__ unsigned long long mg_now()
 {
@@ -497,70 +487,290 @@ __device__ __forceinline__ unsigned long long mg_now()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// phase ids: 0 down0, 1 coarser down passes, 2 coarsest sweeps, 3 coarse up passes, 4 up0 + r.z, 5 d/q pass, 6 r pass
+// phase ids: 0 down0, 1 coarser down passes, 2 coarsest, 3 coarse up passes, 4 up0 + r.z, 5 d pass, 6 r pass, 7 linearise,
+// 8 Galerkin diagonals, 9 update
 #define MG_TICK(id) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = mg_now(); a.prof[id] += n_ - tick; tick = n_; } } while (0)
 
-// z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.
+// ---- fine-level passes: marching along k -----------------------------------------------------------------------------
+// The owned planes of the fine level are cut into 32 x 8 tiles of columns; the work list is (tile, plane unit) with the
+// plane unit fastest, and block b takes the b-th of gridDim equal contiguous pieces of it: a run of consecutive planes of
+// one tile (possibly continuing in the next tile).  Along a run a thread keeps its column's values of planes k-1, k, k+1 in
+// registers, so every vector is read from L2/HBM once per pass (plus two halo planes per run); the x/y neighbours are
+// adjacent lanes' lines in L1.  A plane unit is 2^fk planes of level 1, so a thread finishes whole aggregates.
+// Lane layout inside a tile: a warp covers 16 (i) x 2 (j) columns -> the x partner of an aggregate is lane^1, the y partner
+// lane^16, and a warp reads two 128-byte rows per load.
+
+struct MgCol {
+    int i, j;
+    bool inmesh;      // the column exists
+    bool inner;       // 1 <= i <= ni-2 and 1 <= j <= nj-2: REG nodes only live here, every x/y neighbour exists
+    long long base;   // j*sj + i
+};
+
+struct MgRuns {
+    int ntx, nty, kunit, klo, khi;
+    long long nku, first, last;      // plane units per tile; this block's piece [first, last) of the flattened (tile, unit) list
+};
+
 template <class Own>
-__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, const MgPcgArgs &a, long long t0, long long stride,
-                                            unsigned long long &tick)
+__device__ __forceinline__ MgRuns mg_runs(const Own &own, const MgnArgs &a)
 {
+    MgRuns R;
+    R.ntx = (a.s.ni + MG_TX - 1) / MG_TX;
+    R.nty = (a.s.nj + MG_TY - 1) / MG_TY;
+    R.kunit = a.nlev > 1 ? (1 << a.L[1].fk) : 1;
+    R.klo = own.klo(a.L[0], 0);
+    R.khi = own.khi(a.L[0], 0);
+    R.nku = (R.khi - R.klo + R.kunit - 1) / R.kunit;
+    const long long total = (long long)R.ntx * R.nty * R.nku;
+    R.first = total * blockIdx.x / gridDim.x;
+    R.last = total * (blockIdx.x + 1) / gridDim.x;
+    return R;
+}
+
+__device__ __forceinline__ MgCol mg_col(const StencilC &s, const MgRuns &R, long long tile)
+{
+    const int tx = (int)(tile % R.ntx), ty = (int)(tile / R.ntx);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    MgCol c;
+    c.i = tx * MG_TX + (w & 1) * 16 + (l & 15);
+    c.j = ty * MG_TY + (w >> 1) * 2 + (l >> 4);
+    c.inmesh = c.i < s.ni && c.j < s.nj;
+    c.inner = c.i >= 1 && c.i <= s.ni - 2 && c.j >= 1 && c.j <= s.nj - 2;
+    c.base = (long long)c.j * s.sj + c.i;
+    return c;
+}
+
+// x0 = w D^-1 r with the smoother's FP32 diagonal (0 where the node is not an unknown)
+__device__ __forceinline__ double mg_x0(double r, mgf dg)
+{
+    return dg != (mgf)0 ? MG_OMEGA * r * (double)__frcp_rn(dg) : 0.0;
+}
+
+// calls f(column, kbeg, kend) for every run of this block
+template <typename F>
+__device__ __forceinline__ void mg_for_runs(const StencilC &s, const MgRuns &R, F f)
+{
+    for (long long pos = R.first; pos < R.last;) {
+        const long long tile = pos / R.nku, ku = pos % R.nku;
+        const long long nrun = min(R.last - pos, R.nku - ku);
+        const int kbeg = R.klo + (int)ku * R.kunit, kend = min(R.khi, kbeg + (int)nrun * R.kunit);
+        f(mg_col(s, R, tile), kbeg, kend);
+        pos += nrun;
+    }
+}
+
+// Pass A (down, fine -> level 1): residual of the pre-smoothed iterate x0 = w D^-1 r, summed over each aggregate -> b of level 1
+template <class Own>
+__device__ __forceinline__ void mg_fine_down(const Own &own, const MgnArgs &a, const MgRuns &R, bool to_all)
+{
+    const StencilC &s = a.s;
+    const MgLevel &C = a.L[1];
+    const int lane = threadIdx.x & 31;
+    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
+        const bool act = col.inner;                 // boundary and outside columns hold no unknowns: they only take part in the shuffles
+        long long u = col.base + (long long)kbeg * s.sk;
+        double x0m = 0, x0c = 0, x0p = 0, rc = 0;
+        mgf dgc = 0;
+        if (act) {
+            if (kbeg >= 1) x0m = mg_x0(a.r[u - s.sk], a.diagf[u - s.sk]);
+            rc = a.r[u]; dgc = a.diagf[u];
+            x0c = mg_x0(rc, dgc);
+        }
+        double sum = 0;
+        for (int k = kbeg; k < kend; k++, u += s.sk) {
+            double rp = 0; mgf dgp = 0;
+            if (act && k + 1 < s.nk) { rp = a.r[u + s.sk]; dgp = a.diagf[u + s.sk]; }
+            x0p = mg_x0(rp, dgp);
+            if (act && dgc != (mgf)0) {
+                const double xxm = mg_x0(a.r[u - 1], a.diagf[u - 1]), xxp = mg_x0(a.r[u + 1], a.diagf[u + 1]);
+                const double xym = mg_x0(a.r[u - s.sj], a.diagf[u - s.sj]), xyp = mg_x0(a.r[u + s.sj], a.diagf[u + s.sj]);
+                const double off = s.gdx2 * (xxm + xxp) + s.gdy2 * (xym + xyp) + s.gdz2 * (x0m + x0p);
+                sum += rc - ((double)dgc * x0c - off);
+            }
+            if (((k + 1) & (R.kunit - 1)) == 0 || k + 1 == s.nk) {        // last plane of an aggregate: combine the children, store
+                double t = sum;
+                if (C.fi) t += __shfl_xor_sync(0xffffffffu, t, 1);
+                if (C.fj) t += __shfl_xor_sync(0xffffffffu, t, 16);
+                const bool writer = col.inmesh && (!C.fi || !(lane & 1)) && (!C.fj || !(lane & 16));
+                if (writer) {
+                    const long long I = ((long long)(k >> C.fk) * C.nj + (col.j >> C.fj)) * C.ni + (col.i >> C.fi);
+                    if (to_all) own.st_all(C.b, I, (mgf)t);
+                    else own.st(C.b, I, C, 1, (mgf)t);
+                }
+                sum = 0;
+            }
+            x0m = x0c; x0c = x0p; rc = rp; dgc = dgp;
+        }
+    });
+}
+
+// Pass B (up, level 1 -> fine): z = (x0 + P e) + w D^-1 (r - K (x0 + P e)); returns the thread's share of r.z
+template <class Own>
+__device__ __forceinline__ double mg_fine_up(const Own &own, const MgnArgs &a, const MgRuns &R, const mgf *e)
+{
+    const StencilC &s = a.s;
+    const MgLevel &C = a.L[1], &L0 = a.L[0];
+    double acc = 0;
+    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
+        const bool act = col.inner;
+        long long u = col.base + (long long)kbeg * s.sk;
+        double x0m = 0, x0c = 0, x0p = 0, rc = 0;
+        mgf dgm = 0, dgc = 0;
+        if (act) {
+            if (kbeg >= 1) { dgm = a.diagf[u - s.sk]; x0m = mg_x0(a.r[u - s.sk], dgm); }
+            rc = a.r[u]; dgc = a.diagf[u];
+            x0c = mg_x0(rc, dgc);
+        }
+        const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi), cplane = (long long)C.ni * C.nj;
+        for (int k = kbeg; k < kend; k++, u += s.sk) {
+            double rp = 0; mgf dgp = 0;
+            if (act && k + 1 < s.nk) { rp = a.r[u + s.sk]; dgp = a.diagf[u + s.sk]; }
+            x0p = mg_x0(rp, dgp);
+            mgf zf = 0;
+            if (act && dgc != (mgf)0) {
+                // the correction of a neighbour is that of ITS aggregate; a neighbour that is not an unknown carries 0
+                const long long I0 = (long long)(k >> C.fk) * cplane + crow;
+                const double e0 = e[I0];
+                const mgf gxm = a.diagf[u - 1], gxp = a.diagf[u + 1], gym = a.diagf[u - s.sj], gyp = a.diagf[u + s.sj];
+                const double vxm = gxm != (mgf)0 ? mg_x0(a.r[u - 1], gxm) + (double)e[I0 - (col.i >> C.fi) + ((col.i - 1) >> C.fi)] : 0.0;
+                const double vxp = gxp != (mgf)0 ? mg_x0(a.r[u + 1], gxp) + (double)e[I0 - (col.i >> C.fi) + ((col.i + 1) >> C.fi)] : 0.0;
+                const double vym = gym != (mgf)0 ? mg_x0(a.r[u - s.sj], gym) + (double)e[I0 + (long long)(((col.j - 1) >> C.fj) - (col.j >> C.fj)) * C.ni] : 0.0;
+                const double vyp = gyp != (mgf)0 ? mg_x0(a.r[u + s.sj], gyp) + (double)e[I0 + (long long)(((col.j + 1) >> C.fj) - (col.j >> C.fj)) * C.ni] : 0.0;
+                const double vzm = dgm != (mgf)0 ? x0m + (double)e[I0 + (long long)(((k - 1) >> C.fk) - (k >> C.fk)) * cplane] : 0.0;
+                const double vzp = dgp != (mgf)0 ? x0p + (double)e[I0 + (long long)(((k + 1) >> C.fk) - (k >> C.fk)) * cplane] : 0.0;
+                const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
+                const double xu = x0c + e0;
+                const double zu = xu + MG_OMEGA * (double)__frcp_rn(dgc) * (rc - ((double)dgc * xu - off));
+                zf = (mgf)zu;
+                acc += rc * (double)zf;
+            }
+            if (col.inmesh) own.st(a.z, u, L0, 0, zf);
+            x0m = x0c; x0c = x0p; rc = rp; dgm = dgc; dgc = dgp;
+        }
+    });
+    return acc;
+}
+
+// Pass C: d = z + beta d_old (formed on the fly for the neighbours, written for this node); returns the share of d.K d
+template <class Own>
+__device__ __forceinline__ double mg_fine_dir(const Own &own, const MgnArgs &a, const MgRuns &R, double beta, const double *d_old,
+                                              double *d_new)
+{
+    const StencilC &s = a.s;
     const MgLevel &L0 = a.L[0];
-    if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
-        double acc = 0;
-        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
-            double zu = L0.minv[u] * a.r[u];
-            own.st(a.z, u, L0, 0, zu);
-            acc += a.r[u] * zu;
+    double acc = 0;
+    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
+        long long u = col.base + (long long)kbeg * s.sk;
+        double dm = 0, dc = 0, dp = 0;
+        if (col.inmesh) {
+            if (kbeg >= 1) dm = (double)a.z[u - s.sk] + beta * d_old[u - s.sk];
+            dc = (double)a.z[u] + beta * d_old[u];
         }
-        return acc;
-    }
-    // The coarse levels are tiny: in slab mode the right-hand side of level `lr` (a.first_redundant; by default the coarsest
-    // level) is stored to EVERY rank, and every rank runs the levels lr .. coarsest redundantly in full with grid-local
-    // barriers only (identical arithmetic -> identical result everywhere).  That removes 2 inter-GPU barriers per redundant
-    // level and coarse_sweeps+1 for the coarsest from every V-cycle.
-    const int lc = a.nlev - 1;
-    const MgLevel &Lc = a.L[lc];
-    int lr = lc;
-    if constexpr (Own::slab) lr = a.first_redundant;
-    OwnAll whole;
-    mg_down0(own, a.s, a.r, L0.diag, L0.x, a.L[1], t0, stride, lr == 1);
-    own.barrier(grid);
-    MG_TICK(0);
-    for (int l = 1; l + 1 < a.nlev; l++) {
-        if (Own::slab && l >= lr) {
-            mg_down(whole, a.L[l], l, a.L[l + 1], t0, stride, false);
-            grid.sync();
-        } else {
-            mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lr);
-            own.barrier(grid);
+        for (int k = kbeg; k < kend; k++, u += s.sk) {
+            dp = 0;
+            if (col.inmesh && k + 1 < s.nk) dp = (double)a.z[u + s.sk] + beta * d_old[u + s.sk];
+            if (col.inner) {
+                const double dg = a.diagf[u];
+                if (dg != 0) {
+                    // z and d are identically zero outside the REG set: no neighbour masks
+                    const double off = s.gdx2 * (((double)a.z[u - 1] + beta * d_old[u - 1]) + ((double)a.z[u + 1] + beta * d_old[u + 1])) +
+                                       s.gdy2 * (((double)a.z[u - s.sj] + beta * d_old[u - s.sj]) + ((double)a.z[u + s.sj] + beta * d_old[u + s.sj])) +
+                                       s.gdz2 * (dm + dp);
+                    acc += dc * (dg * dc - off);
+                }
+            }
+            if (col.inmesh) own.st(d_new, u, L0, 0, dc);
+            dm = dc; dc = dp;
         }
-    }
-    MG_TICK(1);
-    {
-        for (long long u = t0; u < Lc.nn; u += stride) Lc.x[u] = MG_OMEGA * Lc.b[u] * Lc.minv[u];
-        grid.sync();
-        for (int sweep = 0; sweep < a.coarse_sweeps; sweep += 2) {
-            mg_jacobi(whole, Lc, lc, Lc.x, Lc.xn, t0, stride);
-            grid.sync();
-            mg_jacobi(whole, Lc, lc, Lc.xn, Lc.x, t0, stride);
-            grid.sync();
+    });
+    return acc;
+}
+
+// Pass D: delta += alpha d ; r -= alpha K d ; returns the share of |r|^2
+template <class Own>
+__device__ __forceinline__ double mg_fine_res(const Own &own, const MgnArgs &a, const MgRuns &R, double alpha, const double *d)
+{
+    const StencilC &s = a.s;
+    const MgLevel &L0 = a.L[0];
+    double acc = 0;
+    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
+        if (!col.inner) return;
+        long long u = col.base + (long long)kbeg * s.sk;
+        double dm = kbeg >= 1 ? d[u - s.sk] : 0.0, dc = d[u], dp = 0;
+        for (int k = kbeg; k < kend; k++, u += s.sk) {
+            dp = k + 1 < s.nk ? d[u + s.sk] : 0.0;
+            const double dg = a.diagf[u];
+            if (dg != 0) {
+                const double q = dg * dc - (s.gdx2 * (d[u - 1] + d[u + 1]) + s.gdy2 * (d[u - s.sj] + d[u + s.sj]) + s.gdz2 * (dm + dp));
+                a.delta[u] = a.delta[u] + alpha * dc;
+                const double rn = a.r[u] - alpha * q;
+                own.st(a.r, u, L0, 0, rn);
+                acc += rn * rn;
+            }
+            dm = dc; dc = dp;
         }
-    }
-    MG_TICK(2);
-    const double *e = Lc.x;
-    for (int l = a.nlev - 2; l >= 1; l--) {
-        if (Own::slab && l >= lr) {
-            mg_up(whole, a.L[l], l, a.L[l + 1], e, t0, stride);
-            grid.sync();
-        } else {
-            mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
-            own.barrier(grid);
+    });
+    return acc;
+}
+
+// Newton linearisation at the current phi (the reference's GS residual with the Neumann face neighbours folded into the
+// node itself, PotentialSolver.cpp:389-421), Jacobian diagonal; delta = 0, d0 = 0.  Returns the share of |R|^2.
+template <class Own>
+__device__ __forceinline__ double mg_linearise(const Own &own, const MgnArgs &a, long long t0, long long stride)
+{
+    const StencilC &s = a.s;
+    const MgLevel &L0 = a.L[0];
+    const double *phi = a.phi;
+    double acc = 0;
+    for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
+        double r = 0;
+        mgf dj = 0;
+        if (a.type[u] == NT_REG) {
+            const double p = phi[u];
+            const double ex = exp((p - a.phi0) / a.Te0);
+            const double src = (a.rho[u] - C_QE * (a.n0 * ex)) / C_EPS_0;
+            const bool fxm = a.type[u - 1] >= NT_I0, fxp = a.type[u + 1] >= NT_I0, fym = a.type[u - s.sj] >= NT_I0,
+                       fyp = a.type[u + s.sj] >= NT_I0, fzm = a.type[u - s.sk] >= NT_I0, fzp = a.type[u + s.sk] >= NT_I0;
+            const double xm = fxm ? p : phi[u - 1], xp = fxp ? p : phi[u + 1];
+            const double ym = fym ? p : phi[u - s.sj], yp = fyp ? p : phi[u + s.sj];
+            const double zm = fzm ? p : phi[u - s.sk], zp = fzp ? p : phi[u + s.sk];
+            r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
+            double d0 = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
+            if (fxm) d0 -= s.gdx2;
+            if (fxp) d0 -= s.gdx2;
+            if (fym) d0 -= s.gdy2;
+            if (fyp) d0 -= s.gdy2;
+            if (fzm) d0 -= s.gdz2;
+            if (fzp) d0 -= s.gdz2;
+            dj = (mgf)(d0 + a.n0 * C_QE / (C_EPS_0 * a.Te0) * ex);
+            acc += r * r;
         }
-        e = a.L[l].xn;
+        own.st(a.r, u, L0, 0, r);
+        own.st(a.diagf, u, L0, 0, dj);
+        own.st(a.d0, u, L0, 0, 0.0);
+        a.delta[u] = 0;
     }
-    MG_TICK(3);
-    return mg_up0(own, a.s, L0, a.r, L0.diag, L0.minv, L0.x, a.nbmask, a.L[1], e, a.z, t0, stride);
+    return acc;
+}
+
+// phi += delta on the unknowns; sum of delta^2 counted once per node that takes the value (the node + the face nodes
+// mirroring it), i.e. the reference's sum over all nodes of y^2 (PotentialSolver.cpp:279-283)
+template <class Own>
+__device__ __forceinline__ double mg_update(const Own &own, const MgnArgs &a, long long t0, long long stride)
+{
+    const StencilC &s = a.s;
+    const MgLevel &L0 = a.L[0];
+    double acc = 0;
+    for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
+        if (a.type[u] != NT_REG) continue;
+        const double dl = a.delta[u];
+        own.st(a.phi, u, L0, 0, a.phi[u] + dl);
+        const int cnt = 1 + (a.type[u - 1] >= NT_I0) + (a.type[u + 1] >= NT_I0) + (a.type[u - s.sj] >= NT_I0) + (a.type[u + s.sj] >= NT_I0) +
+                        (a.type[u - s.sk] >= NT_I0) + (a.type[u + s.sk] >= NT_I0);
+        acc += cnt * (dl * dl);
+    }
+    return acc;
 }
 
 // Sum of per-block partials (of every rank in slab mode), computed redundantly by every block in the same fixed order
@@ -570,8 +780,61 @@ __device__ __forceinline__ double mg_total(const Own &own, const double *part, i
     return grid_total(part, own.nparts(nb), sh, bcast);
 }
 
+// z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.  ok = false: a slab barrier gave up.
 template <class Own>
-__device__ __forceinline__ void mg_pcg_body(MgPcgArgs &a, Own &own)
+__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, const MgnArgs &a, const MgRuns &R, long long t0,
+                                            long long stride, mgf *smem, unsigned long long &tick, bool &ok)
+{
+    const MgLevel &L0 = a.L[0];
+    if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
+        double acc = 0;
+        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
+            const mgf dg = a.diagf[u];
+            const double rr = a.r[u];
+            const mgf zf = dg != (mgf)0 ? (mgf)(rr * (double)__frcp_rn(dg)) : (mgf)0;
+            own.st(a.z, u, L0, 0, zf);
+            acc += rr * (double)zf;
+        }
+        return acc;
+    }
+    // The coarse levels are tiny: in slab mode the right-hand side of level `lr` (a.first_redundant; at the latest the
+    // coarsest level) is stored to EVERY rank, and every rank runs the levels lr .. coarsest redundantly in full with
+    // grid-local barriers only (identical arithmetic -> identical result everywhere).
+    const int lc = a.nlev - 1;
+    int lr = lc;
+    if constexpr (Own::slab) lr = a.first_redundant;
+    OwnAll whole;
+    mg_fine_down(own, a, R, lr == 1);
+    ok = own.barrier(grid) && ok;
+    MG_TICK(0);
+    for (int l = 1; l + 1 < a.nlev; l++) {
+        if (Own::slab && l >= lr) {
+            mg_down(whole, a.L[l], l, a.L[l + 1], t0, stride, false);
+            ok = own.lbarrier(grid) && ok;
+        } else {
+            mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lr);
+            ok = own.barrier(grid) && ok;
+        }
+    }
+    MG_TICK(1);
+    const mgf *e = mg_coarsest(a.L[lc], a.coarse_sweeps, smem);
+    MG_TICK(2);
+    for (int l = a.nlev - 2; l >= 1; l--) {
+        if (Own::slab && l >= lr) {
+            mg_up(whole, a.L[l], l, a.L[l + 1], e, t0, stride);
+            ok = own.lbarrier(grid) && ok;
+        } else {
+            mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
+            ok = own.barrier(grid) && ok;
+        }
+        e = a.L[l].xn;
+    }
+    MG_TICK(3);
+    return mg_fine_up(own, a, R, e);
+}
+
+template <class Own>
+__device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
@@ -583,96 +846,135 @@ __device__ __forceinline__ void mg_pcg_body(MgPcgArgs &a, Own &own)
     const int nb = gridDim.x;
     const int np = own.nparts(nb);
     double *pA = a.part, *pB = a.part + np, *pC = a.part + 2 * np;
-    const double *diag = L0.diag;
-    const double *minv = L0.minv;
-    double *x0 = L0.x;
-    const long long ulo = own.lo(L0, 0), uhi = own.hi(L0, 0);
-
-    // delta = 0: r = R; x0 = w D^-1 r; |r|
-    double acc = 0;
-    for (long long u = ulo + t0; u < uhi; u += stride) {
-        const double r = a.r[u];
-        own.st(x0, u, L0, 0, MG_OMEGA * r * minv[u]);
-        acc += r * r;
-    }
-    double t = block_sum(acc, sh);
-    if (threadIdx.x == 0) own.put_partial(pC, nb, t);
-    own.barrier(grid);
-    double l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / (double)s.nn);
-    const double l2_start = l2;
-    const double stop = fmax(a.tol, a.rel_tol * l2_start);
-    int it = 0, converged = l2 < stop;
-    double rz = 0, beta = 0;
-    double *d_old = a.d0, *d_new = a.d1;
+    const MgRuns R = mg_runs(own, a);
+    const double nn = (double)s.nn;
+    bool ok = true;
     unsigned long long tick = mg_now();
-    while (!converged && it < a.max_it) {
-        // z = M^-1 r ; rz' = r.z
-        acc = mg_vcycle(grid, own, a, t0, stride, tick);
-        t = block_sum(acc, sh);
-        if (threadIdx.x == 0) own.put_partial(pB, nb, t);
-        own.barrier(grid);
-        MG_TICK(4);
-        const double rz_new = mg_total(own, pB, nb, sh, &bc);
-        beta = (it == 0) ? 0.0 : rz_new / rz;
-        rz = rz_new;
-        // d = z + beta d (formed on the fly for the neighbours, written for this node) ; q = K d ; dq = d.q
-        acc = 0;
-        for (long long u = ulo + t0; u < uhi; u += stride) {
-            const double dj = diag[u];
-            double du = 0, qu = 0;
-            if (dj != 0) {
-                du = a.z[u] + beta * d_old[u];
-                // z and d are identically zero outside the REG set: no neighbour masks
-                const double off = s.gdx2 * ((a.z[u - 1] + beta * d_old[u - 1]) + (a.z[u + 1] + beta * d_old[u + 1])) +
-                                   s.gdy2 * ((a.z[u - s.sj] + beta * d_old[u - s.sj]) + (a.z[u + s.sj] + beta * d_old[u + s.sj])) +
-                                   s.gdz2 * ((a.z[u - s.sk] + beta * d_old[u - s.sk]) + (a.z[u + s.sk] + beta * d_old[u + s.sk]));
-                qu = dj * du - off;
-                acc += du * qu;
+
+    if constexpr (Own::slab) {
+        // working copy of phi inside the pool: this rank's planes plus one halo plane on each side (kept current afterwards
+        // by the peer stores of the update pass)
+        const long long plane = s.sk;
+        const long long lo = max(0ll, own.lo(L0, 0) - plane), hi = min(s.nn, own.hi(L0, 0) + plane);
+        for (long long u = lo + t0; u < hi; u += stride) a.phi[u] = a.phi_user[u];
+        ok = own.lbarrier(grid) && ok;
+    }
+
+    int converged = 0, nit = 0, lin_fail = 0;
+    bool last_full = false;       // the previous linear solve went all the way to tol/2 (not stopped early by the forcing term)
+    long long lin_total = 0;
+    double ynorm = 0, Rn = 0, Rprev = 0, R0 = 0, l2 = 0;
+    for (nit = 0;; nit++) {
+        // ---- linearise at the current phi
+        double acc = mg_linearise(own, a, t0, stride);
+        double t = block_sum(acc, sh);
+        if (threadIdx.x == 0) own.put_partial(pC, nb, t);
+        ok = own.barrier(grid) && ok;
+        Rn = sqrt(mg_total(own, pC, nb, sh, &bc) / nn);
+        MG_TICK(7);
+        if (nit == 0) R0 = Rn;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nit < 10) a.out[MGN_OUT_HIST + 2 * nit] = Rn;
+        if (!ok) break;
+        // Converged: the reference's test on the update (PotentialSolver.cpp:282-285) AND the nonlinear residual below tol.  Near
+        // the rounding floor of the residual evaluation (|phi| diag eps, reachable only with tolerances far below production)
+        // |R| stops falling: there a full-accuracy linear solve whose update passed the reference's test is accepted, as the
+        // reference itself would.
+        if (nit == 0 ? Rn < a.tol : (ynorm < a.nr_tol && (Rn < a.tol || last_full))) { converged = 1; break; }
+        if (nit >= a.nr_max_it) break;
+        // ---- Galerkin diagonals of the coarse levels
+        {
+            int lr = a.nlev - 1;
+            if constexpr (Own::slab) lr = a.first_redundant;
+            OwnAll whole;
+            for (int l = 1; l < a.nlev; l++) {
+                if (Own::slab && l > lr) {
+                    mg_diagl(whole, a.L[l - 1], a.L[l], l, t0, stride, false);
+                    ok = own.lbarrier(grid) && ok;
+                } else {
+                    const bool to_all = Own::slab && l == lr;
+                    if (l == 1) mg_diag1(own, s, a.type, a.diagf, a.L[1], t0, stride, to_all);
+                    else mg_diagl(own, a.L[l - 1], a.L[l], l, t0, stride, to_all);
+                    ok = own.barrier(grid) && ok;
+                }
             }
-            own.st(d_new, u, L0, 0, du);
-            a.q[u] = qu;
         }
+        MG_TICK(8);
+        // ---- CG on K delta = R down to the forcing level
+        const double eta = nit == 0 ? a.eta0 : fmin(a.eta_max, a.gamma * (Rn / Rprev) * (Rn / Rprev));
+        const double stop = fmax(0.5 * a.tol, eta * Rn);
+        Rprev = Rn;
+        l2 = Rn;
+        int it = 0;
+        double rz = 0;
+        double *d_old = a.d0, *d_new = a.d1;
+        while (ok && l2 >= stop && it < a.max_it) {
+            // z = M^-1 r ; rz' = r.z
+            acc = mg_vcycle(grid, own, a, R, t0, stride, smem, tick, ok);
+            t = block_sum(acc, sh);
+            if (threadIdx.x == 0) own.put_partial(pB, nb, t);
+            ok = own.barrier(grid) && ok;
+            MG_TICK(4);
+            const double rz_new = mg_total(own, pB, nb, sh, &bc);
+            const double beta = (it == 0) ? 0.0 : rz_new / rz;
+            rz = rz_new;
+            // d = z + beta d ; dq = d.K d
+            acc = mg_fine_dir(own, a, R, beta, d_old, d_new);
+            t = block_sum(acc, sh);
+            if (threadIdx.x == 0) own.put_partial(pA, nb, t);
+            ok = own.barrier(grid) && ok;
+            MG_TICK(5);
+            const double dq = mg_total(own, pA, nb, sh, &bc);
+            if (!(dq > 0)) { lin_fail = 1; break; }          // breakdown (cannot happen for an SPD system short of overflow): give up cleanly
+            const double alpha = rz / dq;
+            // delta += alpha d ; r -= alpha K d ; |r|
+            acc = mg_fine_res(own, a, R, alpha, d_new);
+            t = block_sum(acc, sh);
+            if (threadIdx.x == 0) own.put_partial(pC, nb, t);
+            ok = own.barrier(grid) && ok;
+            MG_TICK(6);
+            l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / nn);
+            it++;
+            double *tmp = d_old; d_old = d_new; d_new = tmp;
+        }
+        if (l2 >= stop) lin_fail = 1;
+        last_full = stop <= 0.5 * a.tol && l2 < stop;
+        lin_total += it;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nit < 10) a.out[MGN_OUT_HIST + 2 * nit + 1] = it;
+        if (!ok) break;
+        // ---- phi += delta
+        acc = mg_update(own, a, t0, stride);
         t = block_sum(acc, sh);
         if (threadIdx.x == 0) own.put_partial(pA, nb, t);
-        own.barrier(grid);
-        MG_TICK(5);
-        const double alpha = rz / mg_total(own, pA, nb, sh, &bc);
-        // delta += alpha d ; r -= alpha q ; |r|
-        acc = 0;
-        for (long long u = ulo + t0; u < uhi; u += stride) {
-            a.delta[u] = a.delta[u] + alpha * d_new[u];
-            const double r = a.r[u] - alpha * a.q[u];
-            a.r[u] = r;
-            own.st(x0, u, L0, 0, MG_OMEGA * r * minv[u]);          // pre-smoothed iterate of the next V-cycle
-            acc += r * r;
-        }
-        t = block_sum(acc, sh);
-        if (threadIdx.x == 0) own.put_partial(pC, nb, t);
-        own.barrier(grid);
-        MG_TICK(6);
-        l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / (double)s.nn);
-        it++;
-        double *tmp = d_old; d_old = d_new; d_new = tmp;
-        if (l2 < stop) converged = 1;
+        ok = own.barrier(grid) && ok;
+        ynorm = sqrt(mg_total(own, pA, nb, sh, &bc) / nn);
+        MG_TICK(9);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { a.out[0] = converged; a.out[1] = it; a.out[2] = l2; a.out[3] = l2_start; }
+    if constexpr (Own::slab) {
+        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) a.phi_user[u] = a.phi[u];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.out[MGN_OUT_CONVERGED] = converged; a.out[MGN_OUT_NEWTON] = nit; a.out[MGN_OUT_LIN] = (double)lin_total;
+        a.out[MGN_OUT_YNORM] = ynorm; a.out[MGN_OUT_RNORM] = Rn; a.out[MGN_OUT_RNORM0] = R0; a.out[MGN_OUT_LINFAIL] = lin_fail;
+        a.out[MGN_OUT_LINL2] = l2; a.out[MGN_OUT_ABORT] = ok ? 0.0 : 1.0;
+    }
 }
 
-#ifndef MG_BLOCK
-#define MG_BLOCK 512
-#endif
-__global__ void __launch_bounds__(MG_BLOCK, 1024 / MG_BLOCK) k_mg_pcg(MgPcgArgs a)
+extern __shared__ mgf mgn_smem[];
+
+__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton(MgnArgs a)
 {
     OwnAll own;
-    mg_pcg_body(a, own);
+    mgn_body(a, own, mgn_smem);
 }
 
 // slab-decomposed variant: one of these kernels per rank, running concurrently, talking through peer memory only
-__global__ void __launch_bounds__(MG_BLOCK, 1024 / MG_BLOCK) k_mg_pcg_slab(MgPcgArgs a, OwnSlab own, unsigned long long *epoch_io)
+__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton_slab(MgnArgs a, OwnSlab own, unsigned long long *epoch_io)
 {
-    own.epoch = *epoch_io;
-    mg_pcg_body(a, own);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *epoch_io = own.epoch;
+    own.epoch = epoch_io[0];
+    own.lepoch = epoch_io[1];
+    mgn_body(a, own, mgn_smem);
+    // every block read the epochs before its first barrier, and nobody gets past that barrier before all have arrived
+    if (blockIdx.x == 0 && threadIdx.x == 0) { epoch_io[0] = own.epoch; epoch_io[1] = own.lepoch; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -696,16 +998,20 @@ static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3], in
         }
         nlev++;
     }
+    // the coarsest level is solved inside shared memory (3 FP32 vectors).  A mesh with one short dimension stops coarsening
+    // early and can leave a last level that does not fit: such a hierarchy is cut back (in the limit to the plain Jacobi
+    // preconditioner of one level).  Never the case for the meshes of this path.
+    while (nlev > 1 && dims[nlev - 1][0] * dims[nlev - 1][1] * dims[nlev - 1][2] > 2 * MG_COARSEST_NODES) nlev--;
     return nlev;
 }
 
-static long long mg_coarse_doubles(const StencilC &s)
+static long long mg_coarse_elems(const StencilC &s)
 {
     long long dims[MG_MAX_LEVELS][3];
     int shifts[MG_MAX_LEVELS][3];
     const int nlev = mg_level_dims(s, dims, shifts);
     long long total = 0;
-    for (int l = 1; l < nlev; l++) total += 8 * dims[l][0] * dims[l][1] * dims[l][2];
+    for (int l = 1; l < nlev; l++) total += 8 * ((dims[l][0] * dims[l][1] * dims[l][2] + 3) & ~3ll);
     return total;
 }
 
@@ -757,28 +1063,30 @@ extern "C" int espic_mg_plan(int ni, int nj, int nk, const double dh[3], int nra
 
 // (re)build the hierarchy H for the current geometry; coarse-level arrays go to `external` if given (slab mode: a pool
 // that the other ranks map), else to an allocation owned by H
-static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *external)
+static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, mgf *external)
 {
     if (H->geom_version == c->geom_version && H->nlev > 0) return 0;
-    if (H->pool && !external) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
-    if (!H->nbmask) CK(cudaMalloc(&H->nbmask, (size_t)s.nn));
-    k_mg_nbmask<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->nbmask);
-    LAUNCH_CHECK(c);
+    if (H->pool && H->own_pool) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->pool)); H->pool = nullptr; }
     long long dims[MG_MAX_LEVELS][3];
     int shifts[MG_MAX_LEVELS][3];
     const int nlev = mg_level_dims(s, dims, shifts);
-    const long long total = mg_coarse_doubles(s);
-    if (external) H->pool = external;
-    else if (total > 0) CK(cudaMalloc(&H->pool, (size_t)total * sizeof(double)));
-    double *p = H->pool;
+    const long long total = mg_coarse_elems(s);
+    if (external) { H->pool = external; H->own_pool = false; }
+    else if (total > 0) {
+        CK(cudaMalloc(&H->pool, (size_t)total * sizeof(mgf)));
+        CK(cudaMemsetAsync(H->pool, 0, (size_t)total * sizeof(mgf), c->stream));
+        H->own_pool = true;
+    }
+    mgf *p = H->pool;
     for (int l = 0; l < nlev; l++) {
         MgLevel &L = H->L[l];
         L.ni = (int)dims[l][0]; L.nj = (int)dims[l][1]; L.nk = (int)dims[l][2];
         L.fi = shifts[l][0]; L.fj = shifts[l][1]; L.fk = shifts[l][2];
         L.nn = dims[l][0] * dims[l][1] * dims[l][2];
         if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = nullptr; continue; }
-        L.diag = p; p += L.nn; L.minv = p; p += L.nn; L.cx = p; p += L.nn; L.cy = p; p += L.nn; L.cz = p; p += L.nn;
-        L.x = p; p += L.nn; L.xn = p; p += L.nn; L.b = p; p += L.nn;
+        const long long pad = (L.nn + 3) & ~3ll;           // keep every array 16-byte aligned
+        L.diag = p; p += pad; L.minv = p; p += pad; L.cx = p; p += pad; L.cy = p; p += pad; L.cz = p; p += pad;
+        L.x = p; p += pad; L.xn = p; p += pad; L.b = p; p += pad;
     }
     H->nlev = nlev;
     for (int l = 1; l < nlev; l++) {
@@ -790,7 +1098,75 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, double *ext
     return 0;
 }
 
-// Newton + multigrid-preconditioned CG (same outer iteration as solve_nrpcg_spd)
+struct MgKnobs { int coarse_sweeps; double eta0, eta_max, gamma; bool profile; };
+// shared by the single-GPU and the slab solver, so that the two paths cannot drift apart
+static const MgKnobs &mg_knobs()
+{
+    static MgKnobs k;
+    static bool init = false;
+    if (!init) {
+        const char *ev = getenv("ESPIC_MG_COARSE_SWEEPS");
+        k.coarse_sweeps = ev ? std::max(0, atoi(ev)) : MG_COARSE_SWEEPS;
+        // ESPIC_MG_EXACT_NEWTON=1: every linear solve goes to tol/2 (the reference's exact Newton); else Eisenstat-Walker
+        const bool exact = getenv("ESPIC_MG_EXACT_NEWTON") != nullptr;
+        k.eta0 = exact ? 0.0 : (getenv("ESPIC_MG_ETA0") ? atof(getenv("ESPIC_MG_ETA0")) : 1e-2);
+        k.eta_max = exact ? 0.0 : 1e-1;
+        k.gamma = exact ? 0.0 : 0.9;
+        k.profile = getenv("ESPIC_MG_PROFILE") != nullptr;
+        init = true;
+    }
+    return k;
+}
+
+static size_t mg_smem_bytes(const MgHierarchy *H)
+{
+    return H->nlev > 1 ? (size_t)3 * H->L[H->nlev - 1].nn * sizeof(mgf) : 0;
+}
+
+template <typename K>
+static int mg_grid(espic_ctx *c, K kernel, size_t smem, const StencilC &s, int planes, int kunit, int *grid)
+{
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, MG_THREADS, smem));
+    if (bps < 1) { espic_set_error("the multigrid Newton kernel cannot be made resident"); return -1; }
+    // no more blocks than marching work items (small meshes: fewer blocks = cheaper barriers)
+    const long long units = (long long)((s.ni + MG_TX - 1) / MG_TX) * ((s.nj + MG_TY - 1) / MG_TY) * ((planes + kunit - 1) / kunit);
+    *grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(units, 1));
+    if (*grid > 1024) *grid = 1024;
+    return 0;
+}
+
+static void mg_report(espic_ctx *c, const double *h, const espic_solve_params *p, espic_solve_info *info, const char *tag)
+{
+    info->converged = h[MGN_OUT_CONVERGED] != 0.0;
+    info->nr_iters = (int)h[MGN_OUT_NEWTON];
+    info->lin_iters = (long long)h[MGN_OUT_LIN];
+    info->residual = h[MGN_OUT_YNORM];
+    if (h[MGN_OUT_LINFAIL] != 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[MGN_OUT_LINL2]);
+    if (!info->converged) printf("NR+PCG failed to converge, norm = %g\n", h[MGN_OUT_YNORM]);
+    if (mg_knobs().profile && c->rank == 0) {
+        fprintf(stderr, "[%s] newton steps %d, CG its %lld, |R| %.3e -> %.3e, |y| %.3e;", tag, info->nr_iters, info->lin_iters,
+                h[MGN_OUT_RNORM0], h[MGN_OUT_RNORM], h[MGN_OUT_YNORM]);
+        for (int q = 0; q < std::min(info->nr_iters + 1, 10); q++) fprintf(stderr, "  |R%d| %.3e (%d its)", q, h[MGN_OUT_HIST + 2 * q], (int)h[MGN_OUT_HIST + 2 * q + 1]);
+        fprintf(stderr, "\n");
+    }
+}
+
+static int mg_print_profile(espic_ctx *c, long long lin_iters, const char *tag)
+{
+    unsigned long long hp[16];
+    CK(cudaMemcpyAsync(hp, c->dscal + 40, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemsetAsync(c->dscal + 40, 0, sizeof(hp), c->stream));
+    const double n = (double)std::max<long long>(lin_iters, 1);
+    fprintf(stderr, "[%s profile] us per CG iteration: down0 %.1f  down %.1f  coarsest %.1f  up %.1f  up0+rz %.1f  d %.1f  r %.1f | per solve: "
+                    "linearise %.1f  galerkin %.1f  update %.1f\n", tag, hp[0] * 1e-3 / n, hp[1] * 1e-3 / n, hp[2] * 1e-3 / n, hp[3] * 1e-3 / n,
+            hp[4] * 1e-3 / n, hp[5] * 1e-3 / n, hp[6] * 1e-3 / n, hp[7] * 1e-3, hp[8] * 1e-3, hp[9] * 1e-3);
+    return 0;
+}
+
+// Newton + multigrid-preconditioned CG, one cooperative launch
 static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve_info *info)
 {
     int r;
@@ -799,97 +1175,37 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
     StencilC s = make_stencil(c->m);
     MgHierarchy *H = g_mg_of(c);
     if ((r = mg_setup(c, s, H, nullptr))) return r;
-    double *diag0 = c->sv[0], *R = c->sv[1], *diagJ = c->sv[2], *minv = c->sv[3];
-    double *delta = c->sv[4], *z = c->sv[5], *d0 = c->sv[6], *d1 = c->sv[7];
-    // two more fine vectors (q, x0) + the partial sums live in the reduction scratch
-    if ((r = ensure_buf(&c->red, &c->red_cap, 2 * s.nn + 8192, c->stream))) return r;
-    double *q = c->red, *x0 = c->red + s.nn, *part = c->red + 2 * s.nn;
-    static int coarse_sweeps = -1;
-    if (coarse_sweeps < 0) {
-        const char *ev = getenv("ESPIC_MG_COARSE_SWEEPS");
-        coarse_sweeps = ev ? std::max(0, atoi(ev)) : MG_COARSE_SWEEPS;
-        coarse_sweeps += coarse_sweeps & 1;
-    }
-    if (c->diag0_version != c->geom_version) {
-        k_spd_diag0<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, diag0);
-        LAUNCH_CHECK(c);
-        c->diag0_version = c->geom_version;
-    }
-    int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg, MG_BLOCK, 0));
-    if (bps < 1) { espic_set_error("k_mg_pcg cannot be made resident"); return -1; }
-    long long want = (s.nn + MG_BLOCK - 1) / MG_BLOCK;
-    int grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(want, 1));
-    if (3 * grid > 4096) grid = 4096 / 3;
-    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
-    double *dout = reinterpret_cast<double *>(c->dscal + 24);
-    double *dres = reinterpret_cast<double *>(c->dscal + 16);
-    double norm = 0, r0_norm = 0, lin_stop = 0;
-    bool converged = false;
-    static const bool inexact = getenv("ESPIC_MG_EXACT_NEWTON") == nullptr;
-    static const double forcing = getenv("ESPIC_MG_FORCING") ? atof(getenv("ESPIC_MG_FORCING")) : 1.0;
-    for (int it = 0; it < p->nr_max_it; it++) {
-        info->nr_iters++;
-        k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, diag0, p->phi0, p->Te0, p->n0,
-                                                                R, diagJ, minv, delta);
-        LAUNCH_CHECK(c);
-        // Galerkin diagonals: the Boltzmann term changes with phi, the links do not
-        for (int l = 1; l < H->nlev; l++) {
-            if (l == 1) k_mg_diag_from_fine<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, diagJ, H->L[1]);
-            else k_mg_diag_from_level<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
-            LAUNCH_CHECK(c);
-        }
-        MgPcgArgs a;
-        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = coarse_sweeps; a.nbmask = H->nbmask; a.first_redundant = H->nlev - 1;
-        a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
-        for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
-        a.L[0].diag = diagJ; a.L[0].minv = minv; a.L[0].x = x0;
-        a.delta = delta; a.r = R; a.z = z; a.d0 = d0; a.d1 = d1; a.q = q;
-        a.part = part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
-        // Newton step 0 leaves a nonlinear residual of about newton_ratio * |R0| whatever the accuracy of its linear solve:
-        // its linear solve stops at that level (measured on the bench case: factor 0.1 / 0.3 / 0.6 / 1.0 -> 58.5 / 56.4 /
-        // 54.6 / 53.7 CG iterations per step, Newton count unchanged); every later step, and a first step without
-        // history, is solved to tol, and convergence is only declared after a solve that went to tol.
-        a.rel_tol = (it == 0 && inexact) ? forcing * std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
-        CK(cudaMemsetAsync(d0, 0, (size_t)s.nn * sizeof(double), c->stream));     // beta = 0 in the first iteration must meet finite numbers
-        void *args[] = {&a};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
-        LAUNCH_CHECK(c);
-        k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, delta, c->phi, part);
-        LAUNCH_CHECK(c);
-        k_sum_final<<<1, 256, 0, c->stream>>>(part, nb_res, dres);
-        LAUNCH_CHECK(c);
-        double *h = reinterpret_cast<double *>(c->hpin) + 24;
-        CK(cudaMemcpyAsync(h, dout, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        double sum;
-        if ((r = read_scalar(c, dres, &sum))) return r;
-        info->lin_iters += (long long)h[1];
-        if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
-        norm = sqrt(sum / (double)s.nn);
-        if (it == 0) r0_norm = h[3];
-        if (it == 1 && r0_norm > 0) H->newton_ratio = h[3] / r0_norm;
-        lin_stop = (a.rel_tol > 0) ? std::max(p->tol, a.rel_tol * h[3]) : p->tol;
-        if (getenv("ESPIC_MG_PROFILE"))
-            fprintf(stderr, "[mg newton %d] |R| %.3e -> %.3e in %d its, |y| = %.3e\n", it, h[3], h[2], (int)h[1], norm);
-        // converged as the reference defines it (update below nr_tol) -- but only after a linear solve that went to tol
-        if (norm < p->nr_tol && lin_stop <= p->tol) { converged = true; break; }
-    }
+    const MgKnobs &kn = mg_knobs();
+    const size_t smem = mg_smem_bytes(H);
+    int grid = 0;
+    if ((r = mg_grid(c, k_mg_newton, smem, s, s.nk, H->nlev > 1 ? (1 << H->L[1].fk) : 1, &grid))) return r;
+    if ((r = ensure_buf(&c->red, &c->red_cap, 3ll * grid + 64, c->stream))) return r;
+    double *dout = reinterpret_cast<double *>(c->dscal + 64);        // 32 doubles: slots 64..95
+    MgnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = s; a.nlev = H->nlev; a.coarse_sweeps = kn.coarse_sweeps; a.first_redundant = H->nlev - 1;
+    for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
+    a.type = c->node_type; a.rho = c->rho; a.phi = c->phi; a.phi_user = c->phi;
+    a.r = c->sv[1]; a.delta = c->sv[4]; a.d0 = c->sv[6]; a.d1 = c->sv[7];
+    a.diagf = reinterpret_cast<mgf *>(c->sv[2]); a.z = reinterpret_cast<mgf *>(c->sv[5]);
+    a.part = c->red;
+    a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
+    a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
+    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma;
+    a.out = dout;
+    a.prof = kn.profile ? c->dscal + 40 : nullptr;
+    void *args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void *)k_mg_newton, dim3(grid), dim3(MG_THREADS), args, smem, c->stream));
+    LAUNCH_CHECK(c);
     for (int level = 0; level < 3; level++) {
         k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
         LAUNCH_CHECK(c);
     }
-    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
-    info->converged = converged;
-    info->residual = norm;
-    if (getenv("ESPIC_MG_PROFILE")) {
-        unsigned long long hp[8];
-        CK(cudaMemcpyAsync(hp, c->dscal + 40, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaMemsetAsync(c->dscal + 40, 0, sizeof(hp), c->stream));
-        fprintf(stderr, "[mg profile] its=%lld  us/it: down0 %.1f  down %.1f  coarsest %.1f  up %.1f  up0+rz %.1f  dq %.1f  r %.1f\n",
-                info->lin_iters, hp[0] * 1e-3 / info->lin_iters, hp[1] * 1e-3 / info->lin_iters, hp[2] * 1e-3 / info->lin_iters,
-                hp[3] * 1e-3 / info->lin_iters, hp[4] * 1e-3 / info->lin_iters, hp[5] * 1e-3 / info->lin_iters, hp[6] * 1e-3 / info->lin_iters);
-    }
+    double *h = reinterpret_cast<double *>(c->hpin) + 64;
+    CK(cudaMemcpyAsync(h, dout, 32 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    mg_report(c, h, p, info, "mg");
+    if (kn.profile) return mg_print_profile(c, info->lin_iters, "mg");
     return 0;
 }
 
@@ -899,14 +1215,15 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
 // ====================================================================================================================
 
 struct SlabState {
-    bool ready = false, diag0_done = false;
+    bool ready = false;
     long long geom_version = -1;
     double *pool = nullptr;            // this rank's pool; every rank carves it identically
     size_t pool_doubles = 0;
     void *peer_base[MG_MAX_RANKS] = {nullptr};
-    // carved arrays (fine vectors), the coarse-level arrays, partial sums, flags
-    double *diag0, *R, *diagJ, *minv, *delta, *z, *d0, *d1, *q, *x0, *coarse, *part;
-    unsigned long long *flags, *epoch, *arrive, *release;
+    // carved arrays
+    double *R, *delta, *d0, *d1, *phi, *part;
+    mgf *z, *diagf, *coarse;
+    unsigned long long *flags, *epoch, *arrive, *release, *abort_word, *larrive, *lrelease;
     MgHierarchy H;
     OwnSlab own;
 };
@@ -918,7 +1235,6 @@ static void slab_destroy(espic_ctx *c)
     for (int p = 0; p < MG_MAX_RANKS; p++)
         if (S->peer_base[p] && p != c->rank) cudaIpcCloseMemHandle(S->peer_base[p]);
     cudaFree(S->pool);
-    cudaFree(S->H.nbmask);
     delete S;
     c->slab = nullptr;
 }
@@ -940,20 +1256,25 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
         return -1;
     }
     const int planes = s.nk / c->nranks;
-    // ---- pool: identical carving on every rank
-    const long long coarse = mg_coarse_doubles(s);
-    const long long nparts = 3ll * c->nranks * 4096;
-    S->pool_doubles = (size_t)(10 * s.nn + coarse + nparts + 128);
+    // ---- pool: identical carving on every rank (counted in doubles; FP32 arrays take half)
+    const long long nnp = (s.nn + 1) & ~1ll;
+    const long long coarse = (mg_coarse_elems(s) + 1) / 2;
+    const long long nparts = 3ll * c->nranks * 1024;
+    S->pool_doubles = (size_t)(5 * nnp + nnp + coarse + nparts + 256);
     CK(cudaMalloc(&S->pool, S->pool_doubles * sizeof(double)));
     CK(cudaMemsetAsync(S->pool, 0, S->pool_doubles * sizeof(double), c->stream));
     double *p = S->pool;
-    S->diag0 = p; p += s.nn; S->R = p; p += s.nn; S->diagJ = p; p += s.nn; S->minv = p; p += s.nn; S->delta = p; p += s.nn;
-    S->z = p; p += s.nn; S->d0 = p; p += s.nn; S->d1 = p; p += s.nn; S->q = p; p += s.nn; S->x0 = p; p += s.nn;
-    S->coarse = p; p += coarse; S->part = p; p += nparts;
+    S->R = p; p += nnp; S->delta = p; p += nnp; S->d0 = p; p += nnp; S->d1 = p; p += nnp; S->phi = p; p += nnp;
+    S->z = reinterpret_cast<mgf *>(p); p += nnp / 2; S->diagf = reinterpret_cast<mgf *>(p); p += nnp / 2;
+    S->coarse = reinterpret_cast<mgf *>(p); p += coarse;
+    S->part = p; p += nparts;
     S->flags = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->epoch = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->arrive = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->release = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->abort_word = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->larrive = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->lrelease = reinterpret_cast<unsigned long long *>(p); p += 16;
     // ---- exchange IPC handles through the NCCL communicator and map the peers
     cudaIpcMemHandle_t mine;
     CK(cudaIpcGetMemHandle(&mine, S->pool));
@@ -969,7 +1290,8 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     CK(cudaFree(dh));
     OwnSlab &own = S->own;
     own.rank = c->rank; own.nranks = c->nranks; own.flags = S->flags; own.epoch = 0;
-    own.arrive = S->arrive; own.release = S->release;
+    own.arrive = S->arrive; own.release = S->release; own.abort_word = S->abort_word;
+    own.larrive = S->larrive; own.lrelease = S->lrelease; own.lepoch = 0;
     for (int q = 0; q < MG_MAX_RANKS; q++) own.peer[q] = 0;
     for (int q = 0; q < c->nranks; q++) {
         if (q == c->rank) { S->peer_base[q] = S->pool; continue; }
@@ -1000,93 +1322,52 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
     if ((r = slab_setup(c, s))) return r;
     SlabState *S = static_cast<SlabState *>(c->slab);
     MgHierarchy *H = &S->H;
+    const MgKnobs &kn = mg_knobs();
     const long long slab_nn = (long long)(s.nk / c->nranks) * s.sk;
-    if (!S->diag0_done) {
-        k_spd_diag0<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, S->diag0);
-        LAUNCH_CHECK(c);
-        S->diag0_done = true;
+    const size_t smem = mg_smem_bytes(H);
+    // the same grid on every rank (the partial-sum layout depends on it)
+    int grid = 0;
+    if ((r = mg_grid(c, k_mg_newton_slab, smem, s, s.nk / c->nranks, H->nlev > 1 ? (1 << H->L[1].fk) : 1, &grid))) return r;
+    double *dout = reinterpret_cast<double *>(c->dscal + 64);
+    MgnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = s; a.nlev = H->nlev; a.coarse_sweeps = kn.coarse_sweeps;
+    // Levels with at most MG_SLAB_REDUNDANT_NODES nodes (override: ESPIC_MG_SLAB_REDUNDANT_NODES, 0 = only the coarsest)
+    // are solved by every rank in full instead of by slabs: 2 inter-GPU barriers less per level and V-cycle for redundant
+    // work on a small level (profiles/r1_slab_redundant_levels_n4.txt).
+    {
+        long long dims[MG_MAX_LEVELS][3];
+        for (int l = 0; l < H->nlev; l++) { dims[l][0] = H->L[l].ni; dims[l][1] = H->L[l].nj; dims[l][2] = H->L[l].nk; }
+        a.first_redundant = mg_first_redundant(H->nlev, dims, mg_slab_redundant_limit());
     }
-    int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_mg_pcg_slab, MG_BLOCK, 0));
-    if (bps < 1) { espic_set_error("k_mg_pcg_slab cannot be made resident"); return -1; }
-    // the same grid on every rank (the partial-sum layout depends on it): all blocks the device can hold
-    int grid = bps * c->sm_count;
-    if (grid > 4096) grid = 4096;
-    const int nb_res = std::min<long long>(nblk(s.nn, 256), 1024);
-    if ((r = ensure_buf(&c->red, &c->red_cap, 8192, c->stream))) return r;
-    double *dout = reinterpret_cast<double *>(c->dscal + 24);
-    double *dres = reinterpret_cast<double *>(c->dscal + 16);
-    double norm = 0, r0_norm = 0;
-    bool converged = false;
-    for (int it = 0; it < p->nr_max_it; it++) {
-        info->nr_iters++;
-        // the Newton linearisation and the Galerkin diagonals are computed by every rank for the whole mesh (cheap, pointwise)
-        k_spd_linearise<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->rho, c->phi, S->diag0, p->phi0, p->Te0, p->n0,
-                                                                S->R, S->diagJ, S->minv, S->delta);
-        LAUNCH_CHECK(c);
-        for (int l = 1; l < H->nlev; l++) {
-            if (l == 1) k_mg_diag_from_fine<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, S->diagJ, H->L[1]);
-            else k_mg_diag_from_level<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
-            LAUNCH_CHECK(c);
-        }
-        CK(cudaMemsetAsync(S->d0, 0, (size_t)s.nn * sizeof(double), c->stream));
-        MgPcgArgs a;
-        a.s = s; a.nlev = H->nlev; a.coarse_sweeps = MG_COARSE_SWEEPS; a.nbmask = H->nbmask;
-        // Levels with at most MG_SLAB_REDUNDANT_NODES nodes (override: ESPIC_MG_SLAB_REDUNDANT_NODES, 0 = only the coarsest)
-        // are solved by every rank in full instead of by slabs: 2 inter-GPU barriers less per level and V-cycle for redundant
-        // work on a small level.  Measured on 4 B200, 256^3 (profiles/r1_slab_redundant_levels_n4.txt): 530 us per CG
-        // iteration with only the coarsest level redundant, 508 with <= 8192 nodes, 493 with <= 65536, 492 with <= 524288.
-        {
-            long long dims[MG_MAX_LEVELS][3];
-            for (int l = 0; l < H->nlev; l++) { dims[l][0] = H->L[l].ni; dims[l][1] = H->L[l].nj; dims[l][2] = H->L[l].nk; }
-            a.first_redundant = mg_first_redundant(H->nlev, dims, mg_slab_redundant_limit());
-        }
-        for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
-        a.L[0].diag = S->diagJ; a.L[0].minv = S->minv; a.L[0].x = S->x0;
-        a.delta = S->delta; a.r = S->R; a.z = S->z; a.d0 = S->d0; a.d1 = S->d1; a.q = S->q;
-        a.part = S->part; a.max_it = p->max_it; a.tol = p->tol; a.out = dout;
-        a.prof = getenv("ESPIC_MG_PROFILE") ? c->dscal + 40 : nullptr;
-        // same inexact-Newton forcing as the single-GPU solver (identical on every rank: it derives from all-reduced norms)
-        a.rel_tol = (it == 0 && getenv("ESPIC_MG_EXACT_NEWTON") == nullptr) ? std::min(std::max(H->newton_ratio, 0.0), 1e-2) : 0.0;
-        // nobody may store into a neighbour's pool before that neighbour has finished preparing this Newton step
-        if ((r = espic_comm_allgather_doubles(c, S->part, 1))) return r;
-        OwnSlab own = S->own;
-        void *args[] = {&a, &own, &S->epoch};
-        CK(cudaLaunchCooperativeKernel((void *)k_mg_pcg_slab, dim3(grid), dim3(MG_BLOCK), args, 0, c->stream));
-        LAUNCH_CHECK(c);
-        // every rank needs the whole update: gather the slabs of delta
-        if ((r = espic_comm_allgather_doubles(c, S->delta, (size_t)slab_nn))) return r;
-        k_spd_update<<<nb_res, 256, 0, c->stream>>>(s, c->node_type, S->delta, c->phi, c->red);
-        LAUNCH_CHECK(c);
-        k_sum_final<<<1, 256, 0, c->stream>>>(c->red, nb_res, dres);
-        LAUNCH_CHECK(c);
-        double *h = reinterpret_cast<double *>(c->hpin) + 24;
-        CK(cudaMemcpyAsync(h, dout, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        double sum;
-        if ((r = read_scalar(c, dres, &sum))) return r;
-        info->lin_iters += (long long)h[1];
-        if (h[0] == 0.0) fprintf(stderr, "PCG failed to converge, norm(g) = %g\n", h[2]);
-        norm = sqrt(sum / (double)s.nn);
-        if (it == 0) r0_norm = h[3];
-        if (it == 1 && r0_norm > 0) H->newton_ratio = h[3] / r0_norm;
-        const double lin_stop = (a.rel_tol > 0) ? std::max(p->tol, a.rel_tol * h[3]) : p->tol;
-        if (norm < p->nr_tol && lin_stop <= p->tol) { converged = true; break; }
-    }
+    for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
+    a.type = c->node_type; a.rho = c->rho; a.phi = S->phi; a.phi_user = c->phi;
+    a.r = S->R; a.delta = S->delta; a.d0 = S->d0; a.d1 = S->d1; a.diagf = S->diagf; a.z = S->z;
+    a.part = S->part;
+    a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
+    a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
+    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma;
+    a.out = dout;
+    a.prof = kn.profile ? c->dscal + 40 : nullptr;
+    OwnSlab own = S->own;
+    void *args[] = {&a, &own, &S->epoch};
+    CK(cudaLaunchCooperativeKernel((void *)k_mg_newton_slab, dim3(grid), dim3(MG_THREADS), args, smem, c->stream));
+    LAUNCH_CHECK(c);
+    // every rank needs the whole potential: gather the slabs.  The collective is also the fence between solves: no rank can
+    // start the next solve's peer stores before every rank has left this kernel.
+    if ((r = espic_comm_allgather_doubles(c, c->phi, (size_t)slab_nn))) return r;
     for (int level = 0; level < 3; level++) {
         k_mirror<<<nblk(s.nn, 256), 256, 0, c->stream>>>(s, c->node_type, c->phi, level);
         LAUNCH_CHECK(c);
     }
-    if (!converged) printf("NR+PCG failed to converge, norm = %g\n", norm);
-    info->converged = converged;
-    info->residual = norm;
-    if (getenv("ESPIC_MG_PROFILE") && c->rank == 0) {
-        unsigned long long hp[8];
-        CK(cudaMemcpyAsync(hp, c->dscal + 40, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaMemsetAsync(c->dscal + 40, 0, sizeof(hp), c->stream));
-        fprintf(stderr, "[mg slab profile] its=%lld  us/it: down0 %.1f  down %.1f  coarsest %.1f  up %.1f  up0+rz %.1f  dq %.1f  r %.1f\n",
-                info->lin_iters, hp[0] * 1e-3 / info->lin_iters, hp[1] * 1e-3 / info->lin_iters, hp[2] * 1e-3 / info->lin_iters,
-                hp[3] * 1e-3 / info->lin_iters, hp[4] * 1e-3 / info->lin_iters, hp[5] * 1e-3 / info->lin_iters, hp[6] * 1e-3 / info->lin_iters);
+    double *h = reinterpret_cast<double *>(c->hpin) + 64;
+    CK(cudaMemcpyAsync(h, dout, 32 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h[MGN_OUT_ABORT] != 0.0) {
+        espic_set_error("ESPIC_SOLVE_PCG_MG_SLAB: an inter-GPU barrier timed out (a peer rank did not arrive); the solve was abandoned");
+        return -1;
     }
+    mg_report(c, h, p, info, "mg slab");
+    if (kn.profile && c->rank == 0) return mg_print_profile(c, info->lin_iters, "mg slab");
     return 0;
 }
