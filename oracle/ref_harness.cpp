@@ -11,6 +11,7 @@
  * Commands: advance | deposit | rho | ef | solve_gs:MAXIT:TOL | solve_pcg:MAXIT:TOL | solve_qn
  *           | solve:MAXIT:TOL (ch2) | sample:SP:VDRIFT:DEN:SEED | loadqs:SP:DEN:NI:NJ:NK:HALF
  *           | average:SP | time:WHAT:REPS (prints seconds per call)
+ *           | fields (ref_ch3 only: the reference's Output::fields, ch3/ver2/Output.cpp:12-79, writes ./results/fields_<ts>.vti)
  * State file layout: see tests/statefile.py (single source of truth for the format).
  */
 #include <cstdio>
@@ -27,6 +28,9 @@
 #include "PotentialSolver.h"
 #ifndef REF_CH2
 #include "Source.h"
+#endif
+#ifdef REF_OUTPUT
+#include "Output.h"
 #endif
 
 using namespace std;
@@ -235,6 +239,12 @@ int main(int argc, char **argv)
 #ifdef REF_MT
         else if (op == "threads") { world.setNumThreads(atoi(c[1].c_str())); }
 #endif
+#endif
+#ifdef REF_OUTPUT
+        else if (op == "fields") {
+            /* den / den_ave / phi / rho / ef / node_vol / object_id as loaded (or as the preceding commands left them) */
+            Output::fields(world, species);
+        }
 #endif
         else if (op == "time") {
             /* time:advance|deposit:REPS -> seconds per call on stdout (cpu_baseline "reference" kind) */

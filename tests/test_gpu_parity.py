@@ -359,11 +359,113 @@ def test_multigrid_pcg_matches_jacobi_pcg(dims, n0):
     assert ja.diag[0] == 1.0 and mg.diag[0] == 1.0
     assert_close(mg.phi, ja.phi, 1e-10, "phi: multigrid vs Jacobi preconditioner")
     assert_close(mg.ef, ja.ef, 1e-9, "ef")
-    assert b.info["nr_iters"] == a.info["nr_iters"]
+    # the multigrid solver is an INEXACT Newton iteration (Eisenstat-Walker forcing): more, cheaper Newton steps are expected
     if dims[0] * dims[1] * dims[2] > 4096:      # smaller meshes have no coarse level: the cycle degenerates to Jacobi
         assert b.info["lin_iters"] < a.info["lin_iters"], (b.info, a.info)
     if dims[0] >= 64:
         assert b.info["lin_iters"] * 3 < a.info["lin_iters"], (b.info, a.info)
+
+
+@pytest.mark.parametrize("dims,n0", [((21, 21, 41), 1e10), ((33, 20, 47), 1e12), ((64, 64, 64), 1e12)])
+def test_mg_tight_parity_vs_oracle(dims, n0):
+    """The SHIPPED solver (ESPIC_SOLVE_PCG_MG: inexact Newton + multigrid PCG, FP32 preconditioner storage) against the oracle's
+    restatement of the reference's own solveGS on the same equations, both converged far below the production tolerance:
+    phi within 1e-10 relative (north_star parity bound), E within 1e-9, on the shipped ch3 mesh, a ragged anisotropic mesh
+    (semi-coarsening in y) and 64^3 (three multigrid levels)."""
+    n = 200000
+    w, sp = cases.sphere_case(seed=91, ni=dims[0], nj=dims[1], nk=dims[2], n=n, amp=0.0, mpw=n0 * 0.016 / n)
+    w.set_reference_values(0.0, 1.5, n0)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    w.solve_qn()
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    g = GpuEngine(st)
+    g.e.nr_tol = 1e-10
+    got = g.run(["solve_mg:20000:1e-9", "ef"])
+    info = w.solve_gs(400000, 1e-9)
+    w.compute_ef()
+    assert info["converged"] == 1 and got.diag[0] == 1.0, (info, g.info)
+    assert_close(got.phi, w.phi, 1e-10, "phi: multigrid Newton-PCG vs the reference's nonlinear SOR")
+    assert_close(got.ef, w.ef, 1e-9, "ef")
+    # and at the production tolerance the answer is within that tolerance's reach of the converged one
+    g2 = GpuEngine(st)
+    prod = g2.run(["solve_mg:5000:1e-4"])
+    assert prod.diag[0] == 1.0
+    assert_close(prod.phi, w.phi, 1e-8, "phi at tol 1e-4")
+
+
+def test_mg_solve_is_a_pure_function_of_its_inputs():
+    """the forcing terms come from the current solve only -- the same (rho, phi) gives the same phi bit for bit,
+    whatever was solved before on the same context."""
+    n = 100000
+    w, sp = cases.sphere_case(seed=92, ni=33, nj=33, nk=65, n=n, amp=0.0, mpw=1e12 * 0.016 / n)
+    w.set_reference_values(0.0, 1.5, 1e12)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    w.solve_qn()
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    es = _espic()
+    a = GpuEngine(st)
+    first = a.run(["solve_mg:5000:1e-4"]).phi
+    # same context: disturb its history with a different problem, then restore the inputs and solve again
+    a.e.set_field(es.RHO, st.rho * 1.3)
+    a.run(["solve_mg:5000:1e-4"])
+    a.e.set_field(es.RHO, st.rho)
+    a.e.set_field(es.PHI, st.phi)
+    again = a.run(["solve_mg:5000:1e-4"]).phi
+    assert_bits(again, first, "phi of two solves of the same inputs on one context")
+    b = GpuEngine(st)
+    assert_bits(b.run(["solve_mg:5000:1e-4"]).phi, first, "phi of the same solve on a fresh context")
+
+
+def test_gs_linear_fallback_numbers():
+    """solveGSLinear (PotentialSolver.cpp:433-461), the fall-back of the reference-exact PCG: a case where the reference's CG
+    gives up on two Newton steps (it stagnates on the non-symmetric matrix), its linear-GS fall-back CONVERGES (26 sweeps each)
+    and the Newton iteration then finishes -- so the NUMBERS can be compared with the oracle, not only the path taken
+    (VERDICT r1 a16).  The GPU sweeps red-black, the reference lexicographically: both reach tol, phi agrees at the level the
+    Newton stopping test (update < 1e-3) leaves."""
+    n0, n = 1e13, 6000
+    w, sp = cases.sphere_case(seed=93, n=n, amp=0.0, mpw=n0 * 0.016 / n)      # 9 x 9 x 13
+    w.set_reference_values(0.0, 1.5, n0)
+    sp.compute_number_density()
+    w.compute_charge_density([sp])
+    w.solve_qn()
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    info = w.solve_nrpcg(80, 1e-6)
+    assert info["converged"] == 1 and info["gs_fallbacks"] >= 1 and info["gs_iters"] < 80 * info["gs_fallbacks"], info
+    g = GpuEngine(st, pcg_ref=True)
+    got = g.run(["solve_pcg:80:1e-6"])
+    assert got.diag[0] == 1.0 and g.info["gs_fallbacks"] >= 1, g.info
+    assert g.info["gs_iters"] < 80 * g.info["gs_fallbacks"], "the fall-back converged on the GPU too"
+    assert_close(got.phi, w.phi, 1e-6, "phi after Newton steps that went through the linear-GS fall-back")
+
+
+@pytest.mark.skipif(not sf.have_ref("ref_ch3"), reason="oracle/_ref/ref_ch3 (the compiled reference) was not built")
+def test_full_mesh_parity_against_the_compiled_reference(tmp_path):
+    """BASELINE configs[2]/[3] mesh (128^3) against the COMPILED, unmodified reference itself (oracle/_ref/ref_ch3 travels to the
+    GPU box): 2e6 particles through two steps of advance -> deposit -> rho -> computeEF in a non-trivial potential.  Bars:
+    particles, their order and count bit-exact; density 1e-12 of the maximum; E from the same phi bit-exact."""
+    es = _espic()
+    n, mesh = 2_000_000, 128
+    rng = np.random.default_rng(128)
+    w = cases.sphere_world(mesh, mesh, mesh)
+    w.set_reference_values(0.0, 1.5, 1e12)
+    cases.smooth_phi(w, rng, amp=20.0)
+    w.compute_ef()
+    sp = cases.orc.Species(w, 16 * cases.AMU, cases.QE, mpw0=8000.0, cap=n + 16)
+    sp.set_particles(cases.random_particles(w, rng, n, mpw=8000.0, near_walls=0.02))
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    cmds = ["ef", "advance", "deposit", "rho", "advance", "deposit", "rho"]
+    ref = sf.run_ref("ref_ch3", st, cmds, tmp_path)
+    got = GpuEngine(st).run(cmds)
+    assert_bits(got.ef, ref.ef, "computeEF on the 128^3 mesh")
+    a, b = got.species[0]["part"], ref.species[0]["part"]
+    assert a.shape == b.shape and a.shape[1] < n, "some particles died (sphere / walls), same count"
+    assert_bits(a, b, "particles after two steps: values and order")
+    assert_close(got.species[0]["den"], ref.species[0]["den"], DEN_RTOL, "number density")
+    assert_close(got.rho, ref.rho, DEN_RTOL, "rho")
+    assert_bits(got.node_vol, ref.node_vol, "node volumes")
+    assert np.array_equal(got.object_id, ref.object_id)
 
 
 def test_pcg_iteration_count_matches_reference():

@@ -263,8 +263,6 @@ def _check_ch3_statistics(got, ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added at the end of round 1 with no GPU minutes left: first run on a B200 pending "
-                                        "(an XPASS is the expected outcome; remove this marker after it)")
 def test_reference_ch3_main_with_pcg_solver_statistics(tmp_path):
     """BASELINE configs[1]: the ch3 sphere program with the nonlinear PCG Poisson solver on the shipped mesh.  bin/main_ch3_pcg is the
     reference's ch3/ver2/Main.cpp with the one expression `SolverType::GS,20000,1e-4` replaced by `SolverType::PCG,1000,1e-4` on its
@@ -446,3 +444,31 @@ def test_reference_ch4_main_neutral_flow_statistics(tmp_path):
         subprocess.run([exe], cwd=str(tmp_path), stdout=log, stderr=subprocess.STDOUT, timeout=900, check=True,
                        env=dict(os.environ, ESPIC_SEED="4242"))
     _check_ch4_statistics(summarise(str(tmp_path)), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not sf.have_ref("ref_ch3"), reason="oracle/_ref/ref_ch3 (the compiled reference) was not built")
+def test_output_fields_vti_matches_the_reference_writer(tmp_path):
+    """Output::fields (ch3/ver2/Output.cpp:12-79): the .vti the shim writes at the last step of a run through the class API
+    against the file the REFERENCE's own Output::fields writes from the same field values (oracle/_ref/ref_ch3 `fields`,
+    fed with the state the shim dumped): every token of every DataArray, header included."""
+    import glob
+    steps = 6
+    st = run_check(tmp_path, "sphere", 9, 9, 13, steps, "QN", 1e-4)
+    mine = glob.glob(str(tmp_path / "results" / "fields_*.vti"))
+    assert len(mine) == 1
+    ref_dir = tmp_path / "ref"
+    os.makedirs(str(ref_dir / "results"))
+    fin = str(ref_dir / "in.state")
+    st.flags = 3                # geometry from addSphere/addInlet, phi as dumped
+    sf.write_state(fin, st)
+    r = subprocess.run([os.path.join(sf.REF_DIR, "ref_ch3"), fin, str(ref_dir / "out.state"), "fields"], cwd=str(ref_dir),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    theirs = glob.glob(str(ref_dir / "results" / "fields_*.vti"))
+    assert len(theirs) == 1
+    a = open(mine[0]).read().split()
+    b = open(theirs[0]).read().replace("nd.sp0", "nd.O+").replace("nd-ave.sp0", "nd-ave.O+").split()
+    assert len(a) == len(b) and len(a) > 9 * 9 * 13 * 9, (len(a), len(b))
+    bad = [i for i in range(len(a)) if a[i] != b[i]]
+    assert not bad, "first differing tokens: %s" % [(i, a[i], b[i]) for i in bad[:5]]

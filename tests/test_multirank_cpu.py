@@ -123,7 +123,7 @@ def test_shift_is_rank_count_independent_bound():
 def test_bench_weak_scaling_bookkeeping():
     """bench.py: per-rank particle seeds differ, mpw = n0 * V / (particles_per_gpu * world)."""
     src = open(os.path.join(sf.ROOT, "bench.py")).read()
-    assert "12345 + rank" in src and "n_total = n_local * (world" in src and "mpw = N0 * box_vol / n_total" in src
+    assert "seed + 1000 * rank" in src and "n_total = n_local * world" in src and "mpw = N0 * box_vol / n_total" in src
 
 
 def test_exact_division_identity():
