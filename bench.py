@@ -320,11 +320,13 @@ def reference_cpu_step(mesh, n_total, steps, warmup, n_sample, gs_sweeps, budget
 class Case:
     """One engine + one ion species for a configuration of the sphere case, warm-started (untimed), with the timed PIC step."""
 
-    def __init__(self, ctx, mesh, n_local, n_total, solver_name, sort_every=8, fixed_point=False, fuse=False, decomp=False, seed=12345):
+    def __init__(self, ctx, mesh, n_local, n_total, solver_name, sort_every=8, fixed_point=False, fuse=False, decomp=False, seed=12345,
+                 sort_order="xtoc"):
         es, torch, dist = ctx["es"], ctx["torch"], ctx["dist"]
         rank, world, local_rank, dev = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dev"]
         self.ctx, self.es, self.mesh, self.n_local, self.n_total = ctx, es, mesh, n_local, n_total
         self.solver_name, self.sort_every, self.fuse = solver_name, sort_every, fuse
+        self.sort_order = es.SORT_DRIFT_Z if sort_order == "drift" else es.SORT_XTOC
         box_vol = (XM[0] - X0[0]) * (XM[1] - X0[1]) * (XM[2] - X0[2])
         self.mpw = mpw = N0 * box_vol / n_total
         solver = {"pcg": es.SOLVE_PCG, "mg": es.SOLVE_PCG_MG, "mgslab": es.SOLVE_PCG_MG_SLAB, "gs": es.SOLVE_GS, "qn": es.SOLVE_QN}[solver_name]
@@ -366,7 +368,7 @@ class Case:
         self.dmode = es.DEPOSIT_FIXED if fixed_point else es.DEPOSIT_FP64
         self.pflags = ((es.PUSH_FUSE_DEPOSIT | (es.PUSH_FIXED_POINT if fixed_point else 0)) if fuse else 0) | (es.PUSH_MIGRATE if self.decomp else 0)
         log("particles resident: %d on rank %d (%d^3 mesh)" % (n_local, rank, mesh))
-        e.sort_by_cell(sp)
+        e.sort_particles(sp, self.sort_order)
         e.deposit(sp, self.dmode)
         e.compute_charge_density()
         e.solve(es.SOLVE_QN, 1, 1.0)                     # the reference's own initial guess (ctor -> solveQN)
@@ -392,7 +394,7 @@ class Case:
             ev[1].record()
         k_ms = e.last_push_ms() if rec is not None else 0.0    # CUDA events around the k_push launch itself, on the launching stream
         if self.sort_every > 0 and i % self.sort_every == 0 and not self.fuse:
-            e.sort_by_cell(sp)       # between push and deposit: the scatter sees perfectly ordered particles
+            e.sort_particles(sp, self.sort_order)       # between push and deposit: the scatter sees perfectly ordered particles
         if ev:
             ev[2].record()
         e.deposit(sp, self.dmode)
@@ -600,6 +602,8 @@ def main():
                     help="pcg: Newton + Jacobi-PCG (the reference's preconditioner); mg: same with a multigrid V-cycle "
                          "preconditioner, solved by every rank; mgslab: the multigrid solve decomposed into one k-slab per rank")
     ap.add_argument("--sort-every", type=int, default=8)
+    ap.add_argument("--sort-order", default="xtoc", choices=["drift", "xtoc"],
+                    help="key order of the periodic cell sort: drift = k fastest (a beam drifting along z keeps it), xtoc = ch4 World::XtoC order")
     ap.add_argument("--fixed-point", action="store_true", help="bit-reproducible int64 deposition")
     ap.add_argument("--decomp", action="store_true",
                     help="N>1: spatial decomposition into k-slabs with particle migration (espic_migrate, ch9/MPI's scheme) "
@@ -648,7 +652,7 @@ def main():
         workload += "-kslab-migration"
 
     # ---------------------------------------------------------------- headline: BASELINE configs[3], weak scaling
-    head = Case(ctx, n_mesh, n_local, n_total, args.solver, args.sort_every, args.fixed_point, args.fuse, args.decomp)
+    head = Case(ctx, n_mesh, n_local, n_total, args.solver, args.sort_every, args.fixed_point, args.fuse, args.decomp, sort_order=args.sort_order)
     e, sp = head.e, head.sp
     # warm-up first, then sample clocks over the timed steps only
     for i in range(args.warmup):
@@ -755,7 +759,7 @@ def main():
                 if need > free:
                     extra[tag] = {"skipped": "needs %.0f GB of device memory, %.0f GB free" % (need / 1e9, free / 1e9)}
                     return
-                cs = Case(ctx, mesh, n_loc, n_tot, solver_name, args.sort_every)
+                cs = Case(ctx, mesh, n_loc, n_tot, solver_name, args.sort_every, sort_order=args.sort_order)
                 r = cs.timed(ks, 3)
                 pk = r["kernel_ms"]
                 extra[tag] = {"value": r["value"], "unit": "particle-pushes/s", "ms_per_step": r["ms_per_step"], "steps": ks, "warmup": 3,
@@ -792,7 +796,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "mesh": [n_mesh] * 3, "particles_per_gpu": n_local, "solver": args.solver,
-                       "solver_tol": head.tol, "dt": DT, "sort_every": args.sort_every,
+                       "solver_tol": head.tol, "dt": DT, "sort_every": args.sort_every, "sort_order": args.sort_order,
                        "deposit": "fixed-point int64" if args.fixed_point else "fp64 atomics",
                        "parallelism": "%s x%d, NCCL density all-reduce, %s" % (
                            "k-slab spatial decomposition with particle migration (%.3g particles sent per rank per step)" % res["migrated_per_step"]

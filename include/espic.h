@@ -100,8 +100,14 @@ enum { ESPIC_DEPOSIT_FP64 = 0,     /* FP64 atomics (order-dependent rounding) */
        ESPIC_DEPOSIT_FIXED = 1 };  /* int64 fixed-point accumulation: bit-reproducible for any order / GPU count */
 int espic_deposit(espic_ctx *ctx, int sp, int mode);
 
-/* periodic maintenance, no reference counterpart: reorder particles by cell for gather/scatter locality */
-int espic_sort_by_cell(espic_ctx *ctx, int sp);
+/* periodic maintenance, no reference counterpart: reorder particles by cell for gather/scatter locality (counting sort; the
+ * particle MULTISET is unchanged, the order is not the reference's any more).  The cell index is that of ch4 World::XtoC
+ * (ch4/World.h:88-98), refined by 8 slabs of the cell along z. */
+enum { ESPIC_SORT_XTOC = 0,        /* key = XtoC cell index: k slowest, i fastest */
+       ESPIC_SORT_DRIFT_Z = 1 };   /* same cells, k FASTEST: a population drifting along z keeps this order from step to step
+                                      (only the thermal x/y motion breaks runs), so sorts can be rare and cheap */
+int espic_sort_by_cell(espic_ctx *ctx, int sp);                 /* = espic_sort_particles(ctx, sp, ESPIC_SORT_XTOC) */
+int espic_sort_particles(espic_ctx *ctx, int sp, int order);
 
 /* ColdBeamSource::sample (Source.cpp:4-27) with Philox4x32-10 counters (seed, stream, step, particle). */
 int espic_inject_cold_beam(espic_ctx *ctx, int sp, double v_drift, double den, double dt,

@@ -37,6 +37,7 @@ struct Species {
     int acc_shift = 0;                 // fixed point: value * 2^shift
     double mpw_max = 0;                // upper bound of any mpw seen (fixed-point scale)
     int pushes_since_sort = 1 << 20;   // how scrambled the cell order is: chooses the deposit kernel
+    int sort_order = 0;                // key order of the most recent sort (ESPIC_SORT_*)
     // ch4 Particle::dt by index (espic_surface.cuh): particles [0, n_settled) went through the last advance (dt = 0),
     // particles [n_settled, np) were added since (dt = world dt)
     long long n_settled = 0;

@@ -244,18 +244,19 @@ struct OwnSlab {
 // The passes spread one node over 8 consecutive lanes (the 8 children of an aggregate, or the 7 stencil terms of a node)
 // and combine with three shuffles; the sum order is fixed, so results are reproducible.
 
-template <typename F>
-__device__ __forceinline__ double mg_offdiag(const MgLevel &L, int i, int j, int k, long long u, F f)
+// Index arithmetic of the coarse passes is 32 bit (a coarse level has < 2^31 nodes) and every load is issued before the first
+// use: a pass is one memory round trip per node, not a chain (node data -> branch -> neighbour data).
+
+struct MgIdx { int i, j, k; };
+__device__ __forceinline__ MgIdx mg_ijk(const MgLevel &L, unsigned u)
 {
-    const long long sj = L.ni, sk = (long long)L.ni * L.nj;
-    double a = 0;
-    if (i > 0) a += (double)L.cx[u - 1] * f(u - 1);
-    if (i + 1 < L.ni) a += (double)L.cx[u] * f(u + 1);
-    if (j > 0) a += (double)L.cy[u - sj] * f(u - sj);
-    if (j + 1 < L.nj) a += (double)L.cy[u] * f(u + sj);
-    if (k > 0) a += (double)L.cz[u - sk] * f(u - sk);
-    if (k + 1 < L.nk) a += (double)L.cz[u] * f(u + sk);
-    return a;
+    const unsigned ni = (unsigned)L.ni, nij = (unsigned)(L.ni * L.nj);
+    MgIdx q;
+    q.k = (int)(u / nij);
+    const unsigned r = u - (unsigned)q.k * nij;
+    q.j = (int)(r / ni);
+    q.i = (int)(r - (unsigned)q.j * ni);
+    return q;
 }
 
 __device__ __forceinline__ double mg_sum8(double v)
@@ -273,129 +274,198 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
                                         bool to_all)
 {
     const long long first = own.lo(C, lf + 1), total = (own.hi(C, lf + 1) - first) * 8;
+    const int sj = F.ni, sk = F.ni * F.nj;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long I = first + (w >> 3);
+        const unsigned I = (unsigned)(first + (w >> 3));
         const int c = (int)(w & 7);
         const bool live = w < total;
         double res = 0;
         if (live) {
-            const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
+            const MgIdx q = mg_ijk(C, I);
             const int di = c & 1, dj = (c >> 1) & 1, dk = c >> 2;
-            const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
+            const int i = (q.i << C.fi) + di, j = (q.j << C.fj) + dj, k = (q.k << C.fk) + dk;
             if (di <= C.fi && dj <= C.fj && dk <= C.fk && i < F.ni && j < F.nj && k < F.nk) {
-                const long long u = ((long long)k * F.nj + j) * F.ni + i;
-                const double mi = F.minv[u];
-                double xu = 0;
-                if (mi != 0) {
-                    const double bu = F.b[u];
-                    xu = MG_OMEGA * bu * mi;
-                    const double off = MG_OMEGA * mg_offdiag(F, i, j, k, u, [&](long long v) { return (double)F.b[v] * (double)F.minv[v]; });
-                    res = bu - ((double)F.diag[u] * xu - off);
-                }
-                own.st(F.x, u, F, lf, (mgf)xu);
+                const int u = (k * F.nj + j) * F.ni + i;
+                const bool xm = i > 0, xp = i + 1 < F.ni, ym = j > 0, yp = j + 1 < F.nj, zm = k > 0, zp = k + 1 < F.nk;
+                // everything this child needs, loaded up front (index predicates only)
+                const mgf mi = F.minv[u], bu = F.b[u], dg = F.diag[u];
+                const mgf lxm = xm ? F.cx[u - 1] : (mgf)0, lxp = xp ? F.cx[u] : (mgf)0;
+                const mgf lym = ym ? F.cy[u - sj] : (mgf)0, lyp = yp ? F.cy[u] : (mgf)0;
+                const mgf lzm = zm ? F.cz[u - sk] : (mgf)0, lzp = zp ? F.cz[u] : (mgf)0;
+                const mgf bxm = xm ? F.b[u - 1] : (mgf)0, bxp = xp ? F.b[u + 1] : (mgf)0;
+                const mgf bym = ym ? F.b[u - sj] : (mgf)0, byp = yp ? F.b[u + sj] : (mgf)0;
+                const mgf bzm = zm ? F.b[u - sk] : (mgf)0, bzp = zp ? F.b[u + sk] : (mgf)0;
+                const mgf mxm = xm ? F.minv[u - 1] : (mgf)0, mxp = xp ? F.minv[u + 1] : (mgf)0;
+                const mgf mym = ym ? F.minv[u - sj] : (mgf)0, myp = yp ? F.minv[u + sj] : (mgf)0;
+                const mgf mzm = zm ? F.minv[u - sk] : (mgf)0, mzp = zp ? F.minv[u + sk] : (mgf)0;
+                const double xu = MG_OMEGA * (double)bu * (double)mi;
+                const double off = MG_OMEGA * ((double)lxm * ((double)bxm * (double)mxm) + (double)lxp * ((double)bxp * (double)mxp) +
+                                               (double)lym * ((double)bym * (double)mym) + (double)lyp * ((double)byp * (double)myp) +
+                                               (double)lzm * ((double)bzm * (double)mzm) + (double)lzp * ((double)bzp * (double)mzp));
+                res = mi != (mgf)0 ? (double)bu - ((double)dg * xu - off) : 0.0;
+                own.st(F.x, (long long)u, F, lf, (mgf)xu);
             }
         }
         res = mg_sum8(res);
         if (c == 0 && live) {
-            if (to_all) own.st_all(C.b, I, (mgf)res);
-            else own.st(C.b, I, C, lf + 1, (mgf)res);
+            if (to_all) own.st_all(C.b, (long long)I, (mgf)res);
+            else own.st(C.b, (long long)I, C, lf + 1, (mgf)res);
         }
-    }
-}
-
-// stencil term c of node u on a coarse level: c = 0 centre (b - diag*v), c = 1..6 the six links, c = 7 nothing
-template <typename F>
-__device__ __forceinline__ double mg_term(const MgLevel &L, int c, int i, int j, int k, long long u, F val, double &centre)
-{
-    const long long sj = L.ni, sk = (long long)L.ni * L.nj;
-    switch (c) {
-        case 0: centre = val(u, i, j, k); return (double)L.b[u] - (double)L.diag[u] * centre;
-        case 1: return i > 0 ? (double)L.cx[u - 1] * val(u - 1, i - 1, j, k) : 0.0;
-        case 2: return i + 1 < L.ni ? (double)L.cx[u] * val(u + 1, i + 1, j, k) : 0.0;
-        case 3: return j > 0 ? (double)L.cy[u - sj] * val(u - sj, i, j - 1, k) : 0.0;
-        case 4: return j + 1 < L.nj ? (double)L.cy[u] * val(u + sj, i, j + 1, k) : 0.0;
-        case 5: return k > 0 ? (double)L.cz[u - sk] * val(u - sk, i, j, k - 1) : 0.0;
-        case 6: return k + 1 < L.nk ? (double)L.cz[u] * val(u + sk, i, j, k + 1) : 0.0;
-        default: return 0.0;
     }
 }
 
 // Up pass on a coarse level F (index lf) with the correction e of the next coarser level C:
 //   xn = (x + P e) + w D^-1 (b - K (x + P e))
+// A big level takes one thread per node, a small one 8 lanes per node (one stencil term each, combined with three shuffles:
+// what matters on the small levels is the length of a thread's dependent chain, not bandwidth).
 template <class Own>
 __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, const MgLevel &C, const mgf *e,
                                       long long t0, long long stride)
 {
     const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
-    auto val = [&](long long v, int vi, int vj, int vk) {
-        // links to nodes without unknowns are zero on coarse levels, so no mask is needed on the neighbours
-        return (double)F.x[v] + (double)e[((long long)(vk >> C.fk) * C.nj + (vj >> C.fj)) * C.ni + (vi >> C.fi)];
+    const int sj = F.ni, sk = F.ni * F.nj, csj = C.ni, csk = C.ni * C.nj;
+    // value of the prolongated iterate at node (vi,vj,vk) = flat v; links to nodes without unknowns are zero on coarse levels,
+    // so no mask is needed on the neighbours
+    auto val = [&](int v, int vi, int vj, int vk) {
+        return (double)F.x[v] + (double)e[(vk >> C.fk) * csk + (vj >> C.fj) * csj + (vi >> C.fi)];
     };
-    if (count * 2 > stride) {          // a big level: one thread per node keeps every lane busy
-        for (long long u = first + t0; u < first + count; u += stride) {
-            const double mi = F.minv[u];
-            double out = 0;
-            if (mi != 0) {
-                const int i = (int)(u % F.ni), j = (int)((u / F.ni) % F.nj), k = (int)(u / ((long long)F.ni * F.nj));
-                double centre = 0, tot = 0;
-#pragma unroll
-                for (int c = 0; c < 7; c++) tot += mg_term(F, c, i, j, k, u, val, centre);
-                out = centre + MG_OMEGA * mi * tot;
-            }
-            own.st(F.xn, u, F, lf, (mgf)out);
+    if (count * 2 > stride) {
+        for (long long uu = first + t0; uu < first + count; uu += stride) {
+            const int u = (int)uu;
+            const MgIdx q = mg_ijk(F, (unsigned)u);
+            const int i = q.i, j = q.j, k = q.k;
+            const bool xm = i > 0, xp = i + 1 < F.ni, ym = j > 0, yp = j + 1 < F.nj, zm = k > 0, zp = k + 1 < F.nk;
+            const mgf mi = F.minv[u], bu = F.b[u], dg = F.diag[u];
+            const mgf lxm = xm ? F.cx[u - 1] : (mgf)0, lxp = xp ? F.cx[u] : (mgf)0;
+            const mgf lym = ym ? F.cy[u - sj] : (mgf)0, lyp = yp ? F.cy[u] : (mgf)0;
+            const mgf lzm = zm ? F.cz[u - sk] : (mgf)0, lzp = zp ? F.cz[u] : (mgf)0;
+            const double vc = val(u, i, j, k);
+            const double vxm = xm ? val(u - 1, i - 1, j, k) : 0.0, vxp = xp ? val(u + 1, i + 1, j, k) : 0.0;
+            const double vym = ym ? val(u - sj, i, j - 1, k) : 0.0, vyp = yp ? val(u + sj, i, j + 1, k) : 0.0;
+            const double vzm = zm ? val(u - sk, i, j, k - 1) : 0.0, vzp = zp ? val(u + sk, i, j, k + 1) : 0.0;
+            const double tot = ((double)bu - (double)dg * vc) + (double)lxm * vxm + (double)lxp * vxp + (double)lym * vym + (double)lyp * vyp +
+                               (double)lzm * vzm + (double)lzp * vzp;
+            own.st(F.xn, uu, F, lf, (mgf)(mi != (mgf)0 ? vc + MG_OMEGA * (double)mi * tot : 0.0));
         }
         return;
     }
-    const long long total = count * 8;          // a small level: 8 lanes per node, one stencil term each
+    const long long total = count * 8;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
-        const long long u = first + (w >> 3);
+        const int u = (int)(first + (w >> 3));
         const int c = (int)(w & 7);
         const bool live = w < total;
-        double term = 0, centre = 0, mi = 0;
+        double term = 0, centre = 0;
+        mgf mi = 0;
         if (live) {
+            const MgIdx q = mg_ijk(F, (unsigned)u);
+            const int i = q.i, j = q.j, k = q.k;
             mi = F.minv[u];
-            if (mi != 0) {
-                const int i = (int)(u % F.ni), j = (int)((u / F.ni) % F.nj), k = (int)(u / ((long long)F.ni * F.nj));
-                term = mg_term(F, c, i, j, k, u, val, centre);
+            // term c: 0 centre (b - diag*v), 1..6 the six links, 7 nothing -- every address is known without waiting for data
+            int v = u, vi = i, vj = j, vk = k, lu = u;
+            bool ok = true;
+            const mgf *lnk = F.cx;
+            switch (c) {
+                case 1: ok = i > 0; v = u - 1; vi = i - 1; lu = u - 1; break;
+                case 2: ok = i + 1 < F.ni; v = u + 1; vi = i + 1; break;
+                case 3: ok = j > 0; v = u - sj; vj = j - 1; lu = u - sj; lnk = F.cy; break;
+                case 4: ok = j + 1 < F.nj; v = u + sj; vj = j + 1; lnk = F.cy; break;
+                case 5: ok = k > 0; v = u - sk; vk = k - 1; lu = u - sk; lnk = F.cz; break;
+                case 6: ok = k + 1 < F.nk; v = u + sk; vk = k + 1; lnk = F.cz; break;
+                case 7: ok = false; break;
+                default: break;
+            }
+            if (ok) {
+                const double vv = val(v, vi, vj, vk);
+                if (c == 0) { centre = vv; term = (double)F.b[u] - (double)F.diag[u] * vv; }
+                else term = (double)lnk[lu] * vv;
             }
         }
         const double tot = mg_sum8(term);
         centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        if (c == 0 && live) own.st(F.xn, u, F, lf, (mgf)((mi != 0) ? centre + MG_OMEGA * mi * tot : 0.0));
+        if (c == 0 && live) own.st(F.xn, (long long)u, F, lf, (mgf)((mi != (mgf)0) ? centre + MG_OMEGA * (double)mi * tot : 0.0));
     }
 }
 
-// The coarsest level, solved by every block on its own in shared memory: x = w D^-1 b, then `sweeps` damped-Jacobi sweeps.
-// Identical arithmetic in every block (and on every rank): identical result everywhere, no grid barrier.  Returns the
-// shared-memory array that holds the solution.  Ends with a __syncthreads.
+// The coarsest level, solved by every block on its own in shared memory: x = w D^-1 b, then `sweeps` damped-Jacobi sweeps in
+// FP32.  Identical arithmetic in every block (and on every rank): identical result everywhere, no grid barrier.
+// Shared-memory layout (floats): eight arrays of n + 2 pad entries, pad = one plane, zero filled -- b | x | y | minv | diag |
+// cx | cy | cz.  Links to neighbours that do not exist are zero in the link arrays and every index u +- 1, +- ni, +- ni*nj
+// stays inside the padded arrays, so a sweep has no index tests at all.  A level of more than MG_STAGE_NODES nodes keeps
+// its coefficients in global memory (three vectors in shared memory only).
+#define MG_STAGE_NODES 2048
+
+__device__ __forceinline__ int mg_cpad(const MgLevel &L) { return L.ni * L.nj; }
+__device__ __forceinline__ bool mg_cstaged(const MgLevel &L) { return L.nn <= MG_STAGE_NODES; }
+
+// once per Newton step, after the Galerkin diagonals are complete: coefficients -> shared memory, pads -> 0
+__device__ __forceinline__ void mg_coarsest_stage(const MgLevel &L, mgf *smem)
+{
+    const int n = (int)L.nn, pad = mg_cpad(L), len = n + 2 * pad;
+    if (!mg_cstaged(L)) {
+        for (int t = threadIdx.x; t < 3 * n; t += blockDim.x) smem[t] = 0;
+        __syncthreads();
+        return;
+    }
+    for (int t = threadIdx.x; t < 8 * len; t += blockDim.x) smem[t] = 0;
+    __syncthreads();
+    mgf *minv = smem + 3 * len + pad, *diag = minv + len, *cx = diag + len, *cy = cx + len, *cz = cy + len;
+    for (int u = threadIdx.x; u < n; u += blockDim.x) {
+        minv[u] = L.minv[u]; diag[u] = L.diag[u]; cx[u] = L.cx[u]; cy[u] = L.cy[u]; cz[u] = L.cz[u];
+    }
+    __syncthreads();
+}
+
+// Returns the shared-memory array that holds the solution (index 0 = node 0).  Ends with a __syncthreads.
 __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, mgf *smem)
 {
     const int n = (int)L.nn;
+    const int sj = L.ni, sk = L.ni * L.nj;
+    if (mg_cstaged(L)) {
+        const int pad = sk, len = n + 2 * pad;
+        mgf *sb = smem + pad, *sx = sb + len, *sy = sx + len;
+        const mgf *minv = sy + len, *diag = minv + len, *cx = diag + len, *cy = cx + len, *cz = cy + len;
+        for (int u = threadIdx.x; u < n; u += blockDim.x) {
+            const mgf b = L.b[u];
+            sb[u] = b;
+            sx[u] = (mgf)MG_OMEGA * b * minv[u];
+        }
+        __syncthreads();
+        for (int sweep = 0; sweep < sweeps; sweep++) {
+            for (int u = threadIdx.x; u < n; u += blockDim.x) {
+                const mgf xc = sx[u];
+                mgf t = sb[u] - diag[u] * xc;
+                t += cx[u - 1] * sx[u - 1];
+                t += cx[u] * sx[u + 1];
+                t += cy[u - sj] * sx[u - sj];
+                t += cy[u] * sx[u + sj];
+                t += cz[u - sk] * sx[u - sk];
+                t += cz[u] * sx[u + sk];
+                sy[u] = xc + (mgf)MG_OMEGA * minv[u] * t;          // minv = 0 on nodes without unknowns, where x stays 0
+            }
+            __syncthreads();
+            mgf *tmp = sx; sx = sy; sy = tmp;
+        }
+        return sx;
+    }
     mgf *sb = smem, *sx = smem + n, *sy = smem + 2 * n;
     for (int u = threadIdx.x; u < n; u += blockDim.x) {
         const mgf b = L.b[u];
         sb[u] = b;
-        sx[u] = (mgf)(MG_OMEGA * (double)b * (double)L.minv[u]);
+        sx[u] = (mgf)MG_OMEGA * b * L.minv[u];
     }
     __syncthreads();
-    const int sj = L.ni, sk = L.ni * L.nj;
     for (int sweep = 0; sweep < sweeps; sweep++) {
         for (int u = threadIdx.x; u < n; u += blockDim.x) {
-            const double mi = L.minv[u];
-            double out = 0;
-            if (mi != 0) {
-                const int i = u % L.ni, j = (u / L.ni) % L.nj, k = u / sk;
-                const double xc = sx[u];
-                double t = (double)sb[u] - (double)L.diag[u] * xc;
-                if (i > 0) t += (double)L.cx[u - 1] * (double)sx[u - 1];
-                if (i + 1 < L.ni) t += (double)L.cx[u] * (double)sx[u + 1];
-                if (j > 0) t += (double)L.cy[u - sj] * (double)sx[u - sj];
-                if (j + 1 < L.nj) t += (double)L.cy[u] * (double)sx[u + sj];
-                if (k > 0) t += (double)L.cz[u - sk] * (double)sx[u - sk];
-                if (k + 1 < L.nk) t += (double)L.cz[u] * (double)sx[u + sk];
-                out = xc + MG_OMEGA * mi * t;
-            }
-            sy[u] = (mgf)out;
+            const MgIdx q = mg_ijk(L, (unsigned)u);
+            const mgf xc = sx[u];
+            mgf t = sb[u] - L.diag[u] * xc;
+            if (q.i > 0) t += L.cx[u - 1] * sx[u - 1];
+            if (q.i + 1 < L.ni) t += L.cx[u] * sx[u + 1];
+            if (q.j > 0) t += L.cy[u - sj] * sx[u - sj];
+            if (q.j + 1 < L.nj) t += L.cy[u] * sx[u + sj];
+            if (q.k > 0) t += L.cz[u - sk] * sx[u - sk];
+            if (q.k + 1 < L.nk) t += L.cz[u] * sx[u + sk];
+            sy[u] = xc + (mgf)MG_OMEGA * L.minv[u] * t;
         }
         __syncthreads();
         mgf *tmp = sx; sx = sy; sy = tmp;
@@ -541,10 +611,12 @@ __device__ __forceinline__ MgCol mg_col(const StencilC &s, const MgRuns &R, long
     return c;
 }
 
-// x0 = w D^-1 r with the smoother's FP32 diagonal (0 where the node is not an unknown)
+// x0 = w D^-1 r with the smoother's FP32 diagonal (0 where the node is not an unknown).  Branch free: the reciprocal of a
+// zero diagonal is discarded by the select.
 __device__ __forceinline__ double mg_x0(double r, mgf dg)
 {
-    return dg != (mgf)0 ? MG_OMEGA * r * (double)__frcp_rn(dg) : 0.0;
+    const double v = MG_OMEGA * r * (double)__frcp_rn(dg);
+    return dg != (mgf)0 ? v : 0.0;
 }
 
 // calls f(column, kbeg, kend) for every run of this block
@@ -560,6 +632,11 @@ __device__ __forceinline__ void mg_for_runs(const StencilC &s, const MgRuns &R, 
     }
 }
 
+// All four passes follow one rule: every load of a plane step is issued unconditionally at the top of the step (an inner
+// column's neighbours always exist), values that must not count are removed by selects afterwards.  A step then costs ONE
+// memory round trip instead of a chain of them (the first version loaded the diagonal, branched on it and only then loaded the
+// neighbours: 2-4 dependent round trips per plane, ncu: long_scoreboard).
+
 // Pass A (down, fine -> level 1): residual of the pre-smoothed iterate x0 = w D^-1 r, summed over each aggregate -> b of level 1
 template <class Own>
 __device__ __forceinline__ void mg_fine_down(const Own &own, const MgnArgs &a, const MgRuns &R, bool to_all)
@@ -567,40 +644,49 @@ __device__ __forceinline__ void mg_fine_down(const Own &own, const MgnArgs &a, c
     const StencilC &s = a.s;
     const MgLevel &C = a.L[1];
     const int lane = threadIdx.x & 31;
+    const int sj = (int)s.sj;
+    const long long sk = s.sk;
     mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
         const bool act = col.inner;                 // boundary and outside columns hold no unknowns: they only take part in the shuffles
-        long long u = col.base + (long long)kbeg * s.sk;
-        double x0m = 0, x0c = 0, x0p = 0, rc = 0;
+        const double *rp = a.r + (col.base + (long long)kbeg * sk);
+        const mgf *gp = a.diagf + (col.base + (long long)kbeg * sk);
+        double x0m = 0, x0c = 0, rc = 0;
         mgf dgc = 0;
         if (act) {
-            if (kbeg >= 1) x0m = mg_x0(a.r[u - s.sk], a.diagf[u - s.sk]);
-            rc = a.r[u]; dgc = a.diagf[u];
+            if (kbeg >= 1) x0m = mg_x0(rp[-sk], gp[-sk]);
+            rc = rp[0]; dgc = gp[0];
             x0c = mg_x0(rc, dgc);
         }
+        const bool writer = col.inmesh && (!C.fi || !(lane & 1)) && (!C.fj || !(lane & 16));
+        const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi), cplane = (long long)C.ni * C.nj;
         double sum = 0;
-        for (int k = kbeg; k < kend; k++, u += s.sk) {
-            double rp = 0; mgf dgp = 0;
-            if (act && k + 1 < s.nk) { rp = a.r[u + s.sk]; dgp = a.diagf[u + s.sk]; }
-            x0p = mg_x0(rp, dgp);
-            if (act && dgc != (mgf)0) {
-                const double xxm = mg_x0(a.r[u - 1], a.diagf[u - 1]), xxp = mg_x0(a.r[u + 1], a.diagf[u + 1]);
-                const double xym = mg_x0(a.r[u - s.sj], a.diagf[u - s.sj]), xyp = mg_x0(a.r[u + s.sj], a.diagf[u + s.sj]);
-                const double off = s.gdx2 * (xxm + xxp) + s.gdy2 * (xym + xyp) + s.gdz2 * (x0m + x0p);
-                sum += rc - ((double)dgc * x0c - off);
+        for (int k = kbeg; k < kend; k++, rp += sk, gp += sk) {
+            double rn = 0; mgf dgn = 0;
+            if (act) {
+                const bool up = k + 1 < s.nk;
+                const double r_p = up ? rp[sk] : 0.0;
+                const mgf g_p = up ? gp[sk] : (mgf)0;
+                const double r_xm = rp[-1], r_xp = rp[1], r_ym = rp[-sj], r_yp = rp[sj];
+                const mgf g_xm = gp[-1], g_xp = gp[1], g_ym = gp[-sj], g_yp = gp[sj];
+                const double x0p = mg_x0(r_p, g_p);
+                const double off = s.gdx2 * (mg_x0(r_xm, g_xm) + mg_x0(r_xp, g_xp)) + s.gdy2 * (mg_x0(r_ym, g_ym) + mg_x0(r_yp, g_yp)) +
+                                   s.gdz2 * (x0m + x0p);
+                const double res = rc - ((double)dgc * x0c - off);
+                sum += dgc != (mgf)0 ? res : 0.0;
+                x0m = x0c; x0c = x0p; rn = r_p; dgn = g_p;
             }
+            rc = rn; dgc = dgn;
             if (((k + 1) & (R.kunit - 1)) == 0 || k + 1 == s.nk) {        // last plane of an aggregate: combine the children, store
                 double t = sum;
                 if (C.fi) t += __shfl_xor_sync(0xffffffffu, t, 1);
                 if (C.fj) t += __shfl_xor_sync(0xffffffffu, t, 16);
-                const bool writer = col.inmesh && (!C.fi || !(lane & 1)) && (!C.fj || !(lane & 16));
                 if (writer) {
-                    const long long I = ((long long)(k >> C.fk) * C.nj + (col.j >> C.fj)) * C.ni + (col.i >> C.fi);
+                    const long long I = (long long)(k >> C.fk) * cplane + crow;
                     if (to_all) own.st_all(C.b, I, (mgf)t);
                     else own.st(C.b, I, C, 1, (mgf)t);
                 }
                 sum = 0;
             }
-            x0m = x0c; x0c = x0p; rc = rp; dgc = dgp;
         }
     });
 }
@@ -611,42 +697,53 @@ __device__ __forceinline__ double mg_fine_up(const Own &own, const MgnArgs &a, c
 {
     const StencilC &s = a.s;
     const MgLevel &C = a.L[1], &L0 = a.L[0];
+    const int sj = (int)s.sj;
+    const long long sk = s.sk;
     double acc = 0;
     mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
         const bool act = col.inner;
-        long long u = col.base + (long long)kbeg * s.sk;
-        double x0m = 0, x0c = 0, x0p = 0, rc = 0;
+        long long u = col.base + (long long)kbeg * sk;
+        const double *rp = a.r + u;
+        const mgf *gp = a.diagf + u;
+        double x0m = 0, x0c = 0, rc = 0;
         mgf dgm = 0, dgc = 0;
         if (act) {
-            if (kbeg >= 1) { dgm = a.diagf[u - s.sk]; x0m = mg_x0(a.r[u - s.sk], dgm); }
-            rc = a.r[u]; dgc = a.diagf[u];
+            if (kbeg >= 1) { dgm = gp[-sk]; x0m = mg_x0(rp[-sk], dgm); }
+            rc = rp[0]; dgc = gp[0];
             x0c = mg_x0(rc, dgc);
         }
-        const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi), cplane = (long long)C.ni * C.nj;
-        for (int k = kbeg; k < kend; k++, u += s.sk) {
-            double rp = 0; mgf dgp = 0;
-            if (act && k + 1 < s.nk) { rp = a.r[u + s.sk]; dgp = a.diagf[u + s.sk]; }
-            x0p = mg_x0(rp, dgp);
+        // the correction of a neighbour is that of ITS aggregate: offsets of the neighbours' aggregates relative to this one's
+        const int cplane = C.ni * C.nj;
+        const int oxm = ((col.i - 1) >> C.fi) - (col.i >> C.fi), oxp = ((col.i + 1) >> C.fi) - (col.i >> C.fi);
+        const int oym = (((col.j - 1) >> C.fj) - (col.j >> C.fj)) * C.ni, oyp = (((col.j + 1) >> C.fj) - (col.j >> C.fj)) * C.ni;
+        const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi);
+        for (int k = kbeg; k < kend; k++, u += sk, rp += sk, gp += sk) {
             mgf zf = 0;
-            if (act && dgc != (mgf)0) {
-                // the correction of a neighbour is that of ITS aggregate; a neighbour that is not an unknown carries 0
-                const long long I0 = (long long)(k >> C.fk) * cplane + crow;
-                const double e0 = e[I0];
-                const mgf gxm = a.diagf[u - 1], gxp = a.diagf[u + 1], gym = a.diagf[u - s.sj], gyp = a.diagf[u + s.sj];
-                const double vxm = gxm != (mgf)0 ? mg_x0(a.r[u - 1], gxm) + (double)e[I0 - (col.i >> C.fi) + ((col.i - 1) >> C.fi)] : 0.0;
-                const double vxp = gxp != (mgf)0 ? mg_x0(a.r[u + 1], gxp) + (double)e[I0 - (col.i >> C.fi) + ((col.i + 1) >> C.fi)] : 0.0;
-                const double vym = gym != (mgf)0 ? mg_x0(a.r[u - s.sj], gym) + (double)e[I0 + (long long)(((col.j - 1) >> C.fj) - (col.j >> C.fj)) * C.ni] : 0.0;
-                const double vyp = gyp != (mgf)0 ? mg_x0(a.r[u + s.sj], gyp) + (double)e[I0 + (long long)(((col.j + 1) >> C.fj) - (col.j >> C.fj)) * C.ni] : 0.0;
-                const double vzm = dgm != (mgf)0 ? x0m + (double)e[I0 + (long long)(((k - 1) >> C.fk) - (k >> C.fk)) * cplane] : 0.0;
-                const double vzp = dgp != (mgf)0 ? x0p + (double)e[I0 + (long long)(((k + 1) >> C.fk) - (k >> C.fk)) * cplane] : 0.0;
+            double rn = 0; mgf dgn = 0;
+            if (act) {
+                const bool up = k + 1 < s.nk;
+                const double r_p = up ? rp[sk] : 0.0;
+                const mgf g_p = up ? gp[sk] : (mgf)0;
+                const double r_xm = rp[-1], r_xp = rp[1], r_ym = rp[-sj], r_yp = rp[sj];
+                const mgf g_xm = gp[-1], g_xp = gp[1], g_ym = gp[-sj], g_yp = gp[sj];
+                const mgf *ep = e + ((long long)(k >> C.fk) * cplane + crow);
+                const int ozm = k >= 1 ? (((k - 1) >> C.fk) - (k >> C.fk)) * cplane : 0;
+                const int ozp = up ? (((k + 1) >> C.fk) - (k >> C.fk)) * cplane : 0;
+                const double e0 = ep[0], exm = ep[oxm], exp_ = ep[oxp], eym = ep[oym], eyp = ep[oyp], ezm = ep[ozm], ezp = ep[ozp];
+                const double x0p = mg_x0(r_p, g_p);
+                // a neighbour that is not an unknown carries 0
+                const double vxm = g_xm != (mgf)0 ? mg_x0(r_xm, g_xm) + exm : 0.0, vxp = g_xp != (mgf)0 ? mg_x0(r_xp, g_xp) + exp_ : 0.0;
+                const double vym = g_ym != (mgf)0 ? mg_x0(r_ym, g_ym) + eym : 0.0, vyp = g_yp != (mgf)0 ? mg_x0(r_yp, g_yp) + eyp : 0.0;
+                const double vzm = dgm != (mgf)0 ? x0m + ezm : 0.0, vzp = g_p != (mgf)0 ? x0p + ezp : 0.0;
                 const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
                 const double xu = x0c + e0;
                 const double zu = xu + MG_OMEGA * (double)__frcp_rn(dgc) * (rc - ((double)dgc * xu - off));
-                zf = (mgf)zu;
+                zf = dgc != (mgf)0 ? (mgf)zu : (mgf)0;
                 acc += rc * (double)zf;
+                x0m = x0c; x0c = x0p; rn = r_p; dgm = dgc; dgn = g_p;
             }
+            rc = rn; dgc = dgn;
             if (col.inmesh) own.st(a.z, u, L0, 0, zf);
-            x0m = x0c; x0c = x0p; rc = rp; dgm = dgc; dgc = dgp;
         }
     });
     return acc;
@@ -659,29 +756,31 @@ __device__ __forceinline__ double mg_fine_dir(const Own &own, const MgnArgs &a, 
 {
     const StencilC &s = a.s;
     const MgLevel &L0 = a.L[0];
+    const int sj = (int)s.sj;
+    const long long sk = s.sk;
     double acc = 0;
     mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
-        long long u = col.base + (long long)kbeg * s.sk;
-        double dm = 0, dc = 0, dp = 0;
-        if (col.inmesh) {
-            if (kbeg >= 1) dm = (double)a.z[u - s.sk] + beta * d_old[u - s.sk];
-            dc = (double)a.z[u] + beta * d_old[u];
-        }
-        for (int k = kbeg; k < kend; k++, u += s.sk) {
-            dp = 0;
-            if (col.inmesh && k + 1 < s.nk) dp = (double)a.z[u + s.sk] + beta * d_old[u + s.sk];
+        if (!col.inmesh) return;
+        long long u = col.base + (long long)kbeg * sk;
+        const mgf *zp = a.z + u, *gp = a.diagf + u;
+        const double *dp = d_old + u;
+        double dm = 0, dc = 0;
+        if (kbeg >= 1) dm = (double)zp[-sk] + beta * dp[-sk];
+        dc = (double)zp[0] + beta * dp[0];
+        for (int k = kbeg; k < kend; k++, u += sk, zp += sk, dp += sk, gp += sk) {
+            const bool up = k + 1 < s.nk;
+            const double dn = up ? (double)zp[sk] + beta * dp[sk] : 0.0;
             if (col.inner) {
-                const double dg = a.diagf[u];
-                if (dg != 0) {
-                    // z and d are identically zero outside the REG set: no neighbour masks
-                    const double off = s.gdx2 * (((double)a.z[u - 1] + beta * d_old[u - 1]) + ((double)a.z[u + 1] + beta * d_old[u + 1])) +
-                                       s.gdy2 * (((double)a.z[u - s.sj] + beta * d_old[u - s.sj]) + ((double)a.z[u + s.sj] + beta * d_old[u + s.sj])) +
-                                       s.gdz2 * (dm + dp);
-                    acc += dc * (dg * dc - off);
-                }
+                // z and d are identically zero outside the REG set: no neighbour masks
+                const double dg = gp[0];
+                const double n_xm = (double)zp[-1] + beta * dp[-1], n_xp = (double)zp[1] + beta * dp[1];
+                const double n_ym = (double)zp[-sj] + beta * dp[-sj], n_yp = (double)zp[sj] + beta * dp[sj];
+                const double off = s.gdx2 * (n_xm + n_xp) + s.gdy2 * (n_ym + n_yp) + s.gdz2 * (dm + dn);
+                const double q = dc * (dg * dc - off);
+                acc += dg != 0 ? q : 0.0;
             }
-            if (col.inmesh) own.st(d_new, u, L0, 0, dc);
-            dm = dc; dc = dp;
+            own.st(d_new, u, L0, 0, dc);
+            dm = dc; dc = dn;
         }
     });
     return acc;
@@ -693,22 +792,28 @@ __device__ __forceinline__ double mg_fine_res(const Own &own, const MgnArgs &a, 
 {
     const StencilC &s = a.s;
     const MgLevel &L0 = a.L[0];
+    const int sj = (int)s.sj;
+    const long long sk = s.sk;
     double acc = 0;
     mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
         if (!col.inner) return;
-        long long u = col.base + (long long)kbeg * s.sk;
-        double dm = kbeg >= 1 ? d[u - s.sk] : 0.0, dc = d[u], dp = 0;
-        for (int k = kbeg; k < kend; k++, u += s.sk) {
-            dp = k + 1 < s.nk ? d[u + s.sk] : 0.0;
-            const double dg = a.diagf[u];
-            if (dg != 0) {
-                const double q = dg * dc - (s.gdx2 * (d[u - 1] + d[u + 1]) + s.gdy2 * (d[u - s.sj] + d[u + s.sj]) + s.gdz2 * (dm + dp));
-                a.delta[u] = a.delta[u] + alpha * dc;
-                const double rn = a.r[u] - alpha * q;
+        long long u = col.base + (long long)kbeg * sk;
+        const double *dp = d + u;
+        const mgf *gp = a.diagf + u;
+        double dm = kbeg >= 1 ? dp[-sk] : 0.0, dc = dp[0];
+        for (int k = kbeg; k < kend; k++, u += sk, dp += sk, gp += sk) {
+            const double dn = k + 1 < s.nk ? dp[sk] : 0.0;
+            const double dg = gp[0];
+            const double d_xm = dp[-1], d_xp = dp[1], d_ym = dp[-sj], d_yp = dp[sj];
+            const double del = a.delta[u], rr = a.r[u];
+            if (dg != 0) {          // stores only: every load of the step is already in flight
+                const double q = dg * dc - (s.gdx2 * (d_xm + d_xp) + s.gdy2 * (d_ym + d_yp) + s.gdz2 * (dm + dn));
+                a.delta[u] = del + alpha * dc;
+                const double rn = rr - alpha * q;
                 own.st(a.r, u, L0, 0, rn);
                 acc += rn * rn;
             }
-            dm = dc; dc = dp;
+            dm = dc; dc = dn;
         }
     });
     return acc;
@@ -726,25 +831,31 @@ __device__ __forceinline__ double mg_linearise(const Own &own, const MgnArgs &a,
     for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
         double r = 0;
         mgf dj = 0;
-        if (a.type[u] == NT_REG) {
-            const double p = phi[u];
-            const double ex = exp((p - a.phi0) / a.Te0);
-            const double src = (a.rho[u] - C_QE * (a.n0 * ex)) / C_EPS_0;
+        // REG nodes are interior, so for u in [sk, nn - sk) every neighbour address is valid whatever the node is: all loads
+        // are issued at once and the node type only selects (no load waits for another load)
+        if (u >= s.sk && u < s.nn - s.sk) {
+            const int ty = a.type[u];
             const bool fxm = a.type[u - 1] >= NT_I0, fxp = a.type[u + 1] >= NT_I0, fym = a.type[u - s.sj] >= NT_I0,
                        fyp = a.type[u + s.sj] >= NT_I0, fzm = a.type[u - s.sk] >= NT_I0, fzp = a.type[u + s.sk] >= NT_I0;
-            const double xm = fxm ? p : phi[u - 1], xp = fxp ? p : phi[u + 1];
-            const double ym = fym ? p : phi[u - s.sj], yp = fyp ? p : phi[u + s.sj];
-            const double zm = fzm ? p : phi[u - s.sk], zp = fzp ? p : phi[u + s.sk];
-            r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
-            double d0 = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
-            if (fxm) d0 -= s.gdx2;
-            if (fxp) d0 -= s.gdx2;
-            if (fym) d0 -= s.gdy2;
-            if (fyp) d0 -= s.gdy2;
-            if (fzm) d0 -= s.gdz2;
-            if (fzp) d0 -= s.gdz2;
-            dj = (mgf)(d0 + a.n0 * C_QE / (C_EPS_0 * a.Te0) * ex);
-            acc += r * r;
+            const double p = phi[u], rho = a.rho[u];
+            const double pxm = phi[u - 1], pxp = phi[u + 1], pym = phi[u - s.sj], pyp = phi[u + s.sj], pzm = phi[u - s.sk], pzp = phi[u + s.sk];
+            if (ty == NT_REG) {
+                const double ex = exp((p - a.phi0) / a.Te0);
+                const double src = (rho - C_QE * (a.n0 * ex)) / C_EPS_0;
+                const double xm = fxm ? p : pxm, xp = fxp ? p : pxp;
+                const double ym = fym ? p : pym, yp = fyp ? p : pyp;
+                const double zm = fzm ? p : pzm, zp = fzp ? p : pzp;
+                r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
+                double d0 = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
+                if (fxm) d0 -= s.gdx2;
+                if (fxp) d0 -= s.gdx2;
+                if (fym) d0 -= s.gdy2;
+                if (fyp) d0 -= s.gdy2;
+                if (fzm) d0 -= s.gdz2;
+                if (fzp) d0 -= s.gdz2;
+                dj = (mgf)(d0 + a.n0 * C_QE / (C_EPS_0 * a.Te0) * ex);
+                acc += r * r;
+            }
         }
         own.st(a.r, u, L0, 0, r);
         own.st(a.diagf, u, L0, 0, dj);
@@ -762,12 +873,13 @@ __device__ __forceinline__ double mg_update(const Own &own, const MgnArgs &a, lo
     const StencilC &s = a.s;
     const MgLevel &L0 = a.L[0];
     double acc = 0;
-    for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
-        if (a.type[u] != NT_REG) continue;
-        const double dl = a.delta[u];
-        own.st(a.phi, u, L0, 0, a.phi[u] + dl);
+    for (long long u = max(own.lo(L0, 0), s.sk) + t0; u < min(own.hi(L0, 0), s.nn - s.sk); u += stride) {      // REG nodes are interior
+        const int ty = a.type[u];
         const int cnt = 1 + (a.type[u - 1] >= NT_I0) + (a.type[u + 1] >= NT_I0) + (a.type[u - s.sj] >= NT_I0) + (a.type[u + s.sj] >= NT_I0) +
                         (a.type[u - s.sk] >= NT_I0) + (a.type[u + s.sk] >= NT_I0);
+        const double dl = a.delta[u], p = a.phi[u];
+        if (ty != NT_REG) continue;
+        own.st(a.phi, u, L0, 0, p + dl);
         acc += cnt * (dl * dl);
     }
     return acc;
@@ -898,6 +1010,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
                 }
             }
         }
+        if (a.nlev > 1) mg_coarsest_stage(a.L[a.nlev - 1], smem);
         MG_TICK(8);
         // ---- CG on K delta = R down to the forcing level
         const double eta = nit == 0 ? a.eta0 : fmin(a.eta_max, a.gamma * (Rn / Rprev) * (Rn / Rprev));
@@ -1120,7 +1233,10 @@ static const MgKnobs &mg_knobs()
 
 static size_t mg_smem_bytes(const MgHierarchy *H)
 {
-    return H->nlev > 1 ? (size_t)3 * H->L[H->nlev - 1].nn * sizeof(mgf) : 0;
+    if (H->nlev <= 1) return 0;
+    const MgLevel &L = H->L[H->nlev - 1];
+    if (L.nn <= MG_STAGE_NODES) return (size_t)8 * (L.nn + 2 * (long long)L.ni * L.nj) * sizeof(mgf);
+    return (size_t)3 * L.nn * sizeof(mgf);
 }
 
 template <typename K>

@@ -279,7 +279,10 @@ static_assert(DT_SLOTS >= DT_TILE && DT_SLOTS == (1 << DT_SLOT_BITS), "one hash 
 
 // VAL selects what is scattered: 0 the weight mpw (number density), 1 mpw*v, 2 (mpw*v)*v with v = vcomp[] (velocity moments,
 // ch4 Species::sampleMoments: the same kernel runs once per sampled quantity)
-template <int MODE, int VAL = 0, int STRIDE = 1>
+// GROUP = false skips steps 1b and 2 (hash, scan, placement): each thread then merges DT_PER CONSECUTIVE particles of the
+// stream.  That is the right kernel while the stream is still in cell order (runs of ~100 particles per cell): it needs a
+// quarter of the warp shuffles of k_deposit (one segmented reduction per 4 particles instead of per 2) and no hashing.
+template <int MODE, int VAL = 0, int STRIDE = 1, bool GROUP = true>
 __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
                                                               const double *__restrict__ z, const double *__restrict__ mpw,
                                                               long long n, double *acc, double scale, int ahead,
@@ -331,6 +334,10 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
                     sx[p + q] = d0; sy[p + q] = d1; sz[p + q] = d2;
                 }
             }
+            if (!GROUP) {           // no grouping: remember the cell's lower node per particle (hkey doubles as that array)
+                hkey[p + q] = key;
+                continue;
+            }
             const unsigned peers = __match_any_sync(0xffffffffu, key);
             const int leader = __ffs(peers) - 1;
             uint32_t slot = 0xffffu;
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
     }
     __syncthreads();
     // ---- 2. exclusive scan of the slot counts (DT_SLOTS / DT_THREADS consecutive entries per thread), then place the ids
-    {
+    if (GROUP) {
         constexpr int PER = DT_SLOTS / DT_THREADS;
         uint32_t cnt[PER], tsum = 0;
 #pragma unroll
@@ -368,6 +375,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         for (int q = 0; q < PER; q++) { hcnt[tid * PER + q] = run; run += cnt[q]; }
         if (tid == DT_THREADS - 1) n_sorted = run;
     }
+    if (GROUP) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < DT_PER; j++) {
@@ -381,8 +389,9 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
         if (slot < DT_SLOTS) order[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)p;
     }
     __syncthreads();
+    }
     // ---- 3. walk the grouped order: DT_PER consecutive entries per thread, merged in registers, then across the warp
-    const int M = (int)n_sorted;
+    const int M = GROUP ? (int)n_sorted : DT_TILE;
     T a[8];
 #pragma unroll
     for (int t = 0; t < 8; t++) a[t] = 0;
@@ -391,9 +400,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
     for (int j = 0; j < DT_PER; j++) {
         const int q = tid * DT_PER + j;
         if (q >= M) break;
-        const int p = order[q];
+        const int p = GROUP ? order[q] : q;
         T v[8];
-        const long long u = (long long)hkey[pslot[p]];
+        const uint32_t cellu = GROUP ? hkey[pslot[p]] : hkey[p];
+        if (!GROUP && cellu == DT_EMPTY) continue;                // nothing to deposit (dead slot, tail of the last tile)
+        const long long u = (long long)cellu;
         weights_from_fractions<MODE>(sx[p], sy[p], sz[p], sw[p], scale, v);
         if (u != ua) {
             if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
@@ -718,18 +729,24 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
         if (r) return r;
         if (s.np > 0) {
             const double scale = ldexp(1.0, s.acc_shift);
-            // directly after a cell sort (no push in between) runs of equal cells are long and the plain warp merge is the
-            // cheaper kernel (2.0 vs 3.6 ms at 2e8 particles); once the order has decayed the tile-grouping kernel wins (3.8 vs 4-7 ms)
-            const bool ordered = s.pushes_since_sort == 0;
+            // Directly after a sort (no push in between) the ungrouped tile kernel (merge 4 consecutive particles per thread, then
+            // the warp) is the cheapest.  A few pushes later the thermal x/y motion (2 % of the particles change cell per step)
+            // has cut the runs to pieces -- in either sort order, measured: profiles/r2_sort_order_sweep.txt -- and the grouping
+            // kernel wins (its time does not depend on the disorder).  ESPIC_DEPOSIT_PLAIN_STEPS moves the switch.
+            static const int plain_steps = getenv("ESPIC_DEPOSIT_PLAIN_STEPS") ? atoi(getenv("ESPIC_DEPOSIT_PLAIN_STEPS")) : 0;
+            const bool ordered = s.pushes_since_sort <= plain_steps;
             static const int ahead_env = getenv("ESPIC_DEPOSIT_PREFETCH") ? atoi(getenv("ESPIC_DEPOSIT_PREFETCH")) : -1;
             const int ahead = ahead_env >= 0 ? ahead_env : 2 * c->sm_count;
+            const unsigned tgrid = nblk(s.np, DT_TILE);
+#define DEP_ARGS c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale, ahead
             if (mode == ESPIC_DEPOSIT_FP64) {
-                if (ordered) k_deposit<ESPIC_DEPOSIT_FP64><<<nblk((s.np + 1) / 2, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
-                else k_deposit_tile<ESPIC_DEPOSIT_FP64><<<nblk(s.np, DT_TILE), DT_THREADS, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale, ahead);
+                if (ordered) k_deposit_tile<ESPIC_DEPOSIT_FP64, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else k_deposit_tile<ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
             } else {
-                if (ordered) k_deposit<ESPIC_DEPOSIT_FIXED><<<nblk((s.np + 1) / 2, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale);
-                else k_deposit_tile<ESPIC_DEPOSIT_FIXED><<<nblk(s.np, DT_TILE), DT_THREADS, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale, ahead);
+                if (ordered) k_deposit_tile<ESPIC_DEPOSIT_FIXED, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else k_deposit_tile<ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
             }
+#undef DEP_ARGS
             LAUNCH_CHECK(c);
         }
     }
@@ -894,7 +911,11 @@ extern "C" int espic_clear_samples(espic_ctx *c, int sp)
 // that have crossed after s steps are still a contiguous run (the warp-level run merging of the deposit and the L1
 // locality of the gather survive between sorts), instead of being interleaved one by one with those that have not.
 #define SORT_ZBINS 8
-__device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y, double z)
+// order 0: the cell index of ch4 World::XtoC (k slowest); order 1 (ESPIC_SORT_DRIFT_Z): k FASTEST -- the particles of one
+// (i,j) column of cells are contiguous and ordered along z.  A beam drifting along z then keeps its order from step to step
+// (the whole column shifts together; only the thermal x/y motion, ~2 % of the particles per step at 300 m/s, breaks runs),
+// where order 0 loses 22 % of the particles of every cell to a far-away key each step.
+__device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y, double z, int order)
 {
     int i, j, k; double d0, d1, d2;
     cell3(m, x, y, z, i, j, k, d0, d1, d2);
@@ -903,15 +924,16 @@ __device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y
     if (k < 0) { k = 0; d2 = 0; }
     int zb = (int)(d2 * SORT_ZBINS);
     zb = zb < 0 ? 0 : (zb > SORT_ZBINS - 1 ? SORT_ZBINS - 1 : zb);
+    if (order == 1) return (((long long)j * (m.ni - 1) + i) * (long long)(m.nk - 1) + k) * SORT_ZBINS + zb;
     return (((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i) * SORT_ZBINS + zb;
 }
 
 __global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
-                                                    const double *__restrict__ z, long long n, uint32_t *__restrict__ cnt)
+                                                    const double *__restrict__ z, long long n, uint32_t *__restrict__ cnt, int order)
 {
     long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= n) return;
-    long long cell = cell_key(m, x[idx], y[idx], z[idx]);
+    long long cell = cell_key(m, x[idx], y[idx], z[idx], order);
     // warp-aggregate equal keys (sorted input: most of a warp shares a cell)
     unsigned act = __activemask();
     unsigned peers = __match_any_sync(act, cell);
@@ -926,12 +948,12 @@ __global__ void __launch_bounds__(256) k_cell_scatter(MeshC m, long long n, uint
                                                       const double *__restrict__ s6,
                                                       double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
                                                       double *__restrict__ d3, double *__restrict__ d4, double *__restrict__ d5,
-                                                      double *__restrict__ d6)
+                                                      double *__restrict__ d6, int order)
 {
     long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= n) return;
     double x = s0[idx], y = s1[idx], z = s2[idx];
-    long long cell = cell_key(m, x, y, z);
+    long long cell = cell_key(m, x, y, z, order);
     unsigned act = __activemask();
     unsigned peers = __match_any_sync(act, cell);
     int lane = threadIdx.x & 31;
@@ -946,10 +968,13 @@ __global__ void __launch_bounds__(256) k_cell_scatter(MeshC m, long long n, uint
     d3[dst] = s3[idx]; d4[dst] = s4[idx]; d5[dst] = s5[idx]; d6[dst] = s6[idx];
 }
 
-extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
+extern "C" int espic_sort_by_cell(espic_ctx *c, int sp) { return espic_sort_particles(c, sp, ESPIC_SORT_XTOC); }
+
+extern "C" int espic_sort_particles(espic_ctx *c, int sp, int order)
 {
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
+    if (order != ESPIC_SORT_XTOC && order != ESPIC_SORT_DRIFT_Z) { espic_set_error("espic_sort_particles: bad order %d", order); return -1; }
     Species &s = c->sp[sp];
     MIG_GUARD(c, s, "espic_sort_by_cell");
     const long long n = s.np;
@@ -970,16 +995,17 @@ extern "C" int espic_sort_by_cell(espic_ctx *c, int sp)
     }
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nc, c->stream))) return r;
     CK(cudaMemsetAsync(c->cell_cnt, 0, (size_t)nc * sizeof(uint32_t), c->stream));
-    k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt);
+    k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt, order);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nc, c->dscal + 1))) return r;
     k_cell_scatter<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, n, c->cell_cnt, c->scan_pre, c->scan_coff,
                                                         s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
-                                                        s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6]);
+                                                        s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6], order);
     LAUNCH_CHECK(c);
     for (int q = 0; q < 7; q++) std::swap(s.p[q], s.alt[q]);
     std::swap(s.cap, s.alt_cap);
     s.pushes_since_sort = 0;
+    s.sort_order = order;
     return 0;
 }
 

@@ -15,6 +15,7 @@ PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM,
 WALL_ABSORB, WALL_REFLECT = 0, 1
 PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_MIGRATE, PUSH_FIXED_POINT = 1, 2, 4, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
+SORT_XTOC, SORT_DRIFT_Z = 0, 1
 SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF, SOLVE_PCG_MG, SOLVE_PCG_MG_SLAB = 0, 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
@@ -22,7 +23,7 @@ EXPORTS = [
     "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
     "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
-    "espic_sort_by_cell", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
+    "espic_sort_by_cell", "espic_sort_particles", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_mg_plan", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init",
     "espic_domain_set", "espic_domain_get", "espic_migrate", "espic_migrate_pack", "espic_migrate_segment", "espic_migrate_finish",
@@ -86,6 +87,7 @@ def load():
     L.espic_last_push_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.espic_deposit.argtypes = [vp, C.c_int, C.c_int]
     L.espic_sort_by_cell.argtypes = [vp, C.c_int]
+    L.espic_sort_particles.argtypes = [vp, C.c_int, C.c_int]
     L.espic_inject_warm_beam.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
                                          C.c_uint32, C.POINTER(C.c_longlong)]
     L.espic_inject_cold_beam.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
@@ -282,6 +284,9 @@ class Engine:
 
     def deposit(self, sp, mode=DEPOSIT_FP64):
         self._ck(self.L.espic_deposit(self.h, sp, mode))
+
+    def sort_particles(self, sp, order):
+        self._ck(self.L.espic_sort_particles(self.h, sp, order))
 
     def sort_by_cell(self, sp):
         self._ck(self.L.espic_sort_by_cell(self.h, sp))
