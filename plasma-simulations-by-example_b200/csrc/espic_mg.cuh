@@ -40,10 +40,13 @@ struct MgLevel {
     int ni, nj, nk;
     int fi, fj, fk;           // log2 of the coarsening factor from the next finer level to this one, per dimension (0 or 1)
     long long nn;
-    mgf *diag, *minv;         // Galerkin diagonal and its inverse (0 on nodes without unknowns)
+    mgf *diag, *minv;         // diagonal and its inverse (0 on nodes without unknowns): dlx + dly + dlz + mass
     mgf *cx, *cy, *cz;        // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
     mgf *x, *xn, *b;          // pre-smoothed iterate, post-smoothed iterate, right-hand side
+    mgf *dlx, *dly, *dlz;     // Laplacian part of the diagonal per direction (geometry only, set up once)
+    mgf *mass;                // Boltzmann part of the diagonal: sum of the children's (changes with phi every Newton step)
 };
+#define MG_LEVEL_ARRAYS 12
 
 struct MgHierarchy {
     int nlev = 0;
@@ -57,45 +60,62 @@ static MgHierarchy *g_mg_of(espic_ctx *c);   // stored in the context (espic_int
 
 // ---- setup kernels (geometry only: links never change with phi) --------------------------------------------------------
 
-// links of level 1 from the fine node types: a fine link (u, u+e) exists iff both ends are REG; its weight is g = 1/dh^2
-__global__ void __launch_bounds__(256) k_mg_links_from_types(StencilC s, const uint8_t *__restrict__ type, MgLevel C)
+// Coarse operators.  Plain Galerkin P^T K P with piecewise-constant P is too stiff in every coarsened direction: summing the
+// 2x2 fine links across an aggregate face gives the 7-point Laplacian of spacing 2h times 2 (relative to what the summed
+// restriction of the right-hand side calls for), so smooth error is under-corrected by that factor and CG needs ~45 % more
+// iterations (measured on the bench problem: 28 -> 19 for six decades).  The links and the Laplacian part of the diagonal
+// are therefore scaled by `scale` (1/2 = rediscretisation on the coarse mesh; 1 = Galerkin) in each direction that is
+// coarsened, level by level; the Boltzmann (mass) part of the diagonal is restricted exactly.  Any SPD coarse operator keeps
+// the V-cycle SPD (symmetric smoother, R = P^T), which is all CG needs.
+
+// level 1 from the fine node types: a fine link (u, u+e) exists iff both ends are REG, weight g = 1/dh^2; the fine Laplacian
+// diagonal of a REG node is 2g per direction minus g per Neumann face neighbour (folded into the node, espic_fields.cu)
+__global__ void __launch_bounds__(256) k_mg_setup_from_types(StencilC s, const uint8_t *__restrict__ type, MgLevel C, double scale)
 {
     long long I = blockIdx.x * 256ll + threadIdx.x;
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-    double lx = 0, ly = 0, lz = 0;
+    double lx = 0, ly = 0, lz = 0, dx = 0, dy = 0, dz = 0;
     for (int dk = 0; dk <= C.fk; dk++)
         for (int dj = 0; dj <= C.fj; dj++)
             for (int di = 0; di <= C.fi; di++) {
                 const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                 const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
-                if (type[u] != NT_REG) continue;
-                if (di == C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) lx += s.gdx2;
-                if (dj == C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) ly += s.gdy2;
-                if (dk == C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) lz += s.gdz2;
+                if (type[u] != NT_REG) continue;            // REG nodes are interior: all six neighbours exist
+                dx += s.gdx2 * (2 - (type[u - 1] >= NT_I0) - (type[u + 1] >= NT_I0));
+                dy += s.gdy2 * (2 - (type[u - s.sj] >= NT_I0) - (type[u + s.sj] >= NT_I0));
+                dz += s.gdz2 * (2 - (type[u - s.sk] >= NT_I0) - (type[u + s.sk] >= NT_I0));
+                if (type[u + 1] == NT_REG) { if (di == C.fi) lx += s.gdx2; else dx -= 2 * s.gdx2; }
+                if (type[u + s.sj] == NT_REG) { if (dj == C.fj) ly += s.gdy2; else dy -= 2 * s.gdy2; }
+                if (type[u + s.sk] == NT_REG) { if (dk == C.fk) lz += s.gdz2; else dz -= 2 * s.gdz2; }
             }
-    C.cx[I] = (mgf)lx; C.cy[I] = (mgf)ly; C.cz[I] = (mgf)lz;
+    const double sx = C.fi ? scale : 1.0, sy = C.fj ? scale : 1.0, sz = C.fk ? scale : 1.0;
+    C.cx[I] = (mgf)(sx * lx); C.cy[I] = (mgf)(sy * ly); C.cz[I] = (mgf)(sz * lz);
+    C.dlx[I] = (mgf)(sx * dx); C.dly[I] = (mgf)(sy * dy); C.dlz[I] = (mgf)(sz * dz);
 }
 
-// links of level l+1 from the links of level l (l >= 1)
-__global__ void __launch_bounds__(256) k_mg_links_from_links(MgLevel F, MgLevel C)
+// level l+1 from level l (l >= 1)
+__global__ void __launch_bounds__(256) k_mg_setup_from_level(MgLevel F, MgLevel C, double scale)
 {
     long long I = blockIdx.x * 256ll + threadIdx.x;
     if (I >= C.nn) return;
     const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-    double lx = 0, ly = 0, lz = 0;
+    double lx = 0, ly = 0, lz = 0, dx = 0, dy = 0, dz = 0;
     for (int dk = 0; dk <= C.fk; dk++)
         for (int dj = 0; dj <= C.fj; dj++)
             for (int di = 0; di <= C.fi; di++) {
                 const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                 if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
                 const long long u = ((long long)k * F.nj + j) * F.ni + i;
-                if (di == C.fi) lx += F.cx[u];
-                if (dj == C.fj) ly += F.cy[u];
-                if (dk == C.fk) lz += F.cz[u];
+                dx += F.dlx[u]; dy += F.dly[u]; dz += F.dlz[u];
+                if (di == C.fi) lx += F.cx[u]; else dx -= 2 * (double)F.cx[u];       // a link at the mesh edge is 0
+                if (dj == C.fj) ly += F.cy[u]; else dy -= 2 * (double)F.cy[u];
+                if (dk == C.fk) lz += F.cz[u]; else dz -= 2 * (double)F.cz[u];
             }
-    C.cx[I] = (mgf)lx; C.cy[I] = (mgf)ly; C.cz[I] = (mgf)lz;
+    const double sx = C.fi ? scale : 1.0, sy = C.fj ? scale : 1.0, sz = C.fk ? scale : 1.0;
+    C.cx[I] = (mgf)(sx * lx); C.cy[I] = (mgf)(sy * ly); C.cz[I] = (mgf)(sz * lz);
+    C.dlx[I] = (mgf)(sx * dx); C.dly[I] = (mgf)(sy * dy); C.dlz[I] = (mgf)(sz * dz);
 }
 
 // ---- who owns what: single GPU, or one k-slab per rank with peer-mapped pools -----------------------------------------
@@ -473,16 +493,16 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
     return sx;
 }
 
-// ---- Galerkin diagonals (the Boltzmann term changes with phi every Newton step; the links do not) ---------------------
+// ---- coarse diagonals, every Newton step: the Boltzmann term changes with phi, links and Laplacian parts do not ----------
 
-// level 1 from the fine diagonal: sum of the children's diagonals minus twice the fine links inside the aggregate
+// level 1: mass = sum over the children of (Jacobian diagonal - Laplacian diagonal)
 template <class Own>
 __device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, const uint8_t *__restrict__ type, const mgf *diagf,
                                          const MgLevel &C, long long t0, long long stride, bool to_all)
 {
     for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
         const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-        double d = 0;
+        double m = 0;
         for (int dk = 0; dk <= C.fk; dk++)
             for (int dj = 0; dj <= C.fj; dj++)
                 for (int di = 0; di <= C.fi; di++) {
@@ -490,14 +510,15 @@ __device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, cons
                     if (i >= s.ni || j >= s.nj || k >= s.nk) continue;
                     const long long u = (long long)k * s.sk + (long long)j * s.sj + i;
                     if (type[u] != NT_REG) continue;
-                    d += (double)diagf[u];
-                    if (di < C.fi && i + 1 < s.ni && type[u + 1] == NT_REG) d -= 2 * s.gdx2;
-                    if (dj < C.fj && j + 1 < s.nj && type[u + s.sj] == NT_REG) d -= 2 * s.gdy2;
-                    if (dk < C.fk && k + 1 < s.nk && type[u + s.sk] == NT_REG) d -= 2 * s.gdz2;
+                    const double d0 = s.gdx2 * (2 - (type[u - 1] >= NT_I0) - (type[u + 1] >= NT_I0)) +
+                                      s.gdy2 * (2 - (type[u - s.sj] >= NT_I0) - (type[u + s.sj] >= NT_I0)) +
+                                      s.gdz2 * (2 - (type[u - s.sk] >= NT_I0) - (type[u + s.sk] >= NT_I0));
+                    m += fmax((double)diagf[u] - d0, 0.0);
                 }
-        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0;
-        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); }
-        else { own.st(C.diag, I, C, 1, df); own.st(C.minv, I, C, 1, mi); }
+        const double d = (double)C.dlx[I] + (double)C.dly[I] + (double)C.dlz[I] + m;
+        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0, mf = (mgf)m;
+        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); own.st_all(C.mass, I, mf); }
+        else { own.st(C.diag, I, C, 1, df); own.st(C.minv, I, C, 1, mi); C.mass[I] = mf; }
     }
 }
 
@@ -507,21 +528,18 @@ __device__ __forceinline__ void mg_diagl(const Own &own, const MgLevel &F, const
 {
     for (long long I = own.lo(C, lc) + t0; I < own.hi(C, lc); I += stride) {
         const int ci = (int)(I % C.ni), cj = (int)((I / C.ni) % C.nj), ck = (int)(I / ((long long)C.ni * C.nj));
-        double d = 0;
+        double m = 0;
         for (int dk = 0; dk <= C.fk; dk++)
             for (int dj = 0; dj <= C.fj; dj++)
                 for (int di = 0; di <= C.fi; di++) {
                     const int i = (ci << C.fi) + di, j = (cj << C.fj) + dj, k = (ck << C.fk) + dk;
                     if (i >= F.ni || j >= F.nj || k >= F.nk) continue;
-                    const long long u = ((long long)k * F.nj + j) * F.ni + i;
-                    d += (double)F.diag[u];
-                    if (di < C.fi && i + 1 < F.ni) d -= 2 * (double)F.cx[u];
-                    if (dj < C.fj && j + 1 < F.nj) d -= 2 * (double)F.cy[u];
-                    if (dk < C.fk && k + 1 < F.nk) d -= 2 * (double)F.cz[u];
+                    m += (double)F.mass[((long long)k * F.nj + j) * F.ni + i];
                 }
-        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0;
-        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); }
-        else { own.st(C.diag, I, C, lc, df); own.st(C.minv, I, C, lc, mi); }
+        const double d = (double)C.dlx[I] + (double)C.dly[I] + (double)C.dlz[I] + m;
+        const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0, mf = (mgf)m;
+        if (to_all) { own.st_all(C.diag, I, df); own.st_all(C.minv, I, mi); own.st_all(C.mass, I, mf); }
+        else { own.st(C.diag, I, C, lc, df); own.st(C.minv, I, C, lc, mi); C.mass[I] = mf; }
     }
 }
 
@@ -544,7 +562,7 @@ struct MgnArgs {
     double phi0, Te0, n0;
     int max_it, nr_max_it;
     double tol, nr_tol;
-    double eta0, eta_max, gamma;  // forcing: eta_0, then min(eta_max, gamma (|R_k|/|R_k-1|)^2)
+    double eta0, eta_max, gamma, eta_pow;  // forcing: eta_0, then min(eta_max, gamma (|R_k|/|R_k-1|)^eta_pow)
     double *out;                  // see MGN_OUT_*
     unsigned long long *prof;     // optional: nanoseconds per phase as seen by block 0 (ESPIC_MG_PROFILE=1), 16 slots
 };
@@ -1013,7 +1031,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
         if (a.nlev > 1) mg_coarsest_stage(a.L[a.nlev - 1], smem);
         MG_TICK(8);
         // ---- CG on K delta = R down to the forcing level
-        const double eta = nit == 0 ? a.eta0 : fmin(a.eta_max, a.gamma * (Rn / Rprev) * (Rn / Rprev));
+        const double eta = nit == 0 ? a.eta0 : fmin(a.eta_max, a.gamma * pow(Rn / Rprev, a.eta_pow));
         const double stop = fmax(0.5 * a.tol, eta * Rn);
         Rprev = Rn;
         l2 = Rn;
@@ -1124,7 +1142,7 @@ static long long mg_coarse_elems(const StencilC &s)
     int shifts[MG_MAX_LEVELS][3];
     const int nlev = mg_level_dims(s, dims, shifts);
     long long total = 0;
-    for (int l = 1; l < nlev; l++) total += 8 * ((dims[l][0] * dims[l][1] * dims[l][2] + 3) & ~3ll);
+    for (int l = 1; l < nlev; l++) total += MG_LEVEL_ARRAYS * ((dims[l][0] * dims[l][1] * dims[l][2] + 3) & ~3ll);
     return total;
 }
 
@@ -1174,6 +1192,30 @@ extern "C" int espic_mg_plan(int ni, int nj, int nk, const double dh[3], int nra
     return nlev;
 }
 
+struct MgKnobs { int coarse_sweeps; double eta0, eta_max, gamma, eta_pow, link_scale; bool profile; };
+// shared by the single-GPU and the slab solver, so that the two paths cannot drift apart
+static const MgKnobs &mg_knobs()
+{
+    static MgKnobs k;
+    static bool init = false;
+    if (!init) {
+        const char *ev = getenv("ESPIC_MG_COARSE_SWEEPS");
+        k.coarse_sweeps = ev ? std::max(0, atoi(ev)) : MG_COARSE_SWEEPS;
+        // ESPIC_MG_EXACT_NEWTON=1: every linear solve goes to tol/2 (the reference's exact Newton); else Eisenstat-Walker
+        const bool exact = getenv("ESPIC_MG_EXACT_NEWTON") != nullptr;
+        k.eta0 = exact ? 0.0 : (getenv("ESPIC_MG_ETA0") ? atof(getenv("ESPIC_MG_ETA0")) : 1e-2);
+        k.eta_max = exact ? 0.0 : 1e-1;
+        k.gamma = exact ? 0.0 : 0.9;
+        // exponent of the Eisenstat-Walker term.  2 (the textbook value for a quadratically converging Newton iteration)
+        // over-solves here: the remainder a Newton step leaves was measured at ~(|R_k|/|R_k-1|)^1.5 |R_k| on the bench case
+        k.eta_pow = getenv("ESPIC_MG_ETA_POW") ? atof(getenv("ESPIC_MG_ETA_POW")) : 1.5;
+        k.link_scale = getenv("ESPIC_MG_LINK_SCALE") ? atof(getenv("ESPIC_MG_LINK_SCALE")) : 0.6;
+        k.profile = getenv("ESPIC_MG_PROFILE") != nullptr;
+        init = true;
+    }
+    return k;
+}
+
 // (re)build the hierarchy H for the current geometry; coarse-level arrays go to `external` if given (slab mode: a pool
 // that the other ranks map), else to an allocation owned by H
 static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, mgf *external)
@@ -1196,39 +1238,21 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, mgf *extern
         L.ni = (int)dims[l][0]; L.nj = (int)dims[l][1]; L.nk = (int)dims[l][2];
         L.fi = shifts[l][0]; L.fj = shifts[l][1]; L.fk = shifts[l][2];
         L.nn = dims[l][0] * dims[l][1] * dims[l][2];
-        if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = nullptr; continue; }
+        if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = L.dlx = L.dly = L.dlz = L.mass = nullptr; continue; }
         const long long pad = (L.nn + 3) & ~3ll;           // keep every array 16-byte aligned
         L.diag = p; p += pad; L.minv = p; p += pad; L.cx = p; p += pad; L.cy = p; p += pad; L.cz = p; p += pad;
         L.x = p; p += pad; L.xn = p; p += pad; L.b = p; p += pad;
+        L.dlx = p; p += pad; L.dly = p; p += pad; L.dlz = p; p += pad; L.mass = p; p += pad;
     }
     H->nlev = nlev;
     for (int l = 1; l < nlev; l++) {
-        if (l == 1) k_mg_links_from_types<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->L[1]);
-        else k_mg_links_from_links<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l]);
+        const double scale = mg_knobs().link_scale;
+        if (l == 1) k_mg_setup_from_types<<<nblk(H->L[1].nn, 256), 256, 0, c->stream>>>(s, c->node_type, H->L[1], scale);
+        else k_mg_setup_from_level<<<nblk(H->L[l].nn, 256), 256, 0, c->stream>>>(H->L[l - 1], H->L[l], scale);
         LAUNCH_CHECK(c);
     }
     H->geom_version = c->geom_version;
     return 0;
-}
-
-struct MgKnobs { int coarse_sweeps; double eta0, eta_max, gamma; bool profile; };
-// shared by the single-GPU and the slab solver, so that the two paths cannot drift apart
-static const MgKnobs &mg_knobs()
-{
-    static MgKnobs k;
-    static bool init = false;
-    if (!init) {
-        const char *ev = getenv("ESPIC_MG_COARSE_SWEEPS");
-        k.coarse_sweeps = ev ? std::max(0, atoi(ev)) : MG_COARSE_SWEEPS;
-        // ESPIC_MG_EXACT_NEWTON=1: every linear solve goes to tol/2 (the reference's exact Newton); else Eisenstat-Walker
-        const bool exact = getenv("ESPIC_MG_EXACT_NEWTON") != nullptr;
-        k.eta0 = exact ? 0.0 : (getenv("ESPIC_MG_ETA0") ? atof(getenv("ESPIC_MG_ETA0")) : 1e-2);
-        k.eta_max = exact ? 0.0 : 1e-1;
-        k.gamma = exact ? 0.0 : 0.9;
-        k.profile = getenv("ESPIC_MG_PROFILE") != nullptr;
-        init = true;
-    }
-    return k;
 }
 
 static size_t mg_smem_bytes(const MgHierarchy *H)
@@ -1307,7 +1331,7 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
     a.part = c->red;
     a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
     a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
-    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma;
+    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma; a.eta_pow = kn.eta_pow;
     a.out = dout;
     a.prof = kn.profile ? c->dscal + 40 : nullptr;
     void *args[] = {&a};
@@ -1462,7 +1486,7 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
     a.part = S->part;
     a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
     a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
-    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma;
+    a.eta0 = kn.eta0; a.eta_max = kn.eta_max; a.gamma = kn.gamma; a.eta_pow = kn.eta_pow;
     a.out = dout;
     a.prof = kn.profile ? c->dscal + 40 : nullptr;
     OwnSlab own = S->own;

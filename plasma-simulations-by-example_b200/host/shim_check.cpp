@@ -110,7 +110,12 @@ int run_sphere(int argc, char **args)
             for (Species &sp : species) sp.updateAverages();
         Output::screenOutput(world, species);
         Output::diagOutput(world, species);
-        if (world.isLastTimeStep()) Output::fields(world, species);
+        if (world.isLastTimeStep()) {
+            Output::fields(world, species);
+            // the reference's loop runs one more step after its "last" one (advanceTime: ts <= num_ts, isLastTimeStep: ts == num_ts-1,
+            // World.h): keep the state the file was written from, for the comparison with the reference's own writer
+            dump_state(std::string(args[8]) + ".fields", world, species, 3, sc, 0.05, -100, 0, 1.5, ndi, ok);
+        }
     }
     dump_state(args[8], world, species, 3, sc, 0.05, -100, 0, 1.5, ndi, ok);
     return 0;

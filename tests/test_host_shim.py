@@ -454,7 +454,8 @@ def test_output_fields_vti_matches_the_reference_writer(tmp_path):
     fed with the state the shim dumped): every token of every DataArray, header included."""
     import glob
     steps = 6
-    st = run_check(tmp_path, "sphere", 9, 9, 13, steps, "QN", 1e-4)
+    run_check(tmp_path, "sphere", 9, 9, 13, steps, "QN", 1e-4)
+    st = sf.read_state(str(tmp_path / "out.state.fields"))          # the state at the moment Output::fields ran
     mine = glob.glob(str(tmp_path / "results" / "fields_*.vti"))
     assert len(mine) == 1
     ref_dir = tmp_path / "ref"
