@@ -835,6 +835,7 @@ void espic_mg_destroy(espic_ctx *c)
     if (!c->mg) return;
     MgHierarchy *H = static_cast<MgHierarchy *>(c->mg);
     if (H->own_pool) cudaFree(H->pool);
+    cudaFree(H->fine);
     delete H;
     c->mg = nullptr;
 }

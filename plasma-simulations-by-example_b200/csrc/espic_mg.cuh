@@ -24,6 +24,7 @@
 //     96 B per node and CG iteration instead of 170.
 //   * one launch and one host synchronisation per solve (the round-1 version: 3 synchronisations per Newton step).
 #pragma once
+#include <cuda.h>       // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no link against libcuda)
 
 #define MG_MAX_LEVELS 8
 #define MG_OMEGA 0.9
@@ -40,6 +41,7 @@ struct MgLevel {
     int ni, nj, nk;
     int fi, fj, fk;           // log2 of the coarsening factor from the next finer level to this one, per dimension (0 or 1)
     long long nn;
+    int pitch;                // elements per row of this level's arrays (level 0: ni rounded up to 4 for the TMA tiles; else ni)
     mgf *diag, *minv;         // diagonal and its inverse (0 on nodes without unknowns): dlx + dly + dlz + mass
     mgf *cx, *cy, *cz;        // link to the +x / +y / +z neighbour (>= 0; K = diag - sum links); level 0: not stored
     mgf *x, *xn, *b;          // pre-smoothed iterate, post-smoothed iterate, right-hand side
@@ -54,6 +56,9 @@ struct MgHierarchy {
     long long geom_version = -1;
     mgf *pool = nullptr;      // one allocation for all coarse-level arrays
     bool own_pool = false;
+    // single-GPU solver: the fine vectors in the padded layout (r | delta | d0 | d1 doubles, z | diagf floats)
+    double *fine = nullptr;
+    long long fine_nnp = 0;
 };
 
 static MgHierarchy *g_mg_of(espic_ctx *c);   // stored in the context (espic_internal.cuh: void *mg)
@@ -133,8 +138,10 @@ struct OwnAll {
     __device__ __forceinline__ int klo(const MgLevel &, int) const { return 0; }
     __device__ __forceinline__ int khi(const MgLevel &L, int) const { return L.nk; }
     __device__ __forceinline__ long long lo(const MgLevel &L, int) const { return 0; }
-    __device__ __forceinline__ long long hi(const MgLevel &L, int) const { return L.nn; }
+    __device__ __forceinline__ long long hi(const MgLevel &L, int) const { return (long long)L.pitch * L.nj * L.nk; }
     template <typename T> __device__ __forceinline__ void st(T *A, long long u, const MgLevel &, int, T v) const { A[u] = v; }
+    // store at flat index u known to lie in plane k of level l (any row pitch)
+    template <typename T> __device__ __forceinline__ void st_k(T *A, long long u, int, int, T v) const { A[u] = v; }
     template <typename T> __device__ __forceinline__ void st_all(T *A, long long u, T v) const { A[u] = v; }
     __device__ __forceinline__ int nparts(int nb) const { return nb; }
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const { base[blockIdx.x] = v; }
@@ -159,8 +166,8 @@ struct OwnSlab {
     unsigned long long lepoch;
     __device__ __forceinline__ int klo(const MgLevel &, int l) const { return k0[l]; }
     __device__ __forceinline__ int khi(const MgLevel &, int l) const { return k1[l]; }
-    __device__ __forceinline__ long long lo(const MgLevel &L, int l) const { return (long long)k0[l] * L.ni * L.nj; }
-    __device__ __forceinline__ long long hi(const MgLevel &L, int l) const { return (long long)k1[l] * L.ni * L.nj; }
+    __device__ __forceinline__ long long lo(const MgLevel &L, int l) const { return (long long)k0[l] * L.pitch * L.nj; }
+    __device__ __forceinline__ long long hi(const MgLevel &L, int l) const { return (long long)k1[l] * L.pitch * L.nj; }
     template <typename T> __device__ __forceinline__ T *at(T *p, int r) const
     {
         return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + peer[r]);
@@ -168,9 +175,16 @@ struct OwnSlab {
     template <typename T> __device__ __forceinline__ void st(T *A, long long u, const MgLevel &L, int l, T v) const
     {
         A[u] = v;
-        const long long plane = (long long)L.ni * L.nj;
+        const long long plane = (long long)L.pitch * L.nj;
         if (rank > 0 && u < lo(L, l) + plane) *at(A + u, rank - 1) = v;
         if (rank + 1 < nranks && u >= hi(L, l) - plane) *at(A + u, rank + 1) = v;
+    }
+    // store at flat index u known to lie in plane k of level l (any row pitch): first / last plane of the slab goes to the neighbour too
+    template <typename T> __device__ __forceinline__ void st_k(T *A, long long u, int k, int l, T v) const
+    {
+        A[u] = v;
+        if (rank > 0 && k == k0[l]) *at(A + u, rank - 1) = v;
+        if (rank + 1 < nranks && k == k1[l] - 1) *at(A + u, rank + 1) = v;
     }
     // store into every rank's copy (the right-hand side of the first level that every rank solves in full)
     template <typename T> __device__ __forceinline__ void st_all(T *A, long long u, T v) const
@@ -279,13 +293,17 @@ __device__ __forceinline__ MgIdx mg_ijk(const MgLevel &L, unsigned u)
     return q;
 }
 
-__device__ __forceinline__ double mg_sum8(double v)
+__device__ __forceinline__ mgf mg_sum8(mgf v)
 {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
+
+// The whole V-cycle is evaluated in FP32 (storage AND arithmetic): it only has to be a fixed SPD operator close to K^-1
+// (scripts/mg_fp32_prototype.py: same CG iteration counts as in FP64), FP32 instructions issue at twice the FP64 rate and
+// nothing has to be converted.  Sums use a fixed order (shuffle trees), so every block and every rank gets the same bits.
 
 // Down pass between coarse levels F (level lf) -> C: x_F = w D^-1 b_F (smoothing from zero), residual b_F - K x_F summed
 // over each aggregate -> b_C.  Lane c of a group of 8 handles child c of coarse node I.
@@ -295,11 +313,12 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
 {
     const long long first = own.lo(C, lf + 1), total = (own.hi(C, lf + 1) - first) * 8;
     const int sj = F.ni, sk = F.ni * F.nj;
+    const mgf W = (mgf)MG_OMEGA;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
         const unsigned I = (unsigned)(first + (w >> 3));
         const int c = (int)(w & 7);
         const bool live = w < total;
-        double res = 0;
+        mgf res = 0;
         if (live) {
             const MgIdx q = mg_ijk(C, I);
             const int di = c & 1, dj = (c >> 1) & 1, dk = c >> 2;
@@ -318,18 +337,16 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
                 const mgf mxm = xm ? F.minv[u - 1] : (mgf)0, mxp = xp ? F.minv[u + 1] : (mgf)0;
                 const mgf mym = ym ? F.minv[u - sj] : (mgf)0, myp = yp ? F.minv[u + sj] : (mgf)0;
                 const mgf mzm = zm ? F.minv[u - sk] : (mgf)0, mzp = zp ? F.minv[u + sk] : (mgf)0;
-                const double xu = MG_OMEGA * (double)bu * (double)mi;
-                const double off = MG_OMEGA * ((double)lxm * ((double)bxm * (double)mxm) + (double)lxp * ((double)bxp * (double)mxp) +
-                                               (double)lym * ((double)bym * (double)mym) + (double)lyp * ((double)byp * (double)myp) +
-                                               (double)lzm * ((double)bzm * (double)mzm) + (double)lzp * ((double)bzp * (double)mzp));
-                res = mi != (mgf)0 ? (double)bu - ((double)dg * xu - off) : 0.0;
-                own.st(F.x, (long long)u, F, lf, (mgf)xu);
+                const mgf xu = W * bu * mi;
+                const mgf off = W * (lxm * (bxm * mxm) + lxp * (bxp * mxp) + lym * (bym * mym) + lyp * (byp * myp) + lzm * (bzm * mzm) + lzp * (bzp * mzp));
+                res = mi != (mgf)0 ? bu - (dg * xu - off) : (mgf)0;
+                own.st(F.x, (long long)u, F, lf, xu);
             }
         }
         res = mg_sum8(res);
         if (c == 0 && live) {
-            if (to_all) own.st_all(C.b, (long long)I, (mgf)res);
-            else own.st(C.b, (long long)I, C, lf + 1, (mgf)res);
+            if (to_all) own.st_all(C.b, (long long)I, res);
+            else own.st(C.b, (long long)I, C, lf + 1, res);
         }
     }
 }
@@ -344,10 +361,11 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
 {
     const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
     const int sj = F.ni, sk = F.ni * F.nj, csj = C.ni, csk = C.ni * C.nj;
+    const mgf W = (mgf)MG_OMEGA;
     // value of the prolongated iterate at node (vi,vj,vk) = flat v; links to nodes without unknowns are zero on coarse levels,
     // so no mask is needed on the neighbours
     auto val = [&](int v, int vi, int vj, int vk) {
-        return (double)F.x[v] + (double)e[(vk >> C.fk) * csk + (vj >> C.fj) * csj + (vi >> C.fi)];
+        return F.x[v] + e[(vk >> C.fk) * csk + (vj >> C.fj) * csj + (vi >> C.fi)];
     };
     if (count * 2 > stride) {
         for (long long uu = first + t0; uu < first + count; uu += stride) {
@@ -359,13 +377,12 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
             const mgf lxm = xm ? F.cx[u - 1] : (mgf)0, lxp = xp ? F.cx[u] : (mgf)0;
             const mgf lym = ym ? F.cy[u - sj] : (mgf)0, lyp = yp ? F.cy[u] : (mgf)0;
             const mgf lzm = zm ? F.cz[u - sk] : (mgf)0, lzp = zp ? F.cz[u] : (mgf)0;
-            const double vc = val(u, i, j, k);
-            const double vxm = xm ? val(u - 1, i - 1, j, k) : 0.0, vxp = xp ? val(u + 1, i + 1, j, k) : 0.0;
-            const double vym = ym ? val(u - sj, i, j - 1, k) : 0.0, vyp = yp ? val(u + sj, i, j + 1, k) : 0.0;
-            const double vzm = zm ? val(u - sk, i, j, k - 1) : 0.0, vzp = zp ? val(u + sk, i, j, k + 1) : 0.0;
-            const double tot = ((double)bu - (double)dg * vc) + (double)lxm * vxm + (double)lxp * vxp + (double)lym * vym + (double)lyp * vyp +
-                               (double)lzm * vzm + (double)lzp * vzp;
-            own.st(F.xn, uu, F, lf, (mgf)(mi != (mgf)0 ? vc + MG_OMEGA * (double)mi * tot : 0.0));
+            const mgf vc = val(u, i, j, k);
+            const mgf vxm = xm ? val(u - 1, i - 1, j, k) : (mgf)0, vxp = xp ? val(u + 1, i + 1, j, k) : (mgf)0;
+            const mgf vym = ym ? val(u - sj, i, j - 1, k) : (mgf)0, vyp = yp ? val(u + sj, i, j + 1, k) : (mgf)0;
+            const mgf vzm = zm ? val(u - sk, i, j, k - 1) : (mgf)0, vzp = zp ? val(u + sk, i, j, k + 1) : (mgf)0;
+            const mgf tot = (bu - dg * vc) + ((lxm * vxm + lxp * vxp) + (lym * vym + lyp * vyp) + (lzm * vzm + lzp * vzp));
+            own.st(F.xn, uu, F, lf, mi != (mgf)0 ? vc + W * mi * tot : (mgf)0);
         }
         return;
     }
@@ -374,8 +391,7 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
         const int u = (int)(first + (w >> 3));
         const int c = (int)(w & 7);
         const bool live = w < total;
-        double term = 0, centre = 0;
-        mgf mi = 0;
+        mgf term = 0, centre = 0, mi = 0;
         if (live) {
             const MgIdx q = mg_ijk(F, (unsigned)u);
             const int i = q.i, j = q.j, k = q.k;
@@ -395,14 +411,14 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
                 default: break;
             }
             if (ok) {
-                const double vv = val(v, vi, vj, vk);
-                if (c == 0) { centre = vv; term = (double)F.b[u] - (double)F.diag[u] * vv; }
-                else term = (double)lnk[lu] * vv;
+                const mgf vv = val(v, vi, vj, vk);
+                if (c == 0) { centre = vv; term = F.b[u] - F.diag[u] * vv; }
+                else term = lnk[lu] * vv;
             }
         }
-        const double tot = mg_sum8(term);
+        const mgf tot = mg_sum8(term);
         centre = __shfl_sync(0xffffffffu, centre, (threadIdx.x & 31) & ~7);
-        if (c == 0 && live) own.st(F.xn, (long long)u, F, lf, (mgf)((mi != (mgf)0) ? centre + MG_OMEGA * (double)mi * tot : 0.0));
+        if (c == 0 && live) own.st(F.xn, (long long)u, F, lf, (mi != (mgf)0) ? centre + W * mi * tot : (mgf)0);
     }
 }
 
@@ -497,7 +513,7 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
 
 // level 1: mass = sum over the children of (Jacobian diagonal - Laplacian diagonal)
 template <class Own>
-__device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, const uint8_t *__restrict__ type, const mgf *diagf,
+__device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, const uint8_t *__restrict__ type, const mgf *diagf, int pitch,
                                          const MgLevel &C, long long t0, long long stride, bool to_all)
 {
     for (long long I = own.lo(C, 1) + t0; I < own.hi(C, 1); I += stride) {
@@ -513,7 +529,7 @@ __device__ __forceinline__ void mg_diag1(const Own &own, const StencilC &s, cons
                     const double d0 = s.gdx2 * (2 - (type[u - 1] >= NT_I0) - (type[u + 1] >= NT_I0)) +
                                       s.gdy2 * (2 - (type[u - s.sj] >= NT_I0) - (type[u + s.sj] >= NT_I0)) +
                                       s.gdz2 * (2 - (type[u - s.sk] >= NT_I0) - (type[u + s.sk] >= NT_I0));
-                    m += fmax((double)diagf[u] - d0, 0.0);
+                    m += fmax((double)diagf[((long long)k * s.nj + j) * pitch + i] - d0, 0.0);
                 }
         const double d = (double)C.dlx[I] + (double)C.dly[I] + (double)C.dlz[I] + m;
         const mgf df = (mgf)d, mi = d > 0 ? (mgf)(1.0 / d) : (mgf)0, mf = (mgf)m;
@@ -555,9 +571,17 @@ struct MgnArgs {
     const double *rho;
     double *phi;                  // the potential the kernel works on (slab mode: the pool copy, halos kept current by peer stores)
     double *phi_user;             // slab mode: the context's phi (read at the start, this rank's slab written at the end); else == phi
-    mgf *diagf;                   // Jacobian diagonal as the smoother and the operator use it (FP32 storage)
+    // the solver's own fine vectors: rows padded to `pitch` elements (a multiple of 4, the pads stay zero) so that TMA can tile them
+    int pitch;
+    long long psk;                // pitch * nj: plane stride of the padded arrays
+    mgf *diagf;                   // Jacobian diagonal as the operator uses it (FP32 storage)
+    mgf *winv;                    // w / diag: the damped-Jacobi smoother's factor (0 on nodes without unknowns)
+    mgf *rf;                      // FP32 copy of r: what the V-cycle reads
     mgf *z;
     double *r, *d0, *d1, *delta;
+    // 3-D tensor maps (x = pitch, y = nj, z = nk) of the vectors read with a stencil; box = one plane of a 32 x 8 tile + halo
+    alignas(64) CUtensorMap tm_rf, tm_w, tm_g, tm_z, tm_d0, tm_d1;
+    int smem_ring_off;            // byte offset of the TMA ring inside the dynamic shared memory (behind the coarsest level's arrays)
     double *part;                 // 3 x nparts partial sums
     double phi0, Te0, n0;
     int max_it, nr_max_it;
@@ -579,20 +603,97 @@ __device__ __forceinline__ unsigned long long mg_now()
 // 8 Galerkin diagonals, 9 update
 #define MG_TICK(id) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long n_ = mg_now(); a.prof[id] += n_ - tick; tick = n_; } } while (0)
 
-// ---- fine-level passes: marching along k -----------------------------------------------------------------------------
+// ---- fine-level passes: marching along k through a TMA-fed shared-memory ring ----------------------------------------
 // The owned planes of the fine level are cut into 32 x 8 tiles of columns; the work list is (tile, plane unit) with the
 // plane unit fastest, and block b takes the b-th of gridDim equal contiguous pieces of it: a run of consecutive planes of
-// one tile (possibly continuing in the next tile).  Along a run a thread keeps its column's values of planes k-1, k, k+1 in
-// registers, so every vector is read from L2/HBM once per pass (plus two halo planes per run); the x/y neighbours are
-// adjacent lanes' lines in L1.  A plane unit is 2^fk planes of level 1, so a thread finishes whole aggregates.
-// Lane layout inside a tile: a warp covers 16 (i) x 2 (j) columns -> the x partner of an aggregate is lane^1, the y partner
-// lane^16, and a warp reads two 128-byte rows per load.
+// one tile (possibly continuing in the next tile).  A plane unit is 2^fk planes of level 1, so a thread finishes whole
+// aggregates.  Lane layout inside a tile: a warp covers 16 (i) x 2 (j) columns -> the x partner of an aggregate is lane^1,
+// the y partner lane^16.
+//
+// Every vector a pass reads with a stencil comes through the TMA unit: one cp.async.bulk.tensor.3d per vector and plane
+// copies the tile plus its one-node halo (box 36 x 10 x 1 doubles, 40 x 10 x 1 floats; out-of-mesh coordinates are zero
+// filled, which is exactly the value a vector has outside the unknowns) into slot (plane mod MG_RING) of a ring in shared
+// memory and signals that slot's mbarrier.  One thread keeps the ring MG_RING planes ahead of the plane being computed, so
+// the L2/HBM latency of a plane is hidden behind the arithmetic of the planes before it, every value crosses L2 -> SM once
+// per pass, and the threads issue no global loads and no address arithmetic for the stencil at all (the first version of
+// these passes loaded straight from global memory and was bound by one memory round trip per plane: 131 us per CG
+// iteration for the four fine passes at 128^3, profiles/r2_mg_newton_history.txt).
+
+// TMA wants the first byte of a box 16-byte aligned in global memory: a double tile starts 2 columns left of the tile (one
+// halo column + one unused), a float tile 4 columns left (scripts/probes/tma_probe.cu: an odd start column is an illegal
+// instruction).
+#define MG_RING 5
+#define MG_TD_W 36                      // doubles per tile row: columns tx0-2 .. tx0+33
+#define MG_TD_X0 2
+#define MG_TD_SLOT 368                  // doubles per ring slot: 36 x 10 = 360, rounded up to a multiple of 128 bytes
+#define MG_TF_W 40                      // floats per tile row: columns tx0-4 .. tx0+35
+#define MG_TF_X0 4
+#define MG_TF_SLOT 416                  // floats per ring slot: 40 x 10 = 400, rounded up to a multiple of 128 bytes
+#define MG_TD_BYTES (MG_TD_W * (MG_TY + 2) * 8)
+#define MG_TF_BYTES (MG_TF_W * (MG_TY + 2) * 4)
+#define MG_RING_BYTES (MG_RING * (MG_TD_SLOT * 8 + 2 * MG_TF_SLOT * 4) + MG_RING * 8)
+
+__device__ __forceinline__ unsigned mg_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct MgRing {
+    double *sd;                  // MG_RING slots of MG_TD_SLOT doubles
+    mgf *sf, *sg;                // two float rings of MG_RING slots of MG_TF_SLOT floats
+    unsigned long long *bar;     // one mbarrier per slot
+    unsigned g;                  // planes staged so far by this block (identical in all its threads): slot = g % MG_RING, phase = g / MG_RING
+};
+
+__device__ __forceinline__ void mg_ring_init(MgRing &ring, unsigned char *base)
+{
+    ring.sd = reinterpret_cast<double *>(base);
+    ring.sf = reinterpret_cast<mgf *>(base + MG_RING * MG_TD_SLOT * 8);
+    ring.sg = ring.sf + MG_RING * MG_TF_SLOT;
+    ring.bar = reinterpret_cast<unsigned long long *>(ring.sg + MG_RING * MG_TF_SLOT);
+    ring.g = 0;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < MG_RING; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mg_smem_u32(ring.bar + q)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void mg_tma_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(mg_smem_u32(dst)), "l"((unsigned long long)map), "r"(mg_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// thread 0: stage plane k of up to three vectors (tile origin tx0, ty0) as ring entry g.  Lane 0 of the ring (double-sized
+// slots) takes either a double tile (md) or a float tile (mfd), lanes 1 and 2 float tiles (mf, mg).
+__device__ __forceinline__ void mg_ring_issue(const MgRing &ring, unsigned g, const CUtensorMap *md, const CUtensorMap *mf,
+                                              const CUtensorMap *mg, const CUtensorMap *mfd, int tx0, int ty0, int k)
+{
+    const unsigned slot = g % MG_RING;
+    unsigned long long *bar = ring.bar + slot;
+    const unsigned bytes = (md ? MG_TD_BYTES : 0) + (mf ? MG_TF_BYTES : 0) + (mg ? MG_TF_BYTES : 0) + (mfd ? MG_TF_BYTES : 0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mg_smem_u32(bar)), "r"(bytes) : "memory");
+    if (md) mg_tma_3d(ring.sd + slot * MG_TD_SLOT, md, bar, tx0 - MG_TD_X0, ty0 - 1, k);
+    if (mfd) mg_tma_3d(ring.sd + slot * MG_TD_SLOT, mfd, bar, tx0 - MG_TF_X0, ty0 - 1, k);
+    if (mf) mg_tma_3d(ring.sf + slot * MG_TF_SLOT, mf, bar, tx0 - MG_TF_X0, ty0 - 1, k);
+    if (mg) mg_tma_3d(ring.sg + slot * MG_TF_SLOT, mg, bar, tx0 - MG_TF_X0, ty0 - 1, k);
+}
+
+__device__ __forceinline__ void mg_ring_wait(const MgRing &ring, unsigned g)
+{
+    const unsigned addr = mg_smem_u32(ring.bar + g % MG_RING), parity = (g / MG_RING) & 1u;
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
 
 struct MgCol {
-    int i, j;
+    int i, j, tx0, ty0;
     bool inmesh;      // the column exists
     bool inner;       // 1 <= i <= ni-2 and 1 <= j <= nj-2: REG nodes only live here, every x/y neighbour exists
-    long long base;   // j*sj + i
+    long long nbase;  // j*ni + i      (native layout: phi, rho, type)
+    long long pbase;  // j*pitch + i   (padded layout: the solver's own vectors)
+    int cd, cf;       // this column's centre inside a double / float tile plane
 };
 
 struct MgRuns {
@@ -616,290 +717,287 @@ __device__ __forceinline__ MgRuns mg_runs(const Own &own, const MgnArgs &a)
     return R;
 }
 
-__device__ __forceinline__ MgCol mg_col(const StencilC &s, const MgRuns &R, long long tile)
+__device__ __forceinline__ MgCol mg_col(const MgnArgs &a, const MgRuns &R, long long tile)
 {
+    const StencilC &s = a.s;
     const int tx = (int)(tile % R.ntx), ty = (int)(tile / R.ntx);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int li = (w & 1) * 16 + (l & 15), lj = (w >> 1) * 2 + (l >> 4);
     MgCol c;
-    c.i = tx * MG_TX + (w & 1) * 16 + (l & 15);
-    c.j = ty * MG_TY + (w >> 1) * 2 + (l >> 4);
+    c.tx0 = tx * MG_TX; c.ty0 = ty * MG_TY;
+    c.i = c.tx0 + li;
+    c.j = c.ty0 + lj;
     c.inmesh = c.i < s.ni && c.j < s.nj;
     c.inner = c.i >= 1 && c.i <= s.ni - 2 && c.j >= 1 && c.j <= s.nj - 2;
-    c.base = (long long)c.j * s.sj + c.i;
+    c.nbase = (long long)c.j * s.sj + c.i;
+    c.pbase = (long long)c.j * a.pitch + c.i;
+    c.cd = (lj + 1) * MG_TD_W + li + MG_TD_X0;
+    c.cf = (lj + 1) * MG_TF_W + li + MG_TF_X0;
     return c;
-}
-
-// x0 = w D^-1 r with the smoother's FP32 diagonal (0 where the node is not an unknown).  Branch free: the reciprocal of a
-// zero diagonal is discarded by the select.
-__device__ __forceinline__ double mg_x0(double r, mgf dg)
-{
-    const double v = MG_OMEGA * r * (double)__frcp_rn(dg);
-    return dg != (mgf)0 ? v : 0.0;
 }
 
 // calls f(column, kbeg, kend) for every run of this block
 template <typename F>
-__device__ __forceinline__ void mg_for_runs(const StencilC &s, const MgRuns &R, F f)
+__device__ __forceinline__ void mg_for_runs(const MgnArgs &a, const MgRuns &R, F f)
 {
     for (long long pos = R.first; pos < R.last;) {
         const long long tile = pos / R.nku, ku = pos % R.nku;
         const long long nrun = min(R.last - pos, R.nku - ku);
         const int kbeg = R.klo + (int)ku * R.kunit, kend = min(R.khi, kbeg + (int)nrun * R.kunit);
-        f(mg_col(s, R, tile), kbeg, kend);
+        f(mg_col(a, R, tile), kbeg, kend);
         pos += nrun;
     }
 }
 
-// All four passes follow one rule: every load of a plane step is issued unconditionally at the top of the step (an inner
-// column's neighbours always exist), values that must not count are removed by selects afterwards.  A step then costs ONE
-// memory round trip instead of a chain of them (the first version loaded the diagonal, branched on it and only then loaded the
-// neighbours: 2-4 dependent round trips per plane, ncu: long_scoreboard).
+// One run through the ring: planes kbeg-1 .. kend of the given vectors are staged (ring entries g0 .. g0 + nplanes - 1), and
+// body(k, m, c, p) is called for k = kbeg .. kend-1 with the slot numbers holding planes k-1, k, k+1.
+template <typename F>
+__device__ __forceinline__ void mg_ring_run(MgRing &ring, const CUtensorMap *md, const CUtensorMap *mf, const CUtensorMap *mg,
+                                            const CUtensorMap *mfd, const MgCol &col, int kbeg, int kend, F body)
+{
+    const int nplanes = kend - kbeg + 2;
+    const unsigned g0 = ring.g;
+    if (threadIdx.x == 0) {
+        // the slots were last read through the generic proxy, and the vectors were last written by generic stores of other
+        // blocks (ordered by the grid barrier before this pass): order both before the async-proxy copies
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int q = 0; q < min(nplanes, MG_RING); q++) mg_ring_issue(ring, g0 + q, md, mf, mg, mfd, col.tx0, col.ty0, kbeg - 1 + q);
+    }
+    mg_ring_wait(ring, g0);
+    mg_ring_wait(ring, g0 + 1);
+    for (int k = kbeg; k < kend; k++) {
+        const unsigned t = (unsigned)(k - kbeg);
+        mg_ring_wait(ring, g0 + t + 2);
+        body(k, (int)((g0 + t) % MG_RING), (int)((g0 + t + 1) % MG_RING), (int)((g0 + t + 2) % MG_RING));
+        __syncthreads();                      // everybody is done with plane k-1: its slot takes the plane MG_RING further on
+        // (reads through the generic proxy followed by an async-proxy write of the same slot need no proxy fence: the block
+        // barrier orders them; a fence per plane cost more than the plane's arithmetic, ncu: membar + barrier stalls)
+        if (threadIdx.x == 0 && (int)t + MG_RING < nplanes)
+            mg_ring_issue(ring, g0 + t + MG_RING, md, mf, mg, mfd, col.tx0, col.ty0, kbeg - 1 + (int)t + MG_RING);
+    }
+    ring.g = g0 + (unsigned)nplanes;
+}
 
-// Pass A (down, fine -> level 1): residual of the pre-smoothed iterate x0 = w D^-1 r, summed over each aggregate -> b of level 1
+// Passes A and B are the fine level of the V-cycle: FP32 throughout (see mg_down).  With x0 = w D^-1 r the pre-smoothed
+// iterate, D x0 = w r, so neither pass needs the diagonal itself:
+//   residual of x0:          r - K x0 = (1 - w) r + offdiag(x0)
+//   post-smoothing of xu:    xu + w D^-1 (r - K xu) = (1 - w) xu + (w D^-1)(r + offdiag(xu))
+// with offdiag(v) = sum over the six neighbours of g v.  Staged vectors: rf (FP32 copy of r) and winv = w / diag.
+
+// Pass A (down, fine -> level 1): residual of the pre-smoothed iterate x0, summed over each aggregate -> b of level 1
 template <class Own>
-__device__ __forceinline__ void mg_fine_down(const Own &own, const MgnArgs &a, const MgRuns &R, bool to_all)
+__device__ __forceinline__ void mg_fine_down(const Own &own, const MgnArgs &a, const MgRuns &R, MgRing &ring, bool to_all)
 {
     const StencilC &s = a.s;
     const MgLevel &C = a.L[1];
     const int lane = threadIdx.x & 31;
-    const int sj = (int)s.sj;
-    const long long sk = s.sk;
-    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
-        const bool act = col.inner;                 // boundary and outside columns hold no unknowns: they only take part in the shuffles
-        const double *rp = a.r + (col.base + (long long)kbeg * sk);
-        const mgf *gp = a.diagf + (col.base + (long long)kbeg * sk);
-        double x0m = 0, x0c = 0, rc = 0;
-        mgf dgc = 0;
-        if (act) {
-            if (kbeg >= 1) x0m = mg_x0(rp[-sk], gp[-sk]);
-            rc = rp[0]; dgc = gp[0];
-            x0c = mg_x0(rc, dgc);
-        }
+    const mgf gx = (mgf)s.gdx2, gy = (mgf)s.gdy2, gz = (mgf)s.gdz2, W1 = (mgf)(1.0 - MG_OMEGA);
+    const mgf *ringr = reinterpret_cast<const mgf *>(ring.sd);          // the double-sized slots carry the FP32 tile of rf
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
         const bool writer = col.inmesh && (!C.fi || !(lane & 1)) && (!C.fj || !(lane & 16));
         const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi), cplane = (long long)C.ni * C.nj;
-        double sum = 0;
-        for (int k = kbeg; k < kend; k++, rp += sk, gp += sk) {
-            double rn = 0; mgf dgn = 0;
-            if (act) {
-                const bool up = k + 1 < s.nk;
-                const double r_p = up ? rp[sk] : 0.0;
-                const mgf g_p = up ? gp[sk] : (mgf)0;
-                const double r_xm = rp[-1], r_xp = rp[1], r_ym = rp[-sj], r_yp = rp[sj];
-                const mgf g_xm = gp[-1], g_xp = gp[1], g_ym = gp[-sj], g_yp = gp[sj];
-                const double x0p = mg_x0(r_p, g_p);
-                const double off = s.gdx2 * (mg_x0(r_xm, g_xm) + mg_x0(r_xp, g_xp)) + s.gdy2 * (mg_x0(r_ym, g_ym) + mg_x0(r_yp, g_yp)) +
-                                   s.gdz2 * (x0m + x0p);
-                const double res = rc - ((double)dgc * x0c - off);
-                sum += dgc != (mgf)0 ? res : 0.0;
-                x0m = x0c; x0c = x0p; rn = r_p; dgn = g_p;
-            }
-            rc = rn; dgc = dgn;
+        mgf sum = 0;
+        mg_ring_run(ring, nullptr, &a.tm_w, nullptr, &a.tm_rf, col, kbeg, kend, [&](int k, int m, int c, int p) {
+            const mgf *rm = ringr + m * (2 * MG_TD_SLOT) + col.cf, *rc = ringr + c * (2 * MG_TD_SLOT) + col.cf, *rp = ringr + p * (2 * MG_TD_SLOT) + col.cf;
+            const mgf *wm = ring.sf + m * MG_TF_SLOT + col.cf, *wc = ring.sf + c * MG_TF_SLOT + col.cf, *wp = ring.sf + p * MG_TF_SLOT + col.cf;
+            const mgf off = gx * (rc[-1] * wc[-1] + rc[1] * wc[1]) + gy * (rc[-MG_TF_W] * wc[-MG_TF_W] + rc[MG_TF_W] * wc[MG_TF_W]) +
+                            gz * (rm[0] * wm[0] + rp[0] * wp[0]);
+            sum += wc[0] != (mgf)0 ? W1 * rc[0] + off : (mgf)0;
             if (((k + 1) & (R.kunit - 1)) == 0 || k + 1 == s.nk) {        // last plane of an aggregate: combine the children, store
-                double t = sum;
+                mgf t = sum;
                 if (C.fi) t += __shfl_xor_sync(0xffffffffu, t, 1);
                 if (C.fj) t += __shfl_xor_sync(0xffffffffu, t, 16);
                 if (writer) {
                     const long long I = (long long)(k >> C.fk) * cplane + crow;
-                    if (to_all) own.st_all(C.b, I, (mgf)t);
-                    else own.st(C.b, I, C, 1, (mgf)t);
+                    if (to_all) own.st_all(C.b, I, t);
+                    else own.st(C.b, I, C, 1, t);
                 }
                 sum = 0;
             }
-        }
+        });
     });
 }
 
-// Pass B (up, level 1 -> fine): z = (x0 + P e) + w D^-1 (r - K (x0 + P e)); returns the thread's share of r.z
+// Pass B (up, level 1 -> fine): z = post-smoothing of x0 + P e; returns the thread's share of r.z
 template <class Own>
-__device__ __forceinline__ double mg_fine_up(const Own &own, const MgnArgs &a, const MgRuns &R, const mgf *e)
+__device__ __forceinline__ double mg_fine_up(const Own &own, const MgnArgs &a, const MgRuns &R, MgRing &ring, const mgf *e)
 {
     const StencilC &s = a.s;
-    const MgLevel &C = a.L[1], &L0 = a.L[0];
-    const int sj = (int)s.sj;
-    const long long sk = s.sk;
+    const MgLevel &C = a.L[1];
+    const mgf gx = (mgf)s.gdx2, gy = (mgf)s.gdy2, gz = (mgf)s.gdz2, W1 = (mgf)(1.0 - MG_OMEGA);
+    const mgf *ringr = reinterpret_cast<const mgf *>(ring.sd);
     double acc = 0;
-    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
-        const bool act = col.inner;
-        long long u = col.base + (long long)kbeg * sk;
-        const double *rp = a.r + u;
-        const mgf *gp = a.diagf + u;
-        double x0m = 0, x0c = 0, rc = 0;
-        mgf dgm = 0, dgc = 0;
-        if (act) {
-            if (kbeg >= 1) { dgm = gp[-sk]; x0m = mg_x0(rp[-sk], dgm); }
-            rc = rp[0]; dgc = gp[0];
-            x0c = mg_x0(rc, dgc);
-        }
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
         // the correction of a neighbour is that of ITS aggregate: offsets of the neighbours' aggregates relative to this one's
         const int cplane = C.ni * C.nj;
         const int oxm = ((col.i - 1) >> C.fi) - (col.i >> C.fi), oxp = ((col.i + 1) >> C.fi) - (col.i >> C.fi);
         const int oym = (((col.j - 1) >> C.fj) - (col.j >> C.fj)) * C.ni, oyp = (((col.j + 1) >> C.fj) - (col.j >> C.fj)) * C.ni;
         const long long crow = (long long)(col.j >> C.fj) * C.ni + (col.i >> C.fi);
-        for (int k = kbeg; k < kend; k++, u += sk, rp += sk, gp += sk) {
-            mgf zf = 0;
-            double rn = 0; mgf dgn = 0;
-            if (act) {
-                const bool up = k + 1 < s.nk;
-                const double r_p = up ? rp[sk] : 0.0;
-                const mgf g_p = up ? gp[sk] : (mgf)0;
-                const double r_xm = rp[-1], r_xp = rp[1], r_ym = rp[-sj], r_yp = rp[sj];
-                const mgf g_xm = gp[-1], g_xp = gp[1], g_ym = gp[-sj], g_yp = gp[sj];
+        long long up = col.pbase + (long long)kbeg * a.psk;
+        mg_ring_run(ring, nullptr, &a.tm_w, nullptr, &a.tm_rf, col, kbeg, kend, [&](int k, int m, int c, int p) {
+            // corrections first: these are the only global loads of the step, in flight while the tile is read
+            mgf e0 = 0, exm = 0, exp_ = 0, eym = 0, eyp = 0, ezm = 0, ezp = 0;
+            if (col.inner) {
                 const mgf *ep = e + ((long long)(k >> C.fk) * cplane + crow);
                 const int ozm = k >= 1 ? (((k - 1) >> C.fk) - (k >> C.fk)) * cplane : 0;
-                const int ozp = up ? (((k + 1) >> C.fk) - (k >> C.fk)) * cplane : 0;
-                const double e0 = ep[0], exm = ep[oxm], exp_ = ep[oxp], eym = ep[oym], eyp = ep[oyp], ezm = ep[ozm], ezp = ep[ozp];
-                const double x0p = mg_x0(r_p, g_p);
-                // a neighbour that is not an unknown carries 0
-                const double vxm = g_xm != (mgf)0 ? mg_x0(r_xm, g_xm) + exm : 0.0, vxp = g_xp != (mgf)0 ? mg_x0(r_xp, g_xp) + exp_ : 0.0;
-                const double vym = g_ym != (mgf)0 ? mg_x0(r_ym, g_ym) + eym : 0.0, vyp = g_yp != (mgf)0 ? mg_x0(r_yp, g_yp) + eyp : 0.0;
-                const double vzm = dgm != (mgf)0 ? x0m + ezm : 0.0, vzp = g_p != (mgf)0 ? x0p + ezp : 0.0;
-                const double off = s.gdx2 * (vxm + vxp) + s.gdy2 * (vym + vyp) + s.gdz2 * (vzm + vzp);
-                const double xu = x0c + e0;
-                const double zu = xu + MG_OMEGA * (double)__frcp_rn(dgc) * (rc - ((double)dgc * xu - off));
-                zf = dgc != (mgf)0 ? (mgf)zu : (mgf)0;
-                acc += rc * (double)zf;
-                x0m = x0c; x0c = x0p; rn = r_p; dgm = dgc; dgn = g_p;
+                const int ozp = k + 1 < s.nk ? (((k + 1) >> C.fk) - (k >> C.fk)) * cplane : 0;
+                e0 = ep[0]; exm = ep[oxm]; exp_ = ep[oxp]; eym = ep[oym]; eyp = ep[oyp]; ezm = ep[ozm]; ezp = ep[ozp];
             }
-            rc = rn; dgc = dgn;
-            if (col.inmesh) own.st(a.z, u, L0, 0, zf);
-        }
+            const mgf *rm = ringr + m * (2 * MG_TD_SLOT) + col.cf, *rc = ringr + c * (2 * MG_TD_SLOT) + col.cf, *rp = ringr + p * (2 * MG_TD_SLOT) + col.cf;
+            const mgf *wm = ring.sf + m * MG_TF_SLOT + col.cf, *wc = ring.sf + c * MG_TF_SLOT + col.cf, *wp = ring.sf + p * MG_TF_SLOT + col.cf;
+            // a neighbour that is not an unknown (winv = 0) carries 0, whatever its aggregate's correction is
+            const mgf w_xm = wc[-1], w_xp = wc[1], w_ym = wc[-MG_TF_W], w_yp = wc[MG_TF_W], w_zm = wm[0], w_zp = wp[0];
+            const mgf vxm = w_xm != (mgf)0 ? rc[-1] * w_xm + exm : (mgf)0, vxp = w_xp != (mgf)0 ? rc[1] * w_xp + exp_ : (mgf)0;
+            const mgf vym = w_ym != (mgf)0 ? rc[-MG_TF_W] * w_ym + eym : (mgf)0, vyp = w_yp != (mgf)0 ? rc[MG_TF_W] * w_yp + eyp : (mgf)0;
+            const mgf vzm = w_zm != (mgf)0 ? rm[0] * w_zm + ezm : (mgf)0, vzp = w_zp != (mgf)0 ? rp[0] * w_zp + ezp : (mgf)0;
+            const mgf off = gx * (vxm + vxp) + gy * (vym + vyp) + gz * (vzm + vzp);
+            const mgf r0 = rc[0], w0 = wc[0];
+            const mgf xu = r0 * w0 + e0;
+            const mgf zf = w0 != (mgf)0 ? W1 * xu + w0 * (r0 + off) : (mgf)0;
+            acc += (double)r0 * (double)zf;
+            if (col.inmesh) own.st_k(a.z, up, k, 0, zf);
+            up += a.psk;
+        });
     });
     return acc;
 }
 
 // Pass C: d = z + beta d_old (formed on the fly for the neighbours, written for this node); returns the share of d.K d
 template <class Own>
-__device__ __forceinline__ double mg_fine_dir(const Own &own, const MgnArgs &a, const MgRuns &R, double beta, const double *d_old,
-                                              double *d_new)
+__device__ __forceinline__ double mg_fine_dir(const Own &own, const MgnArgs &a, const MgRuns &R, MgRing &ring, double beta, bool d_is_d0)
 {
     const StencilC &s = a.s;
-    const MgLevel &L0 = a.L[0];
-    const int sj = (int)s.sj;
-    const long long sk = s.sk;
+    const CUtensorMap *md = d_is_d0 ? &a.tm_d0 : &a.tm_d1;       // d_old
+    double *d_new = d_is_d0 ? a.d1 : a.d0;
     double acc = 0;
-    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
-        if (!col.inmesh) return;
-        long long u = col.base + (long long)kbeg * sk;
-        const mgf *zp = a.z + u, *gp = a.diagf + u;
-        const double *dp = d_old + u;
-        double dm = 0, dc = 0;
-        if (kbeg >= 1) dm = (double)zp[-sk] + beta * dp[-sk];
-        dc = (double)zp[0] + beta * dp[0];
-        for (int k = kbeg; k < kend; k++, u += sk, zp += sk, dp += sk, gp += sk) {
-            const bool up = k + 1 < s.nk;
-            const double dn = up ? (double)zp[sk] + beta * dp[sk] : 0.0;
-            if (col.inner) {
-                // z and d are identically zero outside the REG set: no neighbour masks
-                const double dg = gp[0];
-                const double n_xm = (double)zp[-1] + beta * dp[-1], n_xp = (double)zp[1] + beta * dp[1];
-                const double n_ym = (double)zp[-sj] + beta * dp[-sj], n_yp = (double)zp[sj] + beta * dp[sj];
-                const double off = s.gdx2 * (n_xm + n_xp) + s.gdy2 * (n_ym + n_yp) + s.gdz2 * (dm + dn);
-                const double q = dc * (dg * dc - off);
-                acc += dg != 0 ? q : 0.0;
-            }
-            own.st(d_new, u, L0, 0, dc);
-            dm = dc; dc = dn;
-        }
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
+        long long up = col.pbase + (long long)kbeg * a.psk;
+        mg_ring_run(ring, md, &a.tm_z, &a.tm_g, nullptr, col, kbeg, kend, [&](int k, int m, int c, int p) {
+            const double *dm = ring.sd + m * MG_TD_SLOT + col.cd, *dc = ring.sd + c * MG_TD_SLOT + col.cd, *dp = ring.sd + p * MG_TD_SLOT + col.cd;
+            const mgf *zm = ring.sf + m * MG_TF_SLOT + col.cf, *zc = ring.sf + c * MG_TF_SLOT + col.cf, *zp = ring.sf + p * MG_TF_SLOT + col.cf;
+            const double dg = ring.sg[c * MG_TF_SLOT + col.cf];
+            // z and d are identically zero outside the REG set: no neighbour masks
+            const double n_c = (double)zc[0] + beta * dc[0];
+            const double n_xm = (double)zc[-1] + beta * dc[-1], n_xp = (double)zc[1] + beta * dc[1];
+            const double n_ym = (double)zc[-MG_TF_W] + beta * dc[-MG_TD_W], n_yp = (double)zc[MG_TF_W] + beta * dc[MG_TD_W];
+            const double n_zm = (double)zm[0] + beta * dm[0], n_zp = (double)zp[0] + beta * dp[0];
+            const double off = s.gdx2 * (n_xm + n_xp) + s.gdy2 * (n_ym + n_yp) + s.gdz2 * (n_zm + n_zp);
+            const double q = n_c * (dg * n_c - off);
+            acc += dg != 0 ? q : 0.0;
+            if (col.inmesh) own.st_k(d_new, up, k, 0, n_c);
+            up += a.psk;
+        });
     });
     return acc;
 }
 
 // Pass D: delta += alpha d ; r -= alpha K d ; returns the share of |r|^2
 template <class Own>
-__device__ __forceinline__ double mg_fine_res(const Own &own, const MgnArgs &a, const MgRuns &R, double alpha, const double *d)
+__device__ __forceinline__ double mg_fine_res(const Own &own, const MgnArgs &a, const MgRuns &R, MgRing &ring, double alpha, bool d_is_d0)
 {
     const StencilC &s = a.s;
-    const MgLevel &L0 = a.L[0];
-    const int sj = (int)s.sj;
-    const long long sk = s.sk;
+    const CUtensorMap *md = d_is_d0 ? &a.tm_d0 : &a.tm_d1;
     double acc = 0;
-    mg_for_runs(s, R, [&](const MgCol col, const int kbeg, const int kend) {
-        if (!col.inner) return;
-        long long u = col.base + (long long)kbeg * sk;
-        const double *dp = d + u;
-        const mgf *gp = a.diagf + u;
-        double dm = kbeg >= 1 ? dp[-sk] : 0.0, dc = dp[0];
-        for (int k = kbeg; k < kend; k++, u += sk, dp += sk, gp += sk) {
-            const double dn = k + 1 < s.nk ? dp[sk] : 0.0;
-            const double dg = gp[0];
-            const double d_xm = dp[-1], d_xp = dp[1], d_ym = dp[-sj], d_yp = dp[sj];
-            const double del = a.delta[u], rr = a.r[u];
-            if (dg != 0) {          // stores only: every load of the step is already in flight
-                const double q = dg * dc - (s.gdx2 * (d_xm + d_xp) + s.gdy2 * (d_ym + d_yp) + s.gdz2 * (dm + dn));
-                a.delta[u] = del + alpha * dc;
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
+        long long up = col.pbase + (long long)kbeg * a.psk;
+        // delta and r are read at the node only: straight from global memory, one plane ahead of their use
+        double del_n = 0, r_n = 0;
+        if (col.inmesh) { del_n = a.delta[up]; r_n = a.r[up]; }
+        mg_ring_run(ring, md, &a.tm_g, nullptr, nullptr, col, kbeg, kend, [&](int k, int m, int c, int p) {
+            const double del = del_n, rr = r_n;
+            if (col.inmesh && k + 1 < kend) { del_n = a.delta[up + a.psk]; r_n = a.r[up + a.psk]; }
+            const double *dm = ring.sd + m * MG_TD_SLOT + col.cd, *dc = ring.sd + c * MG_TD_SLOT + col.cd, *dp = ring.sd + p * MG_TD_SLOT + col.cd;
+            const double dg = ring.sf[c * MG_TF_SLOT + col.cf];
+            const double d0 = dc[0];
+            const double q = dg * d0 - (s.gdx2 * (dc[-1] + dc[1]) + s.gdy2 * (dc[-MG_TD_W] + dc[MG_TD_W]) + s.gdz2 * (dm[0] + dp[0]));
+            if (dg != 0) {
+                a.delta[up] = del + alpha * d0;
                 const double rn = rr - alpha * q;
-                own.st(a.r, u, L0, 0, rn);
+                a.r[up] = rn;                                   // r is read at the node only; the V-cycle reads its FP32 copy
+                own.st_k(a.rf, up, k, 0, (mgf)rn);
                 acc += rn * rn;
             }
-            dm = dc; dc = dn;
-        }
+            up += a.psk;
+        });
     });
     return acc;
 }
 
 // Newton linearisation at the current phi (the reference's GS residual with the Neumann face neighbours folded into the
 // node itself, PotentialSolver.cpp:389-421), Jacobian diagonal; delta = 0, d0 = 0.  Returns the share of |R|^2.
+// phi, rho and the node types are the caller's arrays (native layout), r / diagf / d0 / delta the solver's (padded rows).
 template <class Own>
-__device__ __forceinline__ double mg_linearise(const Own &own, const MgnArgs &a, long long t0, long long stride)
+__device__ __forceinline__ double mg_linearise(const Own &own, const MgnArgs &a, const MgRuns &R)
 {
     const StencilC &s = a.s;
-    const MgLevel &L0 = a.L[0];
     const double *phi = a.phi;
     double acc = 0;
-    for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
-        double r = 0;
-        mgf dj = 0;
-        // REG nodes are interior, so for u in [sk, nn - sk) every neighbour address is valid whatever the node is: all loads
-        // are issued at once and the node type only selects (no load waits for another load)
-        if (u >= s.sk && u < s.nn - s.sk) {
-            const int ty = a.type[u];
-            const bool fxm = a.type[u - 1] >= NT_I0, fxp = a.type[u + 1] >= NT_I0, fym = a.type[u - s.sj] >= NT_I0,
-                       fyp = a.type[u + s.sj] >= NT_I0, fzm = a.type[u - s.sk] >= NT_I0, fzp = a.type[u + s.sk] >= NT_I0;
-            const double p = phi[u], rho = a.rho[u];
-            const double pxm = phi[u - 1], pxp = phi[u + 1], pym = phi[u - s.sj], pyp = phi[u + s.sj], pzm = phi[u - s.sk], pzp = phi[u + s.sk];
-            if (ty == NT_REG) {
-                const double ex = exp((p - a.phi0) / a.Te0);
-                const double src = (rho - C_QE * (a.n0 * ex)) / C_EPS_0;
-                const double xm = fxm ? p : pxm, xp = fxp ? p : pxp;
-                const double ym = fym ? p : pym, yp = fyp ? p : pyp;
-                const double zm = fzm ? p : pzm, zp = fzp ? p : pzp;
-                r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
-                double d0 = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
-                if (fxm) d0 -= s.gdx2;
-                if (fxp) d0 -= s.gdx2;
-                if (fym) d0 -= s.gdy2;
-                if (fyp) d0 -= s.gdy2;
-                if (fzm) d0 -= s.gdz2;
-                if (fzp) d0 -= s.gdz2;
-                dj = (mgf)(d0 + a.n0 * C_QE / (C_EPS_0 * a.Te0) * ex);
-                acc += r * r;
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
+        if (!col.inmesh) return;
+        long long u = col.nbase + (long long)kbeg * s.sk, up = col.pbase + (long long)kbeg * a.psk;
+        for (int k = kbeg; k < kend; k++, u += s.sk, up += a.psk) {
+            double r = 0;
+            mgf dj = 0, wi = 0;
+            // REG nodes are interior: on an inner column away from the first and last plane every neighbour address is valid
+            // whatever the node is, so all loads are issued at once and the node type only selects
+            if (col.inner && k >= 1 && k + 1 < s.nk) {
+                const int ty = a.type[u];
+                const bool fxm = a.type[u - 1] >= NT_I0, fxp = a.type[u + 1] >= NT_I0, fym = a.type[u - s.sj] >= NT_I0,
+                           fyp = a.type[u + s.sj] >= NT_I0, fzm = a.type[u - s.sk] >= NT_I0, fzp = a.type[u + s.sk] >= NT_I0;
+                const double p = phi[u], rho = a.rho[u];
+                const double pxm = phi[u - 1], pxp = phi[u + 1], pym = phi[u - s.sj], pyp = phi[u + s.sj], pzm = phi[u - s.sk], pzp = phi[u + s.sk];
+                if (ty == NT_REG) {
+                    const double ex = exp((p - a.phi0) / a.Te0);
+                    const double src = (rho - C_QE * (a.n0 * ex)) / C_EPS_0;
+                    const double xm = fxm ? p : pxm, xp = fxp ? p : pxp;
+                    const double ym = fym ? p : pym, yp = fyp ? p : pyp;
+                    const double zm = fzm ? p : pzm, zp = fzp ? p : pzp;
+                    r = -p * (2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2) + src + s.gdx2 * (xm + xp) + s.gdy2 * (ym + yp) + s.gdz2 * (zm + zp);
+                    double d0 = 2 * s.gdx2 + 2 * s.gdy2 + 2 * s.gdz2;
+                    if (fxm) d0 -= s.gdx2;
+                    if (fxp) d0 -= s.gdx2;
+                    if (fym) d0 -= s.gdy2;
+                    if (fyp) d0 -= s.gdy2;
+                    if (fzm) d0 -= s.gdz2;
+                    if (fzp) d0 -= s.gdz2;
+                    const double djd = d0 + a.n0 * C_QE / (C_EPS_0 * a.Te0) * ex;
+                    dj = (mgf)djd;
+                    wi = (mgf)(MG_OMEGA / djd);
+                    acc += r * r;
+                }
             }
+            a.r[up] = r;
+            own.st_k(a.rf, up, k, 0, (mgf)r);
+            own.st_k(a.winv, up, k, 0, wi);
+            a.diagf[up] = dj;                                   // read at the node only (passes C and D, the coarse diagonals)
+            own.st_k(a.d0, up, k, 0, 0.0);
+            a.delta[up] = 0;
         }
-        own.st(a.r, u, L0, 0, r);
-        own.st(a.diagf, u, L0, 0, dj);
-        own.st(a.d0, u, L0, 0, 0.0);
-        a.delta[u] = 0;
-    }
+    });
     return acc;
 }
 
 // phi += delta on the unknowns; sum of delta^2 counted once per node that takes the value (the node + the face nodes
 // mirroring it), i.e. the reference's sum over all nodes of y^2 (PotentialSolver.cpp:279-283)
 template <class Own>
-__device__ __forceinline__ double mg_update(const Own &own, const MgnArgs &a, long long t0, long long stride)
+__device__ __forceinline__ double mg_update(const Own &own, const MgnArgs &a, const MgRuns &R)
 {
     const StencilC &s = a.s;
-    const MgLevel &L0 = a.L[0];
     double acc = 0;
-    for (long long u = max(own.lo(L0, 0), s.sk) + t0; u < min(own.hi(L0, 0), s.nn - s.sk); u += stride) {      // REG nodes are interior
-        const int ty = a.type[u];
-        const int cnt = 1 + (a.type[u - 1] >= NT_I0) + (a.type[u + 1] >= NT_I0) + (a.type[u - s.sj] >= NT_I0) + (a.type[u + s.sj] >= NT_I0) +
-                        (a.type[u - s.sk] >= NT_I0) + (a.type[u + s.sk] >= NT_I0);
-        const double dl = a.delta[u], p = a.phi[u];
-        if (ty != NT_REG) continue;
-        own.st(a.phi, u, L0, 0, p + dl);
-        acc += cnt * (dl * dl);
-    }
+    mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
+        if (!col.inner) return;                                   // REG nodes are interior
+        long long u = col.nbase + (long long)kbeg * s.sk, up = col.pbase + (long long)kbeg * a.psk;
+        for (int k = kbeg; k < kend; k++, u += s.sk, up += a.psk) {
+            if (k < 1 || k + 1 >= s.nk) continue;
+            const int ty = a.type[u];
+            const int cnt = 1 + (a.type[u - 1] >= NT_I0) + (a.type[u + 1] >= NT_I0) + (a.type[u - s.sj] >= NT_I0) + (a.type[u + s.sj] >= NT_I0) +
+                            (a.type[u - s.sk] >= NT_I0) + (a.type[u + s.sk] >= NT_I0);
+            const double dl = a.delta[up], p = a.phi[u];
+            if (ty != NT_REG) continue;
+            own.st_k(a.phi, u, k, 0, p + dl);
+            acc += cnt * (dl * dl);
+        }
+    });
     return acc;
 }
 
@@ -912,19 +1010,22 @@ __device__ __forceinline__ double mg_total(const Own &own, const double *part, i
 
 // z = M^-1 r (one V-cycle); returns this thread's share of r.z.  Ends WITHOUT a barrier.  ok = false: a slab barrier gave up.
 template <class Own>
-__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, const MgnArgs &a, const MgRuns &R, long long t0,
+__device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, const MgnArgs &a, const MgRuns &R, MgRing &ring, long long t0,
                                             long long stride, mgf *smem, unsigned long long &tick, bool &ok)
 {
-    const MgLevel &L0 = a.L[0];
-    if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
+        if (a.nlev == 1) {           // degenerate hierarchy (tiny mesh): plain Jacobi preconditioner
         double acc = 0;
-        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) {
-            const mgf dg = a.diagf[u];
-            const double rr = a.r[u];
-            const mgf zf = dg != (mgf)0 ? (mgf)(rr * (double)__frcp_rn(dg)) : (mgf)0;
-            own.st(a.z, u, L0, 0, zf);
-            acc += rr * (double)zf;
-        }
+        mg_for_runs(a, R, [&](const MgCol col, const int kbeg, const int kend) {
+            if (!col.inmesh) return;
+            long long up = col.pbase + (long long)kbeg * a.psk;
+            for (int k = kbeg; k < kend; k++, up += a.psk) {
+                const mgf dg = a.diagf[up];
+                const double rr = a.r[up];
+                const mgf zf = dg != (mgf)0 ? (mgf)(rr * (double)__frcp_rn(dg)) : (mgf)0;
+                own.st_k(a.z, up, k, 0, zf);
+                acc += rr * (double)zf;
+            }
+        });
         return acc;
     }
     // The coarse levels are tiny: in slab mode the right-hand side of level `lr` (a.first_redundant; at the latest the
@@ -934,7 +1035,7 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
     int lr = lc;
     if constexpr (Own::slab) lr = a.first_redundant;
     OwnAll whole;
-    mg_fine_down(own, a, R, lr == 1);
+    mg_fine_down(own, a, R, ring, lr == 1);
     ok = own.barrier(grid) && ok;
     MG_TICK(0);
     for (int l = 1; l + 1 < a.nlev; l++) {
@@ -960,11 +1061,11 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
         e = a.L[l].xn;
     }
     MG_TICK(3);
-    return mg_fine_up(own, a, R, e);
+    return mg_fine_up(own, a, R, ring, e);
 }
 
 template <class Own>
-__device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
+__device__ __forceinline__ void mgn_body(const MgnArgs &a, Own &own, unsigned char *smem_raw)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
@@ -978,6 +1079,9 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
     double *pA = a.part, *pB = a.part + np, *pC = a.part + 2 * np;
     const MgRuns R = mg_runs(own, a);
     const double nn = (double)s.nn;
+    mgf *smem = reinterpret_cast<mgf *>(smem_raw);                // the coarsest level's arrays, then the TMA ring
+    MgRing ring;
+    mg_ring_init(ring, smem_raw + a.smem_ring_off);
     bool ok = true;
     unsigned long long tick = mg_now();
 
@@ -985,7 +1089,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
         // working copy of phi inside the pool: this rank's planes plus one halo plane on each side (kept current afterwards
         // by the peer stores of the update pass)
         const long long plane = s.sk;
-        const long long lo = max(0ll, own.lo(L0, 0) - plane), hi = min(s.nn, own.hi(L0, 0) + plane);
+        const long long lo = max(0ll, (long long)own.klo(L0, 0) * plane - plane), hi = min(s.nn, (long long)own.khi(L0, 0) * plane + plane);
         for (long long u = lo + t0; u < hi; u += stride) a.phi[u] = a.phi_user[u];
         ok = own.lbarrier(grid) && ok;
     }
@@ -996,7 +1100,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
     double ynorm = 0, Rn = 0, Rprev = 0, R0 = 0, l2 = 0;
     for (nit = 0;; nit++) {
         // ---- linearise at the current phi
-        double acc = mg_linearise(own, a, t0, stride);
+        double acc = mg_linearise(own, a, R);
         double t = block_sum(acc, sh);
         if (threadIdx.x == 0) own.put_partial(pC, nb, t);
         ok = own.barrier(grid) && ok;
@@ -1022,7 +1126,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
                     ok = own.lbarrier(grid) && ok;
                 } else {
                     const bool to_all = Own::slab && l == lr;
-                    if (l == 1) mg_diag1(own, s, a.type, a.diagf, a.L[1], t0, stride, to_all);
+                    if (l == 1) mg_diag1(own, s, a.type, a.diagf, a.pitch, a.L[1], t0, stride, to_all);
                     else mg_diagl(own, a.L[l - 1], a.L[l], l, t0, stride, to_all);
                     ok = own.barrier(grid) && ok;
                 }
@@ -1037,10 +1141,10 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
         l2 = Rn;
         int it = 0;
         double rz = 0;
-        double *d_old = a.d0, *d_new = a.d1;
+        bool d_is_d0 = true;          // which of d0 / d1 holds the previous search direction
         while (ok && l2 >= stop && it < a.max_it) {
             // z = M^-1 r ; rz' = r.z
-            acc = mg_vcycle(grid, own, a, R, t0, stride, smem, tick, ok);
+            acc = mg_vcycle(grid, own, a, R, ring, t0, stride, smem, tick, ok);
             t = block_sum(acc, sh);
             if (threadIdx.x == 0) own.put_partial(pB, nb, t);
             ok = own.barrier(grid) && ok;
@@ -1049,7 +1153,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
             const double beta = (it == 0) ? 0.0 : rz_new / rz;
             rz = rz_new;
             // d = z + beta d ; dq = d.K d
-            acc = mg_fine_dir(own, a, R, beta, d_old, d_new);
+            acc = mg_fine_dir(own, a, R, ring, beta, d_is_d0);
             t = block_sum(acc, sh);
             if (threadIdx.x == 0) own.put_partial(pA, nb, t);
             ok = own.barrier(grid) && ok;
@@ -1058,14 +1162,14 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
             if (!(dq > 0)) { lin_fail = 1; break; }          // breakdown (cannot happen for an SPD system short of overflow): give up cleanly
             const double alpha = rz / dq;
             // delta += alpha d ; r -= alpha K d ; |r|
-            acc = mg_fine_res(own, a, R, alpha, d_new);
+            acc = mg_fine_res(own, a, R, ring, alpha, !d_is_d0);
             t = block_sum(acc, sh);
             if (threadIdx.x == 0) own.put_partial(pC, nb, t);
             ok = own.barrier(grid) && ok;
             MG_TICK(6);
             l2 = sqrt(mg_total(own, pC, nb, sh, &bc) / nn);
             it++;
-            double *tmp = d_old; d_old = d_new; d_new = tmp;
+            d_is_d0 = !d_is_d0;
         }
         if (l2 >= stop) lin_fail = 1;
         last_full = stop <= 0.5 * a.tol && l2 < stop;
@@ -1073,7 +1177,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
         if (blockIdx.x == 0 && threadIdx.x == 0 && nit < 10) a.out[MGN_OUT_HIST + 2 * nit + 1] = it;
         if (!ok) break;
         // ---- phi += delta
-        acc = mg_update(own, a, t0, stride);
+        acc = mg_update(own, a, R);
         t = block_sum(acc, sh);
         if (threadIdx.x == 0) own.put_partial(pA, nb, t);
         ok = own.barrier(grid) && ok;
@@ -1081,7 +1185,7 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
         MG_TICK(9);
     }
     if constexpr (Own::slab) {
-        for (long long u = own.lo(L0, 0) + t0; u < own.hi(L0, 0); u += stride) a.phi_user[u] = a.phi[u];
+        for (long long u = (long long)own.klo(L0, 0) * s.sk + t0; u < (long long)own.khi(L0, 0) * s.sk; u += stride) a.phi_user[u] = a.phi[u];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.out[MGN_OUT_CONVERGED] = converged; a.out[MGN_OUT_NEWTON] = nit; a.out[MGN_OUT_LIN] = (double)lin_total;
@@ -1090,16 +1194,16 @@ __device__ __forceinline__ void mgn_body(MgnArgs &a, Own &own, mgf *smem)
     }
 }
 
-extern __shared__ mgf mgn_smem[];
+extern __shared__ __align__(128) unsigned char mgn_smem[];
 
-__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton(MgnArgs a)
+__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton(const __grid_constant__ MgnArgs a)
 {
     OwnAll own;
     mgn_body(a, own, mgn_smem);
 }
 
 // slab-decomposed variant: one of these kernels per rank, running concurrently, talking through peer memory only
-__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton_slab(MgnArgs a, OwnSlab own, unsigned long long *epoch_io)
+__global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton_slab(const __grid_constant__ MgnArgs a, OwnSlab own, unsigned long long *epoch_io)
 {
     own.epoch = epoch_io[0];
     own.lepoch = epoch_io[1];
@@ -1109,6 +1213,8 @@ __global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton_slab(MgnArgs a, Own
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
+
+static inline int mg_pitch(int ni) { return (ni + 3) & ~3; }
 
 // number of levels, their dimensions and per-dimension coarsening shifts for an (ni,nj,nk) mesh with spacings dh
 static int mg_level_dims(const StencilC &s, long long dims[MG_MAX_LEVELS][3], int shifts[MG_MAX_LEVELS][3])
@@ -1238,6 +1344,7 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, mgf *extern
         L.ni = (int)dims[l][0]; L.nj = (int)dims[l][1]; L.nk = (int)dims[l][2];
         L.fi = shifts[l][0]; L.fj = shifts[l][1]; L.fk = shifts[l][2];
         L.nn = dims[l][0] * dims[l][1] * dims[l][2];
+        L.pitch = l == 0 ? mg_pitch(L.ni) : L.ni;
         if (l == 0) { L.diag = L.minv = L.cx = L.cy = L.cz = L.x = L.xn = L.b = L.dlx = L.dly = L.dlz = L.mass = nullptr; continue; }
         const long long pad = (L.nn + 3) & ~3ll;           // keep every array 16-byte aligned
         L.diag = p; p += pad; L.minv = p; p += pad; L.cx = p; p += pad; L.cy = p; p += pad; L.cz = p; p += pad;
@@ -1255,12 +1362,64 @@ static int mg_setup(espic_ctx *c, const StencilC &s, MgHierarchy *H, mgf *extern
     return 0;
 }
 
-static size_t mg_smem_bytes(const MgHierarchy *H)
+// dynamic shared memory: the coarsest level's arrays, then (128-byte aligned) the TMA ring
+static size_t mg_smem_coarse_bytes(const MgHierarchy *H)
 {
-    if (H->nlev <= 1) return 0;
-    const MgLevel &L = H->L[H->nlev - 1];
-    if (L.nn <= MG_STAGE_NODES) return (size_t)8 * (L.nn + 2 * (long long)L.ni * L.nj) * sizeof(mgf);
-    return (size_t)3 * L.nn * sizeof(mgf);
+    size_t b = 0;
+    if (H->nlev > 1) {
+        const MgLevel &L = H->L[H->nlev - 1];
+        b = L.nn <= MG_STAGE_NODES ? (size_t)8 * (L.nn + 2 * (long long)L.ni * L.nj) * sizeof(mgf) : (size_t)3 * L.nn * sizeof(mgf);
+    }
+    return (b + 127) & ~(size_t)127;
+}
+static size_t mg_smem_bytes(const MgHierarchy *H) { return mg_smem_coarse_bytes(H) + MG_RING_BYTES; }
+
+// 3-D tensor map of one padded fine vector: box = one plane of a tile plus halo.  The encoder lives in libcuda; it is looked
+// up through the runtime so that this library needs no link-time dependency on the driver.
+static int mg_make_map(CUtensorMap *m, void *base, bool f64, int pitch, int nj, int nk)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+            espic_set_error("cuTensorMapEncodeTiled is not available from this driver (the multigrid solver stages its tiles with TMA)");
+            return -1;
+        }
+        fn = (EncodeFn)p;
+    }
+    const cuuint64_t es = f64 ? 8 : 4;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)nj, (cuuint64_t)nk};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * nj * es};
+    const cuuint32_t box[3] = {(cuuint32_t)(f64 ? MG_TD_W : MG_TF_W), MG_TY + 2, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { espic_set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d vector", (int)r, pitch, nj, nk); return -1; }
+    return 0;
+}
+
+// fine vectors in one block of 6 * nnp doubles: r | delta | d0 | d1 (FP64), then z | diagf | winv | rf (FP32)
+static int mg_fill_fine(MgnArgs &a, const StencilC &s, const MgHierarchy *H, double *base, long long nnp)
+{
+    a.pitch = H->L[0].pitch;
+    a.psk = (long long)a.pitch * s.nj;
+    double *r = base, *delta = base + nnp, *d0 = base + 2 * nnp, *d1 = base + 3 * nnp;
+    mgf *z = reinterpret_cast<mgf *>(base + 4 * nnp), *diagf = z + nnp, *winv = z + 2 * nnp, *rf = z + 3 * nnp;
+    a.r = r; a.delta = delta; a.d0 = d0; a.d1 = d1; a.z = z; a.diagf = diagf; a.winv = winv; a.rf = rf;
+    a.smem_ring_off = (int)mg_smem_coarse_bytes(H);
+    int rc;
+    if ((rc = mg_make_map(&a.tm_rf, rf, false, a.pitch, s.nj, s.nk))) return rc;
+    if ((rc = mg_make_map(&a.tm_w, winv, false, a.pitch, s.nj, s.nk))) return rc;
+    if ((rc = mg_make_map(&a.tm_d0, d0, true, a.pitch, s.nj, s.nk))) return rc;
+    if ((rc = mg_make_map(&a.tm_d1, d1, true, a.pitch, s.nj, s.nk))) return rc;
+    if ((rc = mg_make_map(&a.tm_z, z, false, a.pitch, s.nj, s.nk))) return rc;
+    if ((rc = mg_make_map(&a.tm_g, diagf, false, a.pitch, s.nj, s.nk))) return rc;
+    return 0;
 }
 
 template <typename K>
@@ -1311,7 +1470,6 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
 {
     int r;
     if ((r = ensure_node_types(c, 0))) return r;
-    if ((r = ensure_sv(c, 8))) return r;
     StencilC s = make_stencil(c->m);
     MgHierarchy *H = g_mg_of(c);
     if ((r = mg_setup(c, s, H, nullptr))) return r;
@@ -1326,8 +1484,16 @@ static int solve_nrpcg_mg(espic_ctx *c, const espic_solve_params *p, espic_solve
     a.s = s; a.nlev = H->nlev; a.coarse_sweeps = kn.coarse_sweeps; a.first_redundant = H->nlev - 1;
     for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
     a.type = c->node_type; a.rho = c->rho; a.phi = c->phi; a.phi_user = c->phi;
-    a.r = c->sv[1]; a.delta = c->sv[4]; a.d0 = c->sv[6]; a.d1 = c->sv[7];
-    a.diagf = reinterpret_cast<mgf *>(c->sv[2]); a.z = reinterpret_cast<mgf *>(c->sv[5]);
+    {
+        const long long nnp = (long long)H->L[0].pitch * s.nj * s.nk;
+        if (H->fine_nnp != nnp) {
+            if (H->fine) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(H->fine)); H->fine = nullptr; }
+            CK(cudaMalloc(&H->fine, (size_t)nnp * 6 * sizeof(double)));                 // 4 double + 4 float vectors
+            CK(cudaMemsetAsync(H->fine, 0, (size_t)nnp * 6 * sizeof(double), c->stream));  // the row pads must be (and stay) zero
+            H->fine_nnp = nnp;
+        }
+        if ((r = mg_fill_fine(a, s, H, H->fine, nnp))) return r;
+    }
     a.part = c->red;
     a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
     a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
@@ -1361,8 +1527,9 @@ struct SlabState {
     size_t pool_doubles = 0;
     void *peer_base[MG_MAX_RANKS] = {nullptr};
     // carved arrays
-    double *R, *delta, *d0, *d1, *phi, *part;
-    mgf *z, *diagf, *coarse;
+    double *fine, *phi, *part;
+    long long nnp;
+    mgf *coarse;
     unsigned long long *flags, *epoch, *arrive, *release, *abort_word, *larrive, *lrelease;
     MgHierarchy H;
     OwnSlab own;
@@ -1397,15 +1564,15 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     }
     const int planes = s.nk / c->nranks;
     // ---- pool: identical carving on every rank (counted in doubles; FP32 arrays take half)
-    const long long nnp = (s.nn + 1) & ~1ll;
+    const long long nnp = (long long)mg_pitch(s.ni) * s.nj * s.nk;          // padded rows (a multiple of 4 elements)
     const long long coarse = (mg_coarse_elems(s) + 1) / 2;
     const long long nparts = 3ll * c->nranks * 1024;
-    S->pool_doubles = (size_t)(5 * nnp + nnp + coarse + nparts + 256);
+    S->pool_doubles = (size_t)(6 * nnp + nnp + coarse + nparts + 256);
     CK(cudaMalloc(&S->pool, S->pool_doubles * sizeof(double)));
     CK(cudaMemsetAsync(S->pool, 0, S->pool_doubles * sizeof(double), c->stream));
     double *p = S->pool;
-    S->R = p; p += nnp; S->delta = p; p += nnp; S->d0 = p; p += nnp; S->d1 = p; p += nnp; S->phi = p; p += nnp;
-    S->z = reinterpret_cast<mgf *>(p); p += nnp / 2; S->diagf = reinterpret_cast<mgf *>(p); p += nnp / 2;
+    S->fine = p; p += 6 * nnp; S->phi = p; p += nnp;          // fine vectors (mg_fill_fine's layout), working copy of phi
+    S->nnp = nnp;
     S->coarse = reinterpret_cast<mgf *>(p); p += coarse;
     S->part = p; p += nparts;
     S->flags = reinterpret_cast<unsigned long long *>(p); p += 16;
@@ -1482,7 +1649,7 @@ static int solve_nrpcg_mg_slab(espic_ctx *c, const espic_solve_params *p, espic_
     }
     for (int l = 0; l < H->nlev; l++) a.L[l] = H->L[l];
     a.type = c->node_type; a.rho = c->rho; a.phi = S->phi; a.phi_user = c->phi;
-    a.r = S->R; a.delta = S->delta; a.d0 = S->d0; a.d1 = S->d1; a.diagf = S->diagf; a.z = S->z;
+    if ((r = mg_fill_fine(a, s, H, S->fine, S->nnp))) return r;
     a.part = S->part;
     a.phi0 = p->phi0; a.Te0 = p->Te0; a.n0 = p->n0;
     a.max_it = p->max_it; a.nr_max_it = p->nr_max_it; a.tol = p->tol; a.nr_tol = p->nr_tol;
