@@ -393,7 +393,7 @@ class Case:
         if ev:
             ev[1].record()
         k_ms = e.last_push_ms() if rec is not None else 0.0    # CUDA events around the k_push launch itself, on the launching stream
-        if self.sort_every > 0 and i % self.sort_every == 0 and not self.fuse:
+        if self.sort_every > 0 and i % self.sort_every == 0:
             e.sort_particles(sp, self.sort_order)       # between push and deposit: the scatter sees perfectly ordered particles
         if ev:
             ev[2].record()

@@ -282,26 +282,141 @@ static_assert(DT_SLOTS >= DT_TILE && DT_SLOTS == (1 << DT_SLOT_BITS), "one hash 
 // GROUP = false skips steps 1b and 2 (hash, scan, placement): each thread then merges DT_PER CONSECUTIVE particles of the
 // stream.  That is the right kernel while the stream is still in cell order (runs of ~100 particles per cell): it needs a
 // quarter of the warp shuffles of k_deposit (one segmented reduction per 4 particles instead of per 2) and no hashing.
+
+// shared-memory working set of one tile (45 KB)
+struct DepTile {
+    double sx[DT_TILE], sy[DT_TILE], sz[DT_TILE], sw[DT_TILE];      // cell fractions and weight of every particle of the tile
+    uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS];                        // hash table: lower node of the cell; slot counts, then offsets
+    uint16_t pslot[DT_TILE], order[DT_TILE];
+    uint32_t wsum[DT_THREADS / 32];
+    uint32_t n_sorted;
+};
+
+__device__ __forceinline__ void dt_clear(DepTile &t)
+{
+#pragma unroll
+    for (int q = threadIdx.x; q < DT_SLOTS; q += DT_THREADS) { t.hkey[q] = DT_EMPTY; t.hcnt[q] = 0; }
+}
+
+// Step 1 for one particle per lane (whole-warp call): entry p of the tile is the particle at (px,py,pz) with weight pw
+// (0 = nothing to deposit).  Lanes with the same cell elect one leader that talks to the hash table (a freshly sorted tile
+// would otherwise send 32 CAS + 32 adds to the same shared-memory word).
+template <bool GROUP>
+__device__ __forceinline__ void dt_insert(const MeshC &m, DepTile &t, int p, double px, double py, double pz, double pw)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t key = DT_EMPTY;
+    double d0 = 0, d1 = 0, d2 = 0;
+    if (pw != 0) {
+        int ci, cj, ck;
+        cell3(m, px, py, pz, ci, cj, ck, d0, d1, d2);
+        if (ci >= 0 && cj >= 0 && ck >= 0) key = (uint32_t)node_u(m, ci, cj, ck);
+    }
+    // only the fractions are needed from here on; the cell is recovered from the hash slot (hkey[slot] = lower node of the cell)
+    t.sx[p] = d0; t.sy[p] = d1; t.sz[p] = d2; t.sw[p] = pw;
+    if (!GROUP) {           // no grouping: remember the cell's lower node per particle (hkey doubles as that array)
+        t.hkey[p] = key;
+        return;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t slot = 0xffffu;          // 0xffff: nothing to deposit (the table has a slot per particle of the tile, it cannot fill up)
+    if (key != DT_EMPTY && lane == leader) {
+        uint32_t h = (key * 2654435761u) >> (32 - DT_SLOT_BITS);
+        for (int probe = 0; probe < DT_SLOTS; probe++) {
+            const uint32_t old = atomicCAS(&t.hkey[h], DT_EMPTY, key);
+            if (old == DT_EMPTY || old == key) { slot = h; break; }
+            h = (h + 1) & (DT_SLOTS - 1);
+        }
+        if (slot < DT_SLOTS) atomicAdd(&t.hcnt[slot], (uint32_t)__popc(peers));
+    }
+    slot = __shfl_sync(0xffffffffu, slot, leader);
+    t.pslot[p] = (uint16_t)slot;
+}
+
+// Steps 2 and 3 (whole-block call, after a __syncthreads behind the last dt_insert): counting sort of the particle ids by hash
+// slot, then every thread merges DT_PER consecutive entries of that order, the warp merges runs, run heads issue the REDs.
+template <int MODE, int STRIDE, bool GROUP>
+__device__ __forceinline__ void dt_finish(const MeshC &m, DepTile &t, double *acc, double scale)
+{
+    typedef typename AccVal<MODE>::T T;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (GROUP) {
+        {
+            constexpr int PER = DT_SLOTS / DT_THREADS;
+            uint32_t cnt[PER], tsum = 0;
+#pragma unroll
+            for (int q = 0; q < PER; q++) { cnt[q] = t.hcnt[tid * PER + q]; tsum += cnt[q]; }
+            uint32_t inc = tsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) t.wsum[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t run = inc - tsum;
+            for (int w = 0; w < (tid >> 5); w++) run += t.wsum[w];
+#pragma unroll
+            for (int q = 0; q < PER; q++) { t.hcnt[tid * PER + q] = run; run += cnt[q]; }
+            if (tid == DT_THREADS - 1) t.n_sorted = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < DT_PER; j++) {
+            const int p = j * DT_THREADS + tid;
+            const uint32_t slot = t.pslot[p];
+            const unsigned peers = __match_any_sync(0xffffffffu, slot);
+            const int leader = __ffs(peers) - 1;
+            uint32_t at = 0;
+            if (slot < DT_SLOTS && lane == leader) at = atomicAdd(&t.hcnt[slot], (uint32_t)__popc(peers));
+            at = __shfl_sync(0xffffffffu, at, leader);
+            if (slot < DT_SLOTS) t.order[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)p;
+        }
+        __syncthreads();
+    }
+    const int M = GROUP ? (int)t.n_sorted : DT_TILE;
+    T a[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = 0;
+    long long ua = -1;
+#pragma unroll
+    for (int j = 0; j < DT_PER; j++) {
+        const int q = tid * DT_PER + j;
+        if (q >= M) break;
+        const int p = GROUP ? t.order[q] : q;
+        T v[8];
+        const uint32_t cellu = GROUP ? t.hkey[t.pslot[p]] : t.hkey[p];
+        if (!GROUP && cellu == DT_EMPTY) continue;                // nothing to deposit (dead slot, tail of the last tile)
+        const long long u = (long long)cellu;
+        weights_from_fractions<MODE>(t.sx[p], t.sy[p], t.sz[p], t.sw[p], scale, v);
+        if (u != ua) {
+            if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
+            ua = u;
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = v[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] += v[c];
+        }
+    }
+    warp_deposit<MODE, STRIDE>(m, acc, ua, a);
+}
+
 template <int MODE, int VAL = 0, int STRIDE = 1, bool GROUP = true>
 __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
                                                               const double *__restrict__ z, const double *__restrict__ mpw,
                                                               long long n, double *acc, double scale, int ahead,
                                                               const double *__restrict__ vcomp = nullptr)
 {
-    typedef typename AccVal<MODE>::T T;
-    __shared__ double sx[DT_TILE], sy[DT_TILE], sz[DT_TILE], sw[DT_TILE];
-    __shared__ uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS];     // hcnt: slot counts, then (after the scan) slot offsets
-    __shared__ uint16_t pslot[DT_TILE], order[DT_TILE];
-    __shared__ uint32_t wsum[DT_THREADS / 32];
-    __shared__ uint32_t n_sorted;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ DepTile t;
+    const int tid = threadIdx.x;
     const long long base = blockIdx.x * (long long)DT_TILE;
     if (tid < 4) {
         const long long pf = base + (long long)ahead * DT_TILE;
         if (ahead > 0 && pf + DT_TILE <= n) l2_prefetch((tid == 0 ? x : tid == 1 ? y : tid == 2 ? z : mpw) + pf, DT_TILE * 8);
     }
-#pragma unroll
-    for (int t = tid; t < DT_SLOTS; t += DT_THREADS) { hkey[t] = DT_EMPTY; hcnt[t] = 0; }
+    dt_clear(t);
     __syncthreads();
     // ---- 1. load, hash, count
 #pragma unroll
@@ -316,107 +431,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
             if (VAL == 2) { W.x = W.x * V.x; W.y = W.y * V.y; }       // (mpw*v)*v
         }
         if (g + 1 >= n) W.y = 0;
-        sx[p] = X.x; sx[p + 1] = X.y; sy[p] = Y.x; sy[p + 1] = Y.y;
-        sz[p] = Z.x; sz[p + 1] = Z.y; sw[p] = W.x; sw[p + 1] = W.y;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const double px = q ? X.y : X.x, py = q ? Y.y : Y.x, pz = q ? Z.y : Z.x, pw = q ? W.y : W.x;
-            // slot 0xffff: nothing to deposit (the table has a slot for every particle of the tile, it cannot fill up).  Lanes with the same cell elect one leader that talks to the
-            // hash table (a freshly sorted tile would otherwise send 32 CAS + 32 adds to the same shared-memory word)
-            uint32_t key = DT_EMPTY;
-            if (pw != 0) {
-                int ci, cj, ck; double d0, d1, d2;
-                cell3(m, px, py, pz, ci, cj, ck, d0, d1, d2);
-                if (ci >= 0 && cj >= 0 && ck >= 0) {
-                    key = (uint32_t)node_u(m, ci, cj, ck);
-                    // from here on only the fractions are needed: they replace the position in shared memory, the cell is
-                    // recovered from the hash slot (hkey[slot] is the lower node index of the cell)
-                    sx[p + q] = d0; sy[p + q] = d1; sz[p + q] = d2;
-                }
-            }
-            if (!GROUP) {           // no grouping: remember the cell's lower node per particle (hkey doubles as that array)
-                hkey[p + q] = key;
-                continue;
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const int leader = __ffs(peers) - 1;
-            uint32_t slot = 0xffffu;
-            if (key != DT_EMPTY && lane == leader) {
-                uint32_t h = (key * 2654435761u) >> (32 - DT_SLOT_BITS);
-                for (int probe = 0; probe < DT_SLOTS; probe++) {
-                    const uint32_t old = atomicCAS(&hkey[h], DT_EMPTY, key);
-                    if (old == DT_EMPTY || old == key) { slot = h; break; }
-                    h = (h + 1) & (DT_SLOTS - 1);
-                }
-                if (slot < DT_SLOTS) atomicAdd(&hcnt[slot], (uint32_t)__popc(peers));
-            }
-            slot = __shfl_sync(0xffffffffu, slot, leader);
-            pslot[p + q] = (uint16_t)slot;
-        }
+        dt_insert<GROUP>(m, t, p, X.x, Y.x, Z.x, W.x);
+        dt_insert<GROUP>(m, t, p + 1, X.y, Y.y, Z.y, W.y);
     }
     __syncthreads();
-    // ---- 2. exclusive scan of the slot counts (DT_SLOTS / DT_THREADS consecutive entries per thread), then place the ids
-    if (GROUP) {
-        constexpr int PER = DT_SLOTS / DT_THREADS;
-        uint32_t cnt[PER], tsum = 0;
-#pragma unroll
-        for (int q = 0; q < PER; q++) { cnt[q] = hcnt[tid * PER + q]; tsum += cnt[q]; }
-        uint32_t inc = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) wsum[tid >> 5] = inc;
-        __syncthreads();
-        uint32_t run = inc - tsum;
-        for (int w = 0; w < (tid >> 5); w++) run += wsum[w];
-#pragma unroll
-        for (int q = 0; q < PER; q++) { hcnt[tid * PER + q] = run; run += cnt[q]; }
-        if (tid == DT_THREADS - 1) n_sorted = run;
-    }
-    if (GROUP) {
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < DT_PER; j++) {
-        const int p = j * DT_THREADS + tid;
-        const uint32_t slot = pslot[p];
-        const unsigned peers = __match_any_sync(0xffffffffu, slot);
-        const int leader = __ffs(peers) - 1;
-        uint32_t at = 0;
-        if (slot < DT_SLOTS && lane == leader) at = atomicAdd(&hcnt[slot], (uint32_t)__popc(peers));
-        at = __shfl_sync(0xffffffffu, at, leader);
-        if (slot < DT_SLOTS) order[at + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)p;
-    }
-    __syncthreads();
-    }
-    // ---- 3. walk the grouped order: DT_PER consecutive entries per thread, merged in registers, then across the warp
-    const int M = GROUP ? (int)n_sorted : DT_TILE;
-    T a[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) a[t] = 0;
-    long long ua = -1;
-#pragma unroll
-    for (int j = 0; j < DT_PER; j++) {
-        const int q = tid * DT_PER + j;
-        if (q >= M) break;
-        const int p = GROUP ? order[q] : q;
-        T v[8];
-        const uint32_t cellu = GROUP ? hkey[pslot[p]] : hkey[p];
-        if (!GROUP && cellu == DT_EMPTY) continue;                // nothing to deposit (dead slot, tail of the last tile)
-        const long long u = (long long)cellu;
-        weights_from_fractions<MODE>(sx[p], sy[p], sz[p], sw[p], scale, v);
-        if (u != ua) {
-            if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // rare: a cell boundary inside this thread's four entries
-            ua = u;
-#pragma unroll
-            for (int t = 0; t < 8; t++) a[t] = v[t];
-        } else {
-#pragma unroll
-            for (int t = 0; t < 8; t++) a[t] += v[t];
-        }
-    }
-    warp_deposit<MODE, STRIDE>(m, acc, ua, a);
+    dt_finish<MODE, STRIDE, GROUP>(m, t, acc, scale);
 }
 
 // den = acc / node_vol (0 where node_vol == 0): Field::operator/= (Field.h:125-134)
@@ -550,6 +569,74 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
     if (FUSE) deposit_pair<MODE>(m, acc, scale, v0 && !dead0, X.x, Y.x, Z.x, W.x, v1 && !dead1, X.y, Y.y, Z.y, W.y);
 }
 
+// Push with the tile-grouping scatter fused in (ESPIC_PUSH_FUSE_DEPOSIT): a block owns DT_TILE = 1024 consecutive particles,
+// pushes them two per thread in two rounds exactly as k_push does (same loads, same arithmetic, same kill words), and hands
+// every survivor's NEW position to the shared-memory grouping of k_deposit_tile while it is still in registers.  Against
+// k_push + k_deposit_tile this saves the second read of x, y, z, mpw (32 of 136 bytes per particle) and a launch, and the
+// hashing overlaps the push's memory time (the push alone runs at 84 % of the HBM peak with most issue slots idle).
+template <int WALL, int MODE>
+__global__ void __launch_bounds__(DT_THREADS, 4) k_push_tile(MeshC m, const double *__restrict__ ef4,
+                                                             double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
+                                                             double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
+                                                             double *__restrict__ pmpw, long long n, double s, double dt,
+                                                             uint32_t *__restrict__ dead_words, double *acc, double scale, int ahead)
+{
+    __shared__ DepTile t;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long base = blockIdx.x * (long long)DT_TILE;
+    if (ahead > 0 && tid < 7) {          // L2 prefetch of the tile a block `ahead` blocks later will stream (see k_push)
+        const long long pf = base + (long long)ahead * DT_TILE;
+        if (pf + DT_TILE <= n) {
+            const double *src = tid == 0 ? px : tid == 1 ? py : tid == 2 ? pz : tid == 3 ? pvx : tid == 4 ? pvy : tid == 5 ? pvz : pmpw;
+            l2_prefetch(src + pf, DT_TILE * 8);
+        }
+    }
+    dt_clear(t);
+    __syncthreads();
+#pragma unroll 1
+    for (int round = 0; round < DT_PER / 2; round++) {
+        const int p = 2 * (round * DT_THREADS + tid);
+        const long long i0 = base + p;
+        const long long wbase = i0 - 2 * lane;                   // first particle of this warp in this round (multiple of 64)
+        const bool v0 = i0 < n, v1 = i0 + 1 < n;
+        double2 X = make_double2(m.x0[0], m.x0[0]), Y = make_double2(m.x0[1], m.x0[1]), Z = make_double2(m.x0[2], m.x0[2]);
+        double2 VX = make_double2(0, 0), VY = VX, VZ = VX, W = VX;
+        if (v0) {      // capacity is a multiple of 1024: slot i0+1 is always allocated
+            X = ld2(px + i0); Y = ld2(py + i0); Z = ld2(pz + i0);
+            VX = ld2(pvx + i0); VY = ld2(pvy + i0); VZ = ld2(pvz + i0); W = ld2(pmpw + i0);
+        }
+        if (!v1) { X.y = m.x0[0]; Y.y = m.x0[1]; Z.y = m.x0[2]; VX.y = 0; VY.y = 0; VZ.y = 0; W.y = 0; }
+        if (!v0) W.x = 0;
+        const double w0_in = W.x, w1_in = W.y;
+        bool dead0 = push_one<WALL>(m, ef4, s, dt, X.x, Y.x, Z.x, VX.x, VY.x, VZ.x, W.x);
+        bool dead1 = push_one<WALL>(m, ef4, s, dt, X.y, Y.y, Z.y, VX.y, VY.y, VZ.y, W.y);
+        dead0 = dead0 && v0;
+        dead1 = dead1 && v1;
+        if (v1) {
+            st2(px + i0, X.x, X.y); st2(py + i0, Y.x, Y.y); st2(pz + i0, Z.x, Z.y);
+            st2(pvx + i0, VX.x, VX.y); st2(pvy + i0, VY.x, VY.y); st2(pvz + i0, VZ.x, VZ.y);
+        } else if (v0) {
+            px[i0] = X.x; py[i0] = Y.x; pz[i0] = Z.x; pvx[i0] = VX.x; pvy[i0] = VY.x; pvz[i0] = VZ.x;
+        }
+        if (WALL == ESPIC_WALL_ABSORB) {
+            if (dead0 && w0_in != 0) pmpw[i0] = 0;               // part.mpw = 0 (Species.cpp:31)
+            if (dead1 && w1_in != 0) pmpw[i0 + 1] = 0;
+            if (wbase < n) {                                     // warp-uniform: the kill words of this warp's 64 particles
+                const uint32_t b0 = __ballot_sync(0xffffffffu, dead0), b1 = __ballot_sync(0xffffffffu, dead1);
+                if (lane == 0) {
+                    dead_words[wbase >> 5] = spread16(b0) | (spread16(b1) << 1);
+                    if (wbase + 32 < n) dead_words[(wbase >> 5) + 1] = spread16(b0 >> 16) | (spread16(b1 >> 16) << 1);
+                }
+            }
+        }
+        // survivors go into the tile's grouping with their new position (the reference scatters after the removal, Species.cpp:51-62)
+        dt_insert<true>(m, t, p, X.x, Y.x, Z.x, (v0 && !dead0) ? W.x : 0.0);
+        dt_insert<true>(m, t, p + 1, X.y, Y.y, Z.y, (v1 && !dead1) ? W.y : 0.0);
+    }
+    __syncthreads();
+    dt_finish<MODE, 1, true>(m, t, acc, scale);
+}
+
 // ---- removal in the reference's swap-with-last order (Species.cpp:36-46) ------------------------------
 // With D dead among n, L = n-D survivors.  The sequential loop fills the holes (dead, idx < L) in ascending
 // order with the live particles of the tail (idx >= L) taken from the end: hole rank r <- tail-live rank r.
@@ -680,17 +767,27 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     // default distance: two blocks per SM (measured plateau: 1-3 blocks per SM)
     const int ahead = ahead_env >= 0 ? ahead_env : 2 * c->sm_count;
 #define PUSH_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, s.kill_words, s.acc, scale, ahead, s.leave_words, c->dom_klo, c->dom_khi
+    // the fused scatter groups by cell inside a 1024-particle tile (k_push_tile); ESPIC_FUSE_WARP_MERGE=1 selects the round-1
+    // variant that only merges runs of equal cells inside a warp (2x slower once the cell order has decayed)
+    static const bool warp_fuse = getenv("ESPIC_FUSE_WARP_MERGE") != nullptr;
+    const unsigned tgrid = nblk(n, DT_TILE);
+#define TILE_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, s.kill_words, s.acc, scale, ahead / 2
     if (wall_mode == ESPIC_WALL_ABSORB) {
         if (mig) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64, true><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (!warp_fuse && mode == ESPIC_DEPOSIT_FP64) k_push_tile<ESPIC_WALL_ABSORB, ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
+        else if (!warp_fuse) k_push_tile<ESPIC_WALL_ABSORB, ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
         else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else k_push<ESPIC_WALL_ABSORB, true, ESPIC_DEPOSIT_FIXED><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
     } else if (wall_mode == ESPIC_WALL_REFLECT) {
         if (!fuse) k_push<ESPIC_WALL_REFLECT, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (!warp_fuse && mode == ESPIC_DEPOSIT_FP64) k_push_tile<ESPIC_WALL_REFLECT, ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
+        else if (!warp_fuse) k_push_tile<ESPIC_WALL_REFLECT, ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
         else if (mode == ESPIC_DEPOSIT_FP64) k_push<ESPIC_WALL_REFLECT, true, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else k_push<ESPIC_WALL_REFLECT, true, ESPIC_DEPOSIT_FIXED><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
     } else { espic_set_error("espic_push: bad wall mode %d", wall_mode); return -1; }
 #undef PUSH_ARGS
+#undef TILE_ARGS
     LAUNCH_CHECK(c);
     CK(cudaEventRecord(c->push_ev1, c->stream));
     c->push_timed = true;
