@@ -705,20 +705,28 @@ def main():
         pb = [p.numpy() for p in pinned]
         h2d = 7 * 8 * n_inj
         d2h = 0
-        phi_pinned = torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy()    # where Output::fields would read phi
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pushed_e2e = 0
+        phi_host = [torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+        head.pflags |= es.PUSH_DIAG                            # the step's diagnostics ride in the push kernel's registers
+        e.prefetch_particles(sp, pb[0])                        # the copy engine works one step ahead of the kernels
         for i in range(args.steps):
-            e.add_particles(sp, pb[i % 2], DT)                 # host -> device: this step's injected particles
+            e.add_particles(sp, pb[i % 2], DT)                 # host -> device: this step's injected particles (staged by the prefetch)
+            if i + 1 < args.steps:
+                e.prefetch_particles(sp, pb[(i + 1) % 2])      # next step's batch travels while this step computes
             pushed_e2e += e.count(sp)
             head.step()
             dg = e.diag(sp)                                    # device -> host: the step's diagnostics ...
-            phi_host = e.field(es.PHI, out=phi_pinned)         # ... and the potential (what Output::fields reads)
-            d2h = dg.nbytes + phi_host.nbytes + 8
+            if i > 0:
+                e.copy_sync()                                  # (previous step's potential has arrived in its pinned buffer)
+            e.field_async(es.PHI, phi_host[i % 2])             # ... and the potential (what Output::fields reads), on the copy stream
+            d2h = dg.nbytes + phi_host[0].nbytes + 8
+        e.copy_sync()
+        head.pflags &= ~es.PUSH_DIAG
         e1.record()
         torch.cuda.synchronize()
         ms_e = e0.elapsed_time(e1)

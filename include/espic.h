@@ -62,6 +62,10 @@ enum { ESPIC_PHI = 0, ESPIC_RHO = 1, ESPIC_EF = 2, ESPIC_NODE_VOL = 3, ESPIC_OBJ
        ESPIC_VEL = 7, ESPIC_T = 8, ESPIC_N_SUM = 9, ESPIC_NV_SUM = 10, ESPIC_NUU_SUM = 11, ESPIC_NVV_SUM = 12, ESPIC_NWW_SUM = 13,
        ESPIC_MPC = 14 };   /* macroparticles per CELL, (ni-1)(nj-1)(nk-1) doubles in World::XtoC order (ch4/Species.h:88) */
 int espic_field_download(espic_ctx *ctx, int which, int species, void *host);
+/* The same download without stalling the compute stream (what Output::fields needs while the next step already runs): the field is
+ * snapshotted on the device, the snapshot is copied to `host` (pinned memory) on a second stream; espic_copy_sync waits for it. */
+int espic_field_download_async(espic_ctx *ctx, int which, int species, void *host);
+int espic_copy_sync(espic_ctx *ctx);
 int espic_field_upload(espic_ctx *ctx, int which, int species, const void *host);
 /* device pointer of a field (zero-copy interop: NCCL, torch.from_blob, ...) */
 int espic_field_devptr(espic_ctx *ctx, int which, int species, void **dptr);
@@ -81,6 +85,9 @@ int espic_species_upload_device(espic_ctx *ctx, int sp, const double *const dcom
 /* Species::addParticle for n particles (Species.cpp:65-81): drop positions outside [x0,xm), gather E,
  * rewind the velocity by half a step, append in input order. */
 int espic_species_add(espic_ctx *ctx, int sp, const double *const comp[7], long long n, double dt, long long *n_added);
+/* Start copying the candidates of a LATER espic_species_add(ctx, sp, comp, n, ...) to the device on the copy stream (comp in pinned
+ * host memory, unchanged until that call): issued one step ahead, the transfer overlaps the current step's kernels. */
+int espic_species_prefetch(espic_ctx *ctx, int sp, const double *const comp[7], long long n);
 
 /* Species::advance (ch3/ver2/Species.cpp:7-48; ch2/Species.cpp:7-38). */
 enum { ESPIC_WALL_ABSORB = 0,      /* ch3/ch9: kill on sphere / outside box, swap-with-last removal (same order) */
@@ -89,6 +96,9 @@ enum { ESPIC_PUSH_FUSE_DEPOSIT = 1,   /* also scatter the survivors: the next es
        ESPIC_PUSH_NO_COMPACT = 2,     /* leave dead particles in place with mpw=0 (kill-mask tests) */
        ESPIC_PUSH_MIGRATE = 4,        /* spatial decomposition: also flag the survivors that left this part and postpone the removal to
                                          the espic_migrate that must follow (one pass closes both kinds of holes) */
+       ESPIC_PUSH_DIAG = 8,           /* also sum the survivors' weight, momentum and kinetic energy while they are in registers: the
+                                         next espic_species_diag returns them without a pass over the particles (Species.cpp:84-108;
+                                         honoured by the plain absorbing push, ignored otherwise) */
        ESPIC_PUSH_FIXED_POINT = 256 };/* with FUSE_DEPOSIT: accumulate in int64 fixed point */
 int espic_push(espic_ctx *ctx, int sp, double dt, int wall_mode, int flags);
 /* device time (ms) of the push kernel of the most recent espic_push alone -- CUDA events on the launching stream,

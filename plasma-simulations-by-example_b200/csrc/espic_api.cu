@@ -138,6 +138,10 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
     CK(cudaMemsetAsync(c->dscal, 0, 128 * sizeof(unsigned long long), c->stream));
     k_node_volumes<<<nblk(m.nn, 256), 256, 0, c->stream>>>(m, c->node_vol);
     LAUNCH_CHECK(c);
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     *out = c;
     return 0;
 }
@@ -161,6 +165,9 @@ extern "C" void espic_destroy(espic_ctx *c)
     for (int q = 0; q < 8; q++) cudaFree(c->sv[q]);
     if (c->push_ev0) { cudaEventDestroy(c->push_ev0); cudaEventDestroy(c->push_ev1); }
     cudaFreeHost(c->hpin);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_stage) { cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_snap); cudaEventDestroy(c->ev_copied); }
+    cudaFree(c->stage); cudaFree(c->snap);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -275,6 +282,38 @@ extern "C" int espic_field_download(espic_ctx *c, int which, int sp, void *host)
     return 0;
 }
 
+// The same download without stalling the compute stream: the field is snapshotted device-to-device on the compute stream
+// (microseconds), the snapshot travels to `host` (pinned memory, or the copy degrades to a synchronous one) on the copy
+// stream while the next step computes.  espic_copy_sync waits for it; one transfer in flight at a time.
+extern "C" int espic_field_download_async(espic_ctx *c, int which, int sp, void *host)
+{
+    void *p; size_t b;
+    CK(cudaSetDevice(c->device));
+    if (field_ptr(c, which, sp, &p, &b)) return -1;
+    if (c->copy_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));       // the snapshot buffer is still being read
+    if (b > c->snap_cap) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        if (c->snap) CK(cudaFree(c->snap));
+        CK(cudaMalloc(&c->snap, b));
+        c->snap_cap = b;
+    }
+    CK(cudaMemcpyAsync(c->snap, p, b, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_snap, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    CK(cudaMemcpyAsync(host, c->snap, b, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copied, c->copy_stream));
+    c->copy_pending = true;
+    return 0;
+}
+
+extern "C" int espic_copy_sync(espic_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending = false;
+    return 0;
+}
+
 extern "C" int espic_field_upload(espic_ctx *c, int which, int sp, const void *host)
 {
     void *p; size_t b;
@@ -353,6 +392,7 @@ extern "C" int espic_species_upload(espic_ctx *c, int sp, const double *const co
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
+    s.diag_valid = false;
     MIG_GUARD(c, s, "espic_species_upload");
     long long base = append ? s.np : 0;
     int r = espic_species_reserve(c, sp, base + n);
@@ -374,6 +414,7 @@ extern "C" int espic_species_upload_device(espic_ctx *c, int sp, const double *c
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[sp];
     // appending behind a packed migration is how arrivals come in (espic_migrate_pack -> upload_device(append) -> espic_migrate_finish)
+    s.diag_valid = false;
     if (!(append && s.mig_stage == 2)) MIG_GUARD(c, s, "espic_species_upload_device");
     long long base = append ? s.np : 0;
     int r = espic_species_reserve(c, sp, base + n);

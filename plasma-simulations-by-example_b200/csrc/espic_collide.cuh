@@ -157,6 +157,7 @@ extern "C" int espic_dsmc_mex(espic_ctx *c, int sp, double dt, double *sigma_cr_
     Species &s = c->sp[sp];
     if (num_cols) *num_cols = 0;
     MIG_GUARD(c, s, "espic_dsmc_mex");
+    s.diag_valid = false;
     const long long n = s.np;
     if (n < 2) return 0;
     if (n >= (1ll << 32)) { espic_set_error("espic_dsmc_mex: more than 2^32 particles in one species"); return -1; }
@@ -261,6 +262,7 @@ extern "C" int espic_mcc_cex(espic_ctx *c, int source_sp, int target_sp, double 
     CK(cudaSetDevice(c->device));
     Species &s = c->sp[source_sp];
     if (num_cols) *num_cols = 0;
+    s.diag_valid = false;
     if (s.np == 0) return 0;
     int r;
     if ((r = espic_ensure_moments(c, target_sp))) return r;       // stream velocity: zero until computeGasProperties ran

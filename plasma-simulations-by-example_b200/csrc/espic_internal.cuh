@@ -46,6 +46,9 @@ struct Species {
     // mig_n particles, nothing removed yet; 2 leavers packed, arrivals may be appended, removal still to come
     int mig_stage = 0;
     long long mig_n = 0;
+    // diagnostics of the particles as the last espic_push(ESPIC_PUSH_DIAG) left them: sum mpw, sum mpw v (3), sum mpw v^2
+    bool diag_valid = false;
+    double diag_sums[5] = {0, 0, 0, 0, 0};
     // kill bits (one per particle) written by the push kernels and consumed by the removal; leave bits of a MIGRATE push.
     // Per species: after espic_push(A, ESPIC_PUSH_MIGRATE) they must survive calls on other species until espic_migrate(A).
     uint32_t *kill_words = nullptr;  long long kill_cap = 0;
@@ -87,6 +90,13 @@ struct espic_ctx {
     void *mg = nullptr;            // MgHierarchy of the multigrid-preconditioned solver (espic_mg.cuh)
     void *slab = nullptr;          // SlabState of the slab-decomposed multi-GPU variant (espic_mg.cuh)
     void *mig = nullptr;           // MigState of the spatial decomposition with particle migration (espic_migrate.cuh)
+    // copy engine side: a second stream for host <-> device traffic that overlaps the compute stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_stage = nullptr, ev_snap = nullptr, ev_copied = nullptr;
+    double *stage = nullptr; long long stage_cap = 0;       // particles prefetched by espic_species_prefetch ([7][stage_n])
+    const void *stage_host = nullptr; long long stage_n = 0; int stage_sp = -1;
+    void *snap = nullptr; size_t snap_cap = 0;               // device snapshot of a field on its way to the host
+    bool copy_pending = false;
     // comm
     void *nccl = nullptr; int rank = 0, nranks = 1;
 };

@@ -499,13 +499,16 @@ __device__ __forceinline__ bool push_one(const MeshC &m, const double *__restric
 // MIG (spatial decomposition, espic_migrate.cuh): a survivor whose new cell plane k lies outside [klo, khi) leaves this part;
 // its bit goes to leave_words AND to dead_words (the removal after the exchange closes both kinds of holes in one pass, as
 // ch9/MPI does: moveKernel clears `alive` for both, ch9/MPI/src/Species.cpp:66,185-188).
-template <int WALL, bool FUSE, int MODE, bool MIG = false>
+// DIAG (ESPIC_PUSH_DIAG): the survivors' contributions to Species::getRealCount / getMomentum / getKE (Species.cpp:84-108) are
+// summed while velocity and weight are in registers -- one partial per block and quantity, folded by k_diag_fold -- so that
+// the diagnostics every Main.cpp prints each step cost no second pass over the particles (k_diag: 1 ms at 2e8).
+template <int WALL, bool FUSE, int MODE, bool MIG = false, bool DIAG = false>
 __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const double *__restrict__ ef4,
                                               double *__restrict__ px, double *__restrict__ py, double *__restrict__ pz,
                                               double *__restrict__ pvx, double *__restrict__ pvy, double *__restrict__ pvz,
                                               double *__restrict__ pmpw, long long n, double s, double dt,
                                               uint32_t *__restrict__ dead_words, double *acc, double scale, int ahead,
-                                              uint32_t *__restrict__ leave_words, int klo, int khi)
+                                              uint32_t *__restrict__ leave_words, int klo, int khi, double *__restrict__ diag_part = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const long long i0 = 2 * (blockIdx.x * 256ll + threadIdx.x);
@@ -520,7 +523,8 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
             l2_prefetch(src + pf, 4096);
         }
     }
-    if (wbase >= n) return;
+    const bool warp_live = wbase < n;
+    if (!DIAG && !warp_live) return;                          // (with DIAG every warp stays for the block reduction)
     const bool v0 = i0 < n, v1 = i0 + 1 < n;
     double2 X = make_double2(m.x0[0], m.x0[0]), Y = make_double2(m.x0[1], m.x0[1]), Z = make_double2(m.x0[2], m.x0[2]);
     double2 VX = make_double2(0, 0), VY = VX, VZ = VX, W = VX;
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
             cell_frac(Z.y, m.x0[2], m.dh[2], m.rdh[2], m.nk, k, dk);
             const bool lv1 = v1 && !dead1 && (k < klo || k >= khi);
             const uint32_t l0 = __ballot_sync(0xffffffffu, lv0), l1 = __ballot_sync(0xffffffffu, lv1);
-            if (lane == 0) {
+            if (lane == 0 && warp_live) {
                 leave_words[wbase >> 5] = spread16(l0) | (spread16(l1) << 1);
                 if (wbase + 32 < n) leave_words[(wbase >> 5) + 1] = spread16(l0 >> 16) | (spread16(l1 >> 16) << 1);
             }
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
         }
         // kill bit of particle wbase + b is bit (b & 31) of word (wbase + b) >> 5: interleave the two ballots
         const uint32_t b0 = __ballot_sync(0xffffffffu, gone0), b1 = __ballot_sync(0xffffffffu, gone1);
-        if (lane == 0) {
+        if (lane == 0 && warp_live) {
             const uint32_t lo = spread16(b0) | (spread16(b1) << 1);
             const uint32_t hi = spread16(b0 >> 16) | (spread16(b1 >> 16) << 1);
             dead_words[wbase >> 5] = lo;
@@ -567,7 +571,38 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
         }
     }
     if (FUSE) deposit_pair<MODE>(m, acc, scale, v0 && !dead0, X.x, Y.x, Z.x, W.x, v1 && !dead1, X.y, Y.y, Z.y, W.y);
+    if (DIAG) {
+        __shared__ double sh[32];
+        double a[5] = {0, 0, 0, 0, 0};
+        if (v0 && !dead0) {          // the expressions of k_diag
+            a[0] += W.x; a[1] += VX.x * W.x; a[2] += VY.x * W.x; a[3] += VZ.x * W.x;
+            a[4] += W.x * (VX.x * VX.x + VY.x * VY.x + VZ.x * VZ.x);
+        }
+        if (v1 && !dead1) {
+            a[0] += W.y; a[1] += VX.y * W.y; a[2] += VY.y * W.y; a[3] += VZ.y * W.y;
+            a[4] += W.y * (VX.y * VX.y + VY.y * VY.y + VZ.y * VZ.y);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const double t = block_sum(a[q], sh);
+            if (threadIdx.x == 0) diag_part[(size_t)q * gridDim.x + blockIdx.x] = t;
+        }
+    }
 }
+
+// first fold of the per-block partials of a DIAG push: nq x nparts -> nq x gridDim (fixed order: reproducible)
+__global__ void __launch_bounds__(256) k_diag_fold(const double *__restrict__ part, long long nparts, int nq, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    for (int q = 0; q < nq; q++) {
+        double a = 0;
+        for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nparts; i += (long long)gridDim.x * 256) a += part[(size_t)q * nparts + i];
+        const double t = block_sum(a, sh);
+        if (threadIdx.x == 0) out[(size_t)q * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_final(const double *__restrict__ part, int nparts, int nq, double *__restrict__ out);
 
 // Push with the tile-grouping scatter fused in (ESPIC_PUSH_FUSE_DEPOSIT): a block owns DT_TILE = 1024 consecutive particles,
 // pushes them two per thread in two rounds exactly as k_push does (same loads, same arithmetic, same kill words), and hands
@@ -705,6 +740,7 @@ static int prepare_acc(espic_ctx *c, Species &s, int mode)
 // count the dead of the species' kill words (one bit per particle of [0,n)), then remove them in the reference's order
 static int compact_dead(espic_ctx *c, Species &s, long long n)
 {
+    s.diag_valid = false;
     const long long nw = (n + 31) / 32;
     int r;
     static const bool trace = getenv("ESPIC_TRACE") != nullptr;
@@ -751,6 +787,9 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
         return -1;
     }
     s.acc_fresh = false;
+    s.diag_valid = false;
+    // diagnostics ride along only on the plain absorbing push (the removal's synchronisation then also delivers them)
+    const bool diag = (flags & ESPIC_PUSH_DIAG) && !fuse && !mig && wall_mode == ESPIC_WALL_ABSORB && !(flags & ESPIC_PUSH_NO_COMPACT);
     if (fuse) { int r = prepare_acc(c, s, mode); if (r) return r; }
     if (n == 0) { if (fuse) s.acc_fresh = true; if (mig) { s.mig_stage = 1; s.mig_n = 0; } return 0; }
     const double sfac = dt * s.charge / s.mass;     // Species.cpp:22, evaluated as the reference does
@@ -761,6 +800,7 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&s.kill_words, &s.kill_cap, mig ? nw + nw / 16 + 1024 : nw, c->stream))) return r; }
     if (mig) { if ((r = ensure_buf(&s.leave_words, &s.leave_cap, nw, c->stream))) return r; }
     const unsigned grid = nblk((n + 1) / 2, 256);
+    if (diag && (r = ensure_buf(&c->red, &c->red_cap, 5ll * grid + 5 * 64, c->stream))) return r;
     if (!c->push_ev0) { CK(cudaEventCreate(&c->push_ev0)); CK(cudaEventCreate(&c->push_ev1)); }
     CK(cudaEventRecord(c->push_ev0, c->stream));
     static const int ahead_env = getenv("ESPIC_PUSH_PREFETCH") ? atoi(getenv("ESPIC_PUSH_PREFETCH")) : -1;
@@ -774,6 +814,7 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
 #define TILE_ARGS c->m, c->ef4, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6], n, sfac, dt, s.kill_words, s.acc, scale, ahead / 2
     if (wall_mode == ESPIC_WALL_ABSORB) {
         if (mig) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64, true><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
+        else if (diag) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64, false, true><<<grid, 256, 0, c->stream>>>(PUSH_ARGS, c->red);
         else if (!fuse) k_push<ESPIC_WALL_ABSORB, false, ESPIC_DEPOSIT_FP64><<<grid, 256, 0, c->stream>>>(PUSH_ARGS);
         else if (!warp_fuse && mode == ESPIC_DEPOSIT_FP64) k_push_tile<ESPIC_WALL_ABSORB, ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
         else if (!warp_fuse) k_push_tile<ESPIC_WALL_ABSORB, ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(TILE_ARGS);
@@ -796,8 +837,21 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     if (wall_mode != ESPIC_WALL_ABSORB || (flags & ESPIC_PUSH_NO_COMPACT)) { s.n_settled = s.np; return 0; }
     if (mig) { s.mig_stage = 1; s.mig_n = n; return 0; }     // removal happens in espic_migrate, after the exchange
 
+    double *hd = reinterpret_cast<double *>(c->hpin) + 100;
+    if (diag) {
+        double *fold = c->red + 5ll * grid, *dout = reinterpret_cast<double *>(c->dscal + 100);
+        k_diag_fold<<<64, 256, 0, c->stream>>>(c->red, grid, 5, fold);
+        LAUNCH_CHECK(c);
+        k_reduce_final<<<1, 256, 0, c->stream>>>(fold, 64, 5, dout);
+        LAUNCH_CHECK(c);
+        CK(cudaMemcpyAsync(hd, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // arrives with the removal's count
+    }
     int rr = compact_dead(c, s, n);
     s.n_settled = s.np;
+    if (diag && rr == 0) {
+        for (int q = 0; q < 5; q++) s.diag_sums[q] = hd[q];
+        s.diag_valid = true;
+    }
     return rr;
 }
 
@@ -1207,6 +1261,7 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
 {
     Species &s = c->sp[sp];
     if (n_added) *n_added = 0;
+    s.diag_valid = false;
     MIG_GUARD(c, s, "espic_species_add / espic_inject_*");
     if (n <= 0) return 0;
     int r;
@@ -1228,21 +1283,53 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
     return 0;
 }
 
+// Start the host -> device copy of the candidates a later espic_species_add(ctx, sp, comp, n, ...) will admit, on the copy
+// stream: called one step ahead (comp in pinned memory), the transfer overlaps the current step's kernels.  The matching add
+// recognises the staged data by (species, comp[0], n); anything else simply copies as before.
+extern "C" int espic_species_prefetch(espic_ctx *c, int sp, const double *const comp[7], long long n)
+{
+    SP_CHECK(c, sp);
+    CK(cudaSetDevice(c->device));
+    if (n <= 0) return 0;
+    if (7 * n > c->stage_cap) {
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->stage) CK(cudaFree(c->stage));
+        CK(cudaMalloc(&c->stage, (size_t)7 * n * sizeof(double)));
+        c->stage_cap = 7 * n;
+    }
+    // the staging buffer may still be read by the kernels of the previous add: order behind the compute stream
+    CK(cudaEventRecord(c->ev_snap, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    for (int q = 0; q < 7; q++)
+        CK(cudaMemcpyAsync(c->stage + q * n, comp[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_stage, c->copy_stream));
+    c->stage_host = comp[0]; c->stage_n = n; c->stage_sp = sp;
+    return 0;
+}
+
 extern "C" int espic_species_add(espic_ctx *c, int sp, const double *const comp[7], long long n, double dt, long long *n_added)
 {
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     if (n <= 0) { if (n_added) *n_added = 0; return 0; }
     Species &s = c->sp[sp];
-    // stage the candidates in the sort double buffer region of the reduction scratch
     int r;
-    if ((r = ensure_buf(&c->red, &c->red_cap, 7 * n, c->stream))) return r;
     AddSrc a;
     memset(&a, 0, sizeof(a));
     a.philox = 0;
-    for (int q = 0; q < 7; q++) {
-        CK(cudaMemcpyAsync(c->red + q * n, comp[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        a.in[q] = c->red + q * n;
+    if (c->stage_host == comp[0] && c->stage_n == n && c->stage_sp == sp) {
+        // prefetched by espic_species_prefetch: wait for the copy engine, read the staging buffer in place
+        CK(cudaStreamWaitEvent(c->stream, c->ev_stage, 0));
+        for (int q = 0; q < 7; q++) a.in[q] = c->stage + q * n;
+        c->stage_host = nullptr;
+    } else {
+        // stage the candidates in the reduction scratch
+        if ((r = ensure_buf(&c->red, &c->red_cap, 7 * n, c->stream))) return r;
+        for (int q = 0; q < 7; q++) {
+            CK(cudaMemcpyAsync(c->red + q * n, comp[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            a.in[q] = c->red + q * n;
+        }
     }
     for (long long i = 0; i < n; i++) if (comp[6][i] > s.mpw_max) s.mpw_max = comp[6][i];
     return add_common(c, sp, a, n, dt, n_added);
@@ -1350,6 +1437,12 @@ extern "C" int espic_species_diag(espic_ctx *c, int sp, double out[5])
     Species &s = c->sp[sp];
     for (int q = 0; q < 5; q++) out[q] = 0;
     if (s.np == 0) return 0;
+    if (s.diag_valid) {          // summed by the last espic_push(ESPIC_PUSH_DIAG); nothing touched the particles since
+        out[0] = s.diag_sums[0];
+        out[1] = s.diag_sums[1] * s.mass; out[2] = s.diag_sums[2] * s.mass; out[3] = s.diag_sums[3] * s.mass;
+        out[4] = 0.5 * s.mass * s.diag_sums[4];
+        return 0;
+    }
     int nb = (int)std::min<long long>(nblk(s.np, 256), 4 * c->sm_count);
     int r;
     if ((r = ensure_buf(&c->red, &c->red_cap, 5ll * nb, c->stream))) return r;

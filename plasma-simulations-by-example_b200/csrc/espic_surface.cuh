@@ -258,6 +258,7 @@ extern "C" int espic_push_surface(espic_ctx *c, int sp, double dt, int neutrals_
     Species &s = c->sp[sp];
     if (emitted) emitted[0] = emitted[1] = 0;
     MIG_GUARD(c, s, "espic_push_surface");
+    s.diag_valid = false;
     const bool charged = s.charge != 0;
     if (charged) {
         SP_CHECK(c, neutrals_sp);

@@ -13,16 +13,16 @@ LIB_PATH = os.path.join(HERE, "lib", "libespic_cuda.so")
 
 PHI, RHO, EF, NODE_VOL, OBJECT_ID, DEN, DEN_AVE, VEL, T, N_SUM, NV_SUM, NUU_SUM, NVV_SUM, NWW_SUM, MPC = range(15)
 WALL_ABSORB, WALL_REFLECT = 0, 1
-PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_MIGRATE, PUSH_FIXED_POINT = 1, 2, 4, 256
+PUSH_FUSE_DEPOSIT, PUSH_NO_COMPACT, PUSH_MIGRATE, PUSH_DIAG, PUSH_FIXED_POINT = 1, 2, 4, 8, 256
 DEPOSIT_FP64, DEPOSIT_FIXED = 0, 1
 SORT_XTOC, SORT_DRIFT_Z = 0, 1
 SOLVE_GS, SOLVE_PCG, SOLVE_QN, SOLVE_GS_BOX, SOLVE_PCG_REF, SOLVE_PCG_MG, SOLVE_PCG_MG_SLAB = 0, 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
     "espic_create", "espic_destroy", "espic_last_error", "espic_set_stream", "espic_sync", "espic_kernel_launches",
-    "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_upload",
+    "espic_get_mesh", "espic_add_sphere", "espic_add_inlet", "espic_field_download", "espic_field_download_async", "espic_copy_sync", "espic_field_upload",
     "espic_field_devptr", "espic_species_create", "espic_species_reserve", "espic_species_count",
-    "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_push", "espic_last_push_ms", "espic_deposit",
+    "espic_species_upload", "espic_species_download", "espic_species_upload_device", "espic_species_add", "espic_species_prefetch", "espic_push", "espic_last_push_ms", "espic_deposit",
     "espic_sort_by_cell", "espic_sort_particles", "espic_inject_cold_beam", "espic_inject_warm_beam", "espic_push_surface", "espic_dsmc_mex", "espic_mcc_cex", "espic_compute_mpc", "espic_species_diag", "espic_update_average", "espic_sample_moments", "espic_compute_gas_properties", "espic_clear_samples",
     "espic_charge_density", "espic_solve", "espic_mg_plan", "espic_compute_ef", "espic_field_pe", "espic_comm_unique_id",
     "espic_comm_init",
@@ -72,6 +72,9 @@ def load():
     L.espic_add_sphere.argtypes = [vp, dp, C.c_double, C.c_double]
     L.espic_add_inlet.argtypes = [vp]
     L.espic_field_download.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.espic_field_download_async.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.espic_copy_sync.argtypes = [vp]
+    L.espic_species_prefetch.argtypes = [vp, C.c_int, comp, C.c_longlong]
     L.espic_field_upload.argtypes = [vp, C.c_int, C.c_int, vp]
     L.espic_field_devptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.espic_species_create.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_longlong]
@@ -209,6 +212,16 @@ class Engine:
         self._ck(self.L.espic_field_download(self.h, which, sp, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def field_async(self, which, out, sp=0):
+        """Start the download of a node field into `out` (pinned memory) on the copy stream; copy_sync() waits for it."""
+        n, dt = self.nn * (3 if which in (EF, VEL, NV_SUM) else 1), (np.int32 if which == OBJECT_ID else np.float64)
+        assert out.size == n and out.dtype == dt and out.flags["C_CONTIGUOUS"]
+        self._ck(self.L.espic_field_download_async(self.h, which, sp, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def copy_sync(self):
+        self._ck(self.L.espic_copy_sync(self.h))
+
     def set_field(self, which, arr, sp=0):
         arr = np.ascontiguousarray(arr, dtype=np.int32 if which == OBJECT_ID else np.float64)
         assert arr.size == self.nn * (3 if which in (EF, VEL, NV_SUM) else 1)
@@ -273,6 +286,11 @@ class Engine:
         added = C.c_longlong(0)
         self._ck(self.L.espic_species_add(self.h, sp, _comp(soa), soa.shape[1], dt, C.byref(added)))
         return added.value
+
+    def prefetch_particles(self, sp, soa):
+        """Start the host -> device copy of the candidates a later add_particles(sp, soa, dt) will admit (soa: the same pinned array)."""
+        assert soa.dtype == np.float64 and soa.flags["C_CONTIGUOUS"]
+        self._ck(self.L.espic_species_prefetch(self.h, sp, _comp(soa), soa.shape[1]))
 
     def push(self, sp, dt, wall=WALL_ABSORB, flags=0):
         self._ck(self.L.espic_push(self.h, sp, dt, wall, flags))

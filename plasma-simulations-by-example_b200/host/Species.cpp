@@ -86,11 +86,14 @@ void Species::advance()
     flush();
     world.fields_to_device();
     // with the periodic cell sort enabled the sort goes between push and scatter (the deposit then sees perfectly
-    // ordered particles); otherwise the scatter is fused into the push kernel
+    // ordered particles); otherwise the scatter is fused into the push kernel.  Absorbing walls (ch3, ch9): the push also
+    // sums what getRealCount / getMomentum / getKE return (Species.cpp:84-108), so the diagnostics the book's Main.cpp prints
+    // every step cost no second pass over the particles.
     const bool sort_now = sort_every > 0 && n_advance % sort_every == 0;
     n_advance++;
-    espic_host::check(espic_push(world.engine(), sp_id, world.getDt(), reflect ? ESPIC_WALL_REFLECT : ESPIC_WALL_ABSORB,
-                                 sort_every > 0 ? 0 : ESPIC_PUSH_FUSE_DEPOSIT),
+    int flags = sort_every > 0 ? 0 : ESPIC_PUSH_FUSE_DEPOSIT;
+    if (!reflect) flags = ESPIC_PUSH_DIAG;
+    espic_host::check(espic_push(world.engine(), sp_id, world.getDt(), reflect ? ESPIC_WALL_REFLECT : ESPIC_WALL_ABSORB, flags),
                       "espic_push");
     if (sort_now) sortByCell();
     particles_changed();

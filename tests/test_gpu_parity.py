@@ -624,3 +624,60 @@ def test_properties_at_full_baseline_size():
     assert again["lin_iters"] <= first["lin_iters"] // 2 + 1
     assert np.abs(phi2 - phi1).max() <= 2e-3, "a converged potential moves by less than the Newton tolerance when re-solved"
     e.close()
+
+
+def test_push_diag_matches_the_separate_reduction():
+    """ESPIC_PUSH_DIAG: the sums the push kernel collects for the survivors (Species::getRealCount / getMomentum / getKE,
+    Species.cpp:84-108) equal the separate reduction over the particles after the removal, and a later change of the
+    particles invalidates them."""
+    es = _espic()
+    w, sp = cases.sphere_case(seed=131, ni=21, nj=21, nk=41, n=300001, near_walls=0.1)
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    a, b = GpuEngine(st), GpuEngine(st)
+    for step in range(3):
+        a.e.push(a.species[0], 1e-7, es.WALL_ABSORB, es.PUSH_DIAG)
+        b.e.push(b.species[0], 1e-7, es.WALL_ABSORB, 0)
+        da, db = a.e.diag(a.species[0]), b.e.diag(b.species[0])
+        assert a.e.count(a.species[0]) == b.e.count(b.species[0]) < 300001
+        assert np.abs(da - db).max() <= 1e-12 * np.abs(db).max(), (step, da, db)
+    assert_bits(a.e.download(a.species[0]), b.e.download(b.species[0]), "the particles themselves are untouched by the option")
+    # the oracle's sums of the same state
+    o = OracleEngine(st)
+    for step in range(3):
+        o.species[0].advance(1e-7)
+    ref = np.concatenate([[o.species[0].real_count()], o.species[0].momentum(), [o.species[0].ke()]])
+    assert np.abs(da - ref).max() <= 1e-12 * np.abs(ref).max()
+    # adding particles invalidates the cached sums
+    extra = np.ascontiguousarray(cases.random_particles(w, np.random.default_rng(5), 1000))
+    a.e.add_particles(a.species[0], extra, 1e-7)
+    b.e.add_particles(b.species[0], extra, 1e-7)
+    da, db = a.e.diag(a.species[0]), b.e.diag(b.species[0])
+    assert np.abs(da - db).max() <= 1e-12 * np.abs(db).max() and da[0] > ref[0]
+
+
+def test_prefetched_add_and_async_field_download():
+    """espic_species_prefetch + espic_species_add and espic_field_download_async + espic_copy_sync give exactly what the
+    synchronous calls give."""
+    import torch
+    es = _espic()
+    w, sp = cases.sphere_case(seed=132, ni=21, nj=21, nk=41, n=50000)
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    a, b = GpuEngine(st), GpuEngine(st)
+    rng = np.random.default_rng(6)
+    batches = [torch.from_numpy(np.ascontiguousarray(cases.random_particles(w, rng, 4000))).pin_memory().numpy() for _ in range(3)]
+    a.e.prefetch_particles(a.species[0], batches[0])
+    for i, bt in enumerate(batches):
+        na = a.e.add_particles(a.species[0], bt, 1e-7)
+        if i + 1 < len(batches):
+            a.e.prefetch_particles(a.species[0], batches[i + 1])
+        nb = b.e.add_particles(b.species[0], bt.copy(), 1e-7)
+        assert na == nb
+        a.e.push(a.species[0], 1e-7, es.WALL_ABSORB, 0)
+        b.e.push(b.species[0], 1e-7, es.WALL_ABSORB, 0)
+    assert_bits(a.e.download(a.species[0]), b.e.download(b.species[0]), "particles after prefetched adds")
+    a.e.deposit(a.species[0], es.DEPOSIT_FIXED)
+    out = torch.empty(w.nn, dtype=torch.float64).pin_memory().numpy()
+    a.e.field_async(es.DEN, out, a.species[0])
+    a.e.set_field(es.RHO, np.zeros(w.nn))              # unrelated work on the compute stream meanwhile
+    a.e.copy_sync()
+    assert_bits(out, a.e.field(es.DEN, a.species[0]), "asynchronously downloaded field")
