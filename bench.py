@@ -612,6 +612,8 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=1e7, help="particles of the reference arm's bounded sample (the in-line cpu_baseline uses at most 2e6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", type=int, default=7, help="bit 0: diagnostics inside the push kernel, bit 1: particle H2D prefetched one "
+                                                            "step ahead on the copy stream, bit 2: potential downloaded asynchronously")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra QN-solver measurement")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra records (configs[2], strong scaling, configs[4], parity check)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
@@ -705,27 +707,60 @@ def main():
         pb = [p.numpy() for p in pinned]
         h2d = 7 * 8 * n_inj
         d2h = 0
+        phi_host = [torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+        m_diag, m_pre, m_async = bool(args.e2e_mode & 1), bool(args.e2e_mode & 2), bool(args.e2e_mode & 4)
+        if m_diag:
+            head.pflags |= es.PUSH_DIAG                        # the step's diagnostics ride in the push kernel's registers
+
+        def e2e_steps(count):
+            pushed, d2h_b = 0, 0
+            if m_pre:
+                e.prefetch_particles(sp, pb[0])                # the copy engine works one step ahead of the kernels
+            for i in range(count):
+                e.add_particles(sp, pb[i % 2], DT)             # host -> device: this step's injected particles (staged by the prefetch)
+                if m_pre and i + 1 < count:
+                    e.prefetch_particles(sp, pb[(i + 1) % 2])  # next step's batch travels while this step computes
+                pushed += e.count(sp)
+                head.step()
+                dg = e.diag(sp)                                # device -> host: the step's diagnostics ...
+                if m_async:
+                    if i > 0:
+                        e.copy_sync()                          # (previous step's potential has arrived in its pinned buffer)
+                    e.field_async(es.PHI, phi_host[i % 2])     # ... and the potential (what Output::fields reads), on the copy stream
+                else:
+                    e.field(es.PHI, out=phi_host[i % 2])
+                d2h_b = dg.nbytes + phi_host[0].nbytes + 8
+            e.copy_sync()
+            return pushed, d2h_b
+
+        if os.environ.get("BENCH_E2E_TRACE"):          # development aid: serialised cost of every call of the e2e step
+            tr = {}
+
+            def timed_call(name, fn):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                e.copy_sync()
+                tr.setdefault(name, []).append((time.perf_counter() - t0) * 1e3)
+                return r
+            for i in range(6):
+                timed_call("add_particles", lambda: e.add_particles(sp, pb[i % 2], DT))
+                timed_call("push", lambda: e.push(sp, DT, es.WALL_ABSORB, head.pflags))
+                timed_call("deposit", lambda: e.deposit(sp, head.dmode))
+                timed_call("rho", lambda: e.compute_charge_density())
+                timed_call("solve", lambda: e.solve(head.solver, head.max_it, head.tol))
+                timed_call("ef", lambda: e.compute_ef())
+                timed_call("diag", lambda: e.diag(sp))
+                timed_call("phi download", lambda: e.field(es.PHI, out=phi_host[0]))
+            log("e2e trace (ms, serialised): %s" % {k: round(float(np.mean(v[1:])), 3) for k, v in tr.items()})
+        e2e_steps(3)             # untimed: first-use allocations of the staging buffers (a cudaMalloc next to 22 GB of particles costs ~100 ms)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pushed_e2e = 0
-        phi_host = [torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
-        head.pflags |= es.PUSH_DIAG                            # the step's diagnostics ride in the push kernel's registers
-        e.prefetch_particles(sp, pb[0])                        # the copy engine works one step ahead of the kernels
-        for i in range(args.steps):
-            e.add_particles(sp, pb[i % 2], DT)                 # host -> device: this step's injected particles (staged by the prefetch)
-            if i + 1 < args.steps:
-                e.prefetch_particles(sp, pb[(i + 1) % 2])      # next step's batch travels while this step computes
-            pushed_e2e += e.count(sp)
-            head.step()
-            dg = e.diag(sp)                                    # device -> host: the step's diagnostics ...
-            if i > 0:
-                e.copy_sync()                                  # (previous step's potential has arrived in its pinned buffer)
-            e.field_async(es.PHI, phi_host[i % 2])             # ... and the potential (what Output::fields reads), on the copy stream
-            d2h = dg.nbytes + phi_host[0].nbytes + 8
-        e.copy_sync()
+        pushed_e2e, d2h = e2e_steps(args.steps)
         head.pflags &= ~es.PUSH_DIAG
         e1.record()
         torch.cuda.synchronize()
