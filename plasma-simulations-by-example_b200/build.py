@@ -82,6 +82,13 @@ def build_host(force=False, reference="/root/reference"):
     if force or not os.path.exists(chk) or os.path.getmtime(chk) < max(deps, os.path.getmtime(src)):
         subprocess.check_call([CXX] + CXXFLAGS + ["-o", chk, src] + LINK)
     built = [chk]
+    # the ion-beam case with velocity moments (north-star parity check #2): the same driver file is also compiled against the
+    # unmodified ch4 reference sources by oracle/Makefile
+    ion = os.path.join(BIN, "ion_sphere")
+    src = os.path.join(HOST, "ion_sphere.cpp")
+    if force or not os.path.exists(ion) or os.path.getmtime(ion) < max(deps, os.path.getmtime(src)):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-o", ion, src] + LINK)
+    built.append(ion)
     for name, rel in REF_MAINS.items():
         main = os.path.join(reference, rel)
         exe = os.path.join(BIN, name)

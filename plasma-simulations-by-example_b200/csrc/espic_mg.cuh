@@ -147,6 +147,7 @@ struct OwnAll {
     __device__ __forceinline__ void put_partial(double *base, int nb, double v) const { base[blockIdx.x] = v; }
     __device__ __forceinline__ bool barrier(cg::grid_group &grid) { grid.sync(); return true; }
     __device__ __forceinline__ bool lbarrier(cg::grid_group &grid) { grid.sync(); return true; }
+    __device__ __forceinline__ bool nbarrier(cg::grid_group &grid) { grid.sync(); return true; }
 };
 
 #define MG_MAX_RANKS 8
@@ -158,7 +159,11 @@ struct OwnSlab {
     int rank, nranks;
     int k0[MG_MAX_LEVELS], k1[MG_MAX_LEVELS];
     long long peer[MG_MAX_RANKS];        // byte distance from an address in this rank's pool to the same address in rank p's pool
-    unsigned long long *flags;           // in the pool: flags[p] = last barrier epoch rank p has reached (written by rank p)
+    unsigned long long *flags;           // in the pool: flags[p] = last all-rank barrier epoch rank p has reached (written by rank p)
+    unsigned long long *nflags;          // the same for the neighbour-only barriers
+    unsigned long long nepoch;           // neighbour-only barriers passed so far
+    unsigned long long lepoch_all;       // barriers of either kind passed so far (local arrive / release counters)
+    int neighbour_sync;                  // 0: nbarrier() is a full barrier (ESPIC_MG_SLAB_NEIGHBOUR_SYNC=0)
     unsigned long long *abort_word;      // in the pool: non-zero once any rank gave up waiting (written by that rank to every pool)
     unsigned long long epoch;            // barriers passed so far (identical on every rank)
     unsigned long long *arrive, *release;     // in the local pool
@@ -196,35 +201,42 @@ struct OwnSlab {
     {
         for (int p = 0; p < nranks; p++) *at(base + rank * nb + blockIdx.x, p) = v;
     }
-    // All blocks of all ranks.  Local arrival (one atomic per block on a cumulative counter), then block 0 exchanges one
-    // flag with every peer over NVLink, then it releases the local blocks: one local round trip plus one remote one.
-    // Ordering: every block's thread 0 issues a system-scope fence after the block barrier and before arriving, block 0
-    // fences again (system scope) between seeing all arrivals and signalling the peers, so a peer that sees the flag also
-    // sees every halo value and partial sum stored before this barrier.  Returns false once the abort word is up.
-    __device__ __forceinline__ bool barrier(cg::grid_group &)
+    // All blocks of the ranks [pfirst, plast] (this rank included).  Local arrival (one atomic per block on a cumulative
+    // counter), then block 0 exchanges one flag with every peer of the set over NVLink, then it releases the local blocks:
+    // one local round trip plus one remote one.
+    // Ordering: every block's thread 0 fences at GPU scope after the block barrier and before arriving; block 0, having seen
+    // all arrivals, fences once at SYSTEM scope before it signals the peers (fences are cumulative: what block 0 has observed
+    // is ordered before its own later writes at the wider scope), so a peer that sees the flag also sees every halo value and
+    // partial sum stored before this barrier.  Returns false once the abort word is up.
+    // kind 0: every rank (flags[]), kind 1: the two neighbours only (nflags[]: halo planes need no more).
+    __device__ __forceinline__ bool sync_ranks(int kind)
     {
         __syncthreads();
-        epoch++;
+        unsigned long long &ep = kind == 0 ? epoch : nepoch;
+        ep++;
+        lepoch_all++;
         volatile unsigned long long *ab = abort_word;
+        unsigned long long *fl = kind == 0 ? flags : nflags;
+        const int pfirst = kind == 0 ? 0 : max(rank - 1, 0), plast = kind == 0 ? nranks - 1 : min(rank + 1, nranks - 1);
         if (blockIdx.x == 0) {
-            if (threadIdx.x < 32) {          // first warp: lane 0 collects the local arrivals, lane p talks to peer p
+            if (threadIdx.x < 32) {          // first warp: lane 0 collects the local arrivals, lane p talks to peer pfirst + p
                 const int lane = threadIdx.x;
                 if (lane == 0) {
-                    __threadfence_system();
                     volatile unsigned long long *arr = arrive;
-                    const unsigned long long want = (unsigned long long)(gridDim.x - 1) * epoch;
+                    const unsigned long long want = (unsigned long long)(gridDim.x - 1) * lepoch_all;
                     unsigned long long spins = 0;
                     while (*arr < want && !*ab) { if (++spins > MG_SPIN_BUDGET) break; }
                     __threadfence_system();
                 }
                 __syncwarp();
-                if (lane < nranks) {
-                    *reinterpret_cast<volatile unsigned long long *>(at(flags + rank, lane)) = epoch;
-                    volatile unsigned long long *mine = flags + lane;
+                const int peer_rank = pfirst + lane;
+                if (peer_rank <= plast) {
+                    *reinterpret_cast<volatile unsigned long long *>(at(fl + rank, peer_rank)) = ep;
+                    volatile unsigned long long *mine = fl + peer_rank;
                     unsigned long long spins = 0;
-                    while (*mine < epoch && !*ab) {
+                    while (*mine < ep && !*ab) {
                         if (++spins > MG_SPIN_BUDGET) {          // a peer never arrived: tell everybody and give up
-                            for (int p = 0; p < nranks; p++) *reinterpret_cast<volatile unsigned long long *>(at(abort_word, p)) = epoch;
+                            for (int p = 0; p < nranks; p++) *reinterpret_cast<volatile unsigned long long *>(at(abort_word, p)) = ep;
                             break;
                         }
                     }
@@ -233,20 +245,22 @@ struct OwnSlab {
                 __syncwarp();
                 if (lane == 0) {
                     volatile unsigned long long *rel = release;
-                    *rel = epoch;
+                    *rel = lepoch_all;
                     __threadfence();
                 }
             }
         } else if (threadIdx.x == 0) {
-            __threadfence_system();
+            __threadfence();
             atomicAdd(arrive, 1ull);
             volatile unsigned long long *rel = release;
-            while (*rel < epoch && !*ab) { }
+            while (*rel < lepoch_all && !*ab) { }
             __threadfence();
         }
         __syncthreads();
         return *ab == 0;
     }
+    __device__ __forceinline__ bool barrier(cg::grid_group &) { return sync_ranks(0); }
+    __device__ __forceinline__ bool nbarrier(cg::grid_group &) { return sync_ranks(neighbour_sync ? 1 : 0); }
     // the blocks of THIS rank only (levels every rank solves in full): same arrive / release scheme without the peer exchange
     __device__ __forceinline__ bool lbarrier(cg::grid_group &)
     {
@@ -1035,8 +1049,10 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
     int lr = lc;
     if constexpr (Own::slab) lr = a.first_redundant;
     OwnAll whole;
+    // a pass whose output is only read across the slab boundary (halo planes) synchronises with the two neighbours; one that
+    // stores to every rank (the right-hand side of the first redundant level) or feeds a dot product needs all ranks
     mg_fine_down(own, a, R, ring, lr == 1);
-    ok = own.barrier(grid) && ok;
+    ok = (lr == 1 ? own.barrier(grid) : own.nbarrier(grid)) && ok;
     MG_TICK(0);
     for (int l = 1; l + 1 < a.nlev; l++) {
         if (Own::slab && l >= lr) {
@@ -1044,7 +1060,7 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
             ok = own.lbarrier(grid) && ok;
         } else {
             mg_down(own, a.L[l], l, a.L[l + 1], t0, stride, l + 1 == lr);
-            ok = own.barrier(grid) && ok;
+            ok = (l + 1 == lr ? own.barrier(grid) : own.nbarrier(grid)) && ok;
         }
     }
     MG_TICK(1);
@@ -1056,7 +1072,7 @@ __device__ __forceinline__ double mg_vcycle(cg::grid_group &grid, Own &own, cons
             ok = own.lbarrier(grid) && ok;
         } else {
             mg_up(own, a.L[l], l, a.L[l + 1], e, t0, stride);
-            ok = own.barrier(grid) && ok;
+            ok = own.nbarrier(grid) && ok;
         }
         e = a.L[l].xn;
     }
@@ -1128,7 +1144,7 @@ __device__ __forceinline__ void mgn_body(const MgnArgs &a, Own &own, unsigned ch
                     const bool to_all = Own::slab && l == lr;
                     if (l == 1) mg_diag1(own, s, a.type, a.diagf, a.pitch, a.L[1], t0, stride, to_all);
                     else mg_diagl(own, a.L[l - 1], a.L[l], l, t0, stride, to_all);
-                    ok = own.barrier(grid) && ok;
+                    ok = (to_all ? own.barrier(grid) : own.nbarrier(grid)) && ok;
                 }
             }
         }
@@ -1207,9 +1223,11 @@ __global__ void __launch_bounds__(MG_THREADS, 3) k_mg_newton_slab(const __grid_c
 {
     own.epoch = epoch_io[0];
     own.lepoch = epoch_io[1];
+    own.nepoch = epoch_io[2];
+    own.lepoch_all = epoch_io[3];
     mgn_body(a, own, mgn_smem);
     // every block read the epochs before its first barrier, and nobody gets past that barrier before all have arrived
-    if (blockIdx.x == 0 && threadIdx.x == 0) { epoch_io[0] = own.epoch; epoch_io[1] = own.lepoch; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { epoch_io[0] = own.epoch; epoch_io[1] = own.lepoch; epoch_io[2] = own.nepoch; epoch_io[3] = own.lepoch_all; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -1530,7 +1548,7 @@ struct SlabState {
     double *fine, *phi, *part;
     long long nnp;
     mgf *coarse;
-    unsigned long long *flags, *epoch, *arrive, *release, *abort_word, *larrive, *lrelease;
+    unsigned long long *flags, *nflags, *epoch, *arrive, *release, *abort_word, *larrive, *lrelease;
     MgHierarchy H;
     OwnSlab own;
 };
@@ -1576,6 +1594,7 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     S->coarse = reinterpret_cast<mgf *>(p); p += coarse;
     S->part = p; p += nparts;
     S->flags = reinterpret_cast<unsigned long long *>(p); p += 16;
+    S->nflags = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->epoch = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->arrive = reinterpret_cast<unsigned long long *>(p); p += 16;
     S->release = reinterpret_cast<unsigned long long *>(p); p += 16;
@@ -1597,6 +1616,8 @@ static int slab_setup(espic_ctx *c, const StencilC &s)
     CK(cudaFree(dh));
     OwnSlab &own = S->own;
     own.rank = c->rank; own.nranks = c->nranks; own.flags = S->flags; own.epoch = 0;
+    own.nflags = S->nflags; own.nepoch = 0; own.lepoch_all = 0;
+    own.neighbour_sync = getenv("ESPIC_MG_SLAB_NEIGHBOUR_SYNC") ? atoi(getenv("ESPIC_MG_SLAB_NEIGHBOUR_SYNC")) : 1;
     own.arrive = S->arrive; own.release = S->release; own.abort_word = S->abort_word;
     own.larrive = S->larrive; own.lrelease = S->lrelease; own.lepoch = 0;
     for (int q = 0; q < MG_MAX_RANKS; q++) own.peer[q] = 0;

@@ -494,3 +494,28 @@ def test_output_fields_vti_matches_the_reference_writer(tmp_path):
         assert len(ta) == len(tb) == ni * nj * nk * (3 if name == "ef" else 1), (name, len(ta), len(tb))
         bad = [i for i in range(len(ta)) if ta[i] != tb[i]]
         assert not bad, "%s: first differing tokens: %s" % (name, [(i, ta[i], tb[i]) for i in bad[:5]])
+
+
+@pytest.mark.gpu
+def test_ion_sphere_stream_velocity_and_temperature(tmp_path):
+    """north_star parity check #2 for the ION species: steady-state mesh-averaged density, stream velocity and temperature on the
+    full injection run of the sphere case.  bin/ion_sphere and the golden run are the SAME driver file (host/ion_sphere.cpp: the
+    ch3/ver2 program written against the ch4 class API, with Species::sampleMoments / computeGasProperties, ch4/Species.cpp:190-240);
+    the golden numbers come from compiling it against the unmodified ch4 reference sources (oracle/_ref/ref_ch4_ion_sphere, shipped
+    GS solver, tests/golden/make_ion_sphere_statistics.py).  Statistical pins: the reference seeds from std::random_device; the
+    tolerances are a few times the difference between two reference runs (recorded in the golden file)."""
+    import json
+    exe = os.path.join(BIN, "ion_sphere")
+    gold = json.load(open(os.path.join(sf.ROOT, "tests", "golden", "ch4_ion_sphere_statistics.json")))
+    ref, spread = gold["run"], gold["spread_between_two_reference_runs"]
+    r = subprocess.run([exe, "400", "PCG"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ESPIC_SEED="2024"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout[r.stdout.index("{"):])
+    assert abs(got["steady_state_ts"] - ref["steady_state_ts"]) <= 15
+    assert abs(got["mp_count"] / ref["mp_count"] - 1) < 0.01 and abs(got["KE"] / ref["KE"] - 1) < 0.01
+    for key, floor in (("den_ave_k_profile", 0.02), ("uz_k_profile", 0.005), ("T_k_profile", 0.05), ("den_ave_axis_profile", 0.10),
+                       ("uz_axis_profile", 0.03), ("T_axis_profile", 0.15), ("uz_wake_plane", 0.01), ("T_wake_plane", 0.10)):
+        a, b = np.array(got[key]), np.array(ref[key])
+        tol = max(floor, 4 * spread[key])
+        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (key, np.abs(a - b).max() / np.abs(b).max(), tol)
