@@ -461,10 +461,10 @@ class Case:
 
 
 # algorithmic bytes of the multigrid Newton solve (espic_mg.cuh), per node
-MG_FINE_BYTES_PER_IT = 97      # A: r 8 + diag 4 | B: r 8 + diag 4 + e 1, z 4 written | C: z 4 + d 8 + diag 4, d' 8 written | D: d' 8 + diag 4 + delta 8+8 + r 8+8
-MG_COARSE_BYTES_PER_IT = 62    # FP32 level: down 24 read + 5 written, up 29 read + 4 written
-MG_NEWTON_BYTES = 75           # linearise 17 read + 28 written, Galerkin 5, update 17 read + 8 written
-MG_LINEARISE_BYTES = 45        # the closing residual evaluation
+MG_FINE_BYTES_PER_IT = 93      # A: rf 4 + winv 4 | B: rf 4 + winv 4 + e 1, z 4 written | C: z 4 + d 8 + diag 4, d' 8 written | D: d' 8 + diag 4 + delta 8+8 + r 8+8, rf 4 written
+MG_COARSE_BYTES_PER_IT = 61    # FP32 level: down 24 read + 4.5 written, up 28.5 read + 4 written
+MG_NEWTON_BYTES = 83           # linearise 17 read + 36 written, coarse diagonals 5, update 17 read + 8 written
+MG_LINEARISE_BYTES = 53        # the closing residual evaluation
 
 
 def poisson_roofline(case, res, peak):

@@ -1447,6 +1447,8 @@ static int mg_grid(espic_ctx *c, K kernel, size_t smem, const StencilC &s, int p
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, MG_THREADS, smem));
     if (bps < 1) { espic_set_error("the multigrid Newton kernel cannot be made resident"); return -1; }
+    static const int bps_env = getenv("ESPIC_MG_BLOCKS_PER_SM") ? atoi(getenv("ESPIC_MG_BLOCKS_PER_SM")) : 0;
+    if (bps_env > 0 && bps_env < bps) bps = bps_env;
     // no more blocks than marching work items (small meshes: fewer blocks = cheaper barriers)
     const long long units = (long long)((s.ni + MG_TX - 1) / MG_TX) * ((s.nj + MG_TY - 1) / MG_TY) * ((planes + kunit - 1) / kunit);
     *grid = (int)std::min<long long>((long long)bps * c->sm_count, std::max<long long>(units, 1));

@@ -74,6 +74,7 @@ int World::register_species(Species *, double mass, double charge, double mpw0)
     int id = espic_species_create(engine(), mass, charge, mpw0, 0);
     espic_host::check(id, "espic_species_create");
     n_species++;
+    if (charge != 0) n_charged++;
     return id;
 }
 
@@ -83,11 +84,14 @@ double World::getWallTime()
     return d.count();
 }
 
-// World::computeChargeDensity (World.cpp:46-54).  The engine sums charge*den over every species of this World.
+// World::computeChargeDensity (World.cpp:46-54).  The engine sums charge*den over every species of this World; the reference sums
+// over the vector it is given and skips neutral species, so the two agree exactly when the vector holds every CHARGED species.
 void World::computeChargeDensity(std::vector<Species> &species)
 {
-    if ((int)species.size() != n_species)
-        throw std::runtime_error("World::computeChargeDensity: pass all species created on this World");
+    int charged = 0;
+    for (Species &sp : species) charged += sp.charge != 0;
+    if (charged != n_charged)
+        throw std::runtime_error("World::computeChargeDensity: pass every charged species created on this World");
     for (Species &sp : species) sp.den.to_device();
     espic_host::check(espic_charge_density(engine()), "espic_charge_density");
     rho.mark_device_wrote();

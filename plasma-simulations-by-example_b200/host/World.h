@@ -120,7 +120,7 @@ protected:
     int num_threads = 1;
 
     espic_ctx *ctx = nullptr;
-    int n_species = 0;
+    int n_species = 0, n_charged = 0;
     unsigned n_sources = 0;
 };
 
