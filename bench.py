@@ -700,30 +700,41 @@ def main():
     # ---------------------------------------------------------------- e2e: same steps through the API with host buffers
     e2e = None
     if not args.no_e2e:
+        # a second, identical case taken through the same warm-up: the e2e region then works on the population the device-timed
+        # region worked on (the beam leaves the box at ~0.5 % per step; timing the e2e steps on what the headline region left
+        # behind would compare 1.6e8 with 1.85e8 particles per step)
+        ec = Case(ctx, n_mesh, n_local, n_total, args.solver, args.sort_every, args.fixed_point, args.fuse, args.decomp, sort_order=args.sort_order)
+        for i in range(args.warmup):
+            ec.step()
+        e, sp = ec.e, ec.sp
         rng = np.random.default_rng(99 + rank)
         n_inj = max(1, int(0.003 * n_local))
-        batches = [host_particles(rng, n_inj, head.mpw) for _ in range(2)]
+        batches = [host_particles(rng, n_inj, ec.mpw) for _ in range(2)]
         pinned = [torch.from_numpy(b).pin_memory() for b in batches]
         pb = [p.numpy() for p in pinned]
         h2d = 7 * 8 * n_inj
         d2h = 0
         phi_host = [torch.empty(n_mesh ** 3, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
         m_diag, m_pre, m_async = bool(args.e2e_mode & 1), bool(args.e2e_mode & 2), bool(args.e2e_mode & 4)
+        skip = int(os.environ.get("BENCH_E2E_SKIP", "0"))      # development aid: 1 no injection, 2 no diagnostics, 4 no potential
         if m_diag:
-            head.pflags |= es.PUSH_DIAG                        # the step's diagnostics ride in the push kernel's registers
+            ec.pflags |= es.PUSH_DIAG                          # the step's diagnostics ride in the push kernel's registers
 
-        def e2e_steps(count):
+        def e2e_steps(count, pev=None):
             pushed, d2h_b = 0, 0
-            if m_pre:
+            if m_pre and not skip & 1:
                 e.prefetch_particles(sp, pb[0])                # the copy engine works one step ahead of the kernels
             for i in range(count):
-                e.add_particles(sp, pb[i % 2], DT)             # host -> device: this step's injected particles (staged by the prefetch)
-                if m_pre and i + 1 < count:
-                    e.prefetch_particles(sp, pb[(i + 1) % 2])  # next step's batch travels while this step computes
+                if not skip & 1:
+                    e.add_particles(sp, pb[i % 2], DT)         # host -> device: this step's injected particles (staged by the prefetch)
+                    if m_pre and i + 1 < count:
+                        e.prefetch_particles(sp, pb[(i + 1) % 2])  # next step's batch travels while this step computes
                 pushed += e.count(sp)
-                head.step()
-                dg = e.diag(sp)                                # device -> host: the step's diagnostics ...
-                if m_async:
+                ec.step(None, erec if pev else None, pev[i] if pev else None)
+                dg = e.diag(sp) if not skip & 2 else np.zeros(5)   # device -> host: the step's diagnostics ...
+                if skip & 4:
+                    pass
+                elif m_async:
                     if i > 0:
                         e.copy_sync()                          # (previous step's potential has arrived in its pinned buffer)
                     e.field_async(es.PHI, phi_host[i % 2])     # ... and the potential (what Output::fields reads), on the copy stream
@@ -746,10 +757,10 @@ def main():
                 return r
             for i in range(6):
                 timed_call("add_particles", lambda: e.add_particles(sp, pb[i % 2], DT))
-                timed_call("push", lambda: e.push(sp, DT, es.WALL_ABSORB, head.pflags))
-                timed_call("deposit", lambda: e.deposit(sp, head.dmode))
+                timed_call("push", lambda: e.push(sp, DT, es.WALL_ABSORB, ec.pflags))
+                timed_call("deposit", lambda: e.deposit(sp, ec.dmode))
                 timed_call("rho", lambda: e.compute_charge_density())
-                timed_call("solve", lambda: e.solve(head.solver, head.max_it, head.tol))
+                timed_call("solve", lambda: e.solve(ec.solver, ec.max_it, ec.tol))
                 timed_call("ef", lambda: e.compute_ef())
                 timed_call("diag", lambda: e.diag(sp))
                 timed_call("phi download", lambda: e.field(es.PHI, out=phi_host[0]))
@@ -760,11 +771,18 @@ def main():
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pushed_e2e, d2h = e2e_steps(args.steps)
-        head.pflags &= ~es.PUSH_DIAG
+        pev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+        erec = []
+        pushed_e2e, d2h = e2e_steps(args.steps, pev)
         e1.record()
         torch.cuda.synchronize()
         ms_e = e0.elapsed_time(e1)
+        eph = np.array([[p[j].elapsed_time(p[j + 1]) for j in range(5)] for p in pev]).mean(axis=0)
+        e2e_phases = {"push+removal+diagnostics": float(eph[0]), "sort(amortised)": float(eph[1]), "deposit+rho": float(eph[2]),
+                      "poisson": float(eph[3]), "ef": float(eph[4]),
+                      "injection, downloads, host gaps": float(ms_e / args.steps - eph.sum())}
+        ec.close()
+        e, sp = head.e, head.sp
         if world > 1:
             tms = torch.tensor([ms_e, pushed_e2e], dtype=torch.float64, device=dev)
             mx = tms.clone()
@@ -773,7 +791,10 @@ def main():
             ms_e, pushed_e2e = float(mx[0].item()), float(tms[1].item())
         log("e2e region done")
         e2e = {"value": pushed_e2e / (ms_e * 1e-3), "unit": "particle-pushes/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / args.steps}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / args.steps,
+               "particles_per_step": pushed_e2e / args.steps / world, "phases_ms": e2e_phases, "k_push_ms": float(np.mean([r[2] for r in erec])),
+               "note": "a second, identical case after the same warm-up steps (+3 untimed e2e steps), so that both regions push the same "
+                       "population; every step: injected particles from pinned host memory, diagnostics and the potential back to the host"}
 
     # ---------------------------------------------------------------- the same step with ch9's own default field solver (QN)
     variants = None

@@ -161,7 +161,7 @@ extern "C" void espic_destroy(espic_ctx *c)
         cudaFree(c->sp[s].kill_words); cudaFree(c->sp[s].leave_words);
     }
     cudaFree(c->dead_words); cudaFree(c->hit_words); cudaFree(c->scan_pre); cudaFree(c->scan_coff); cudaFree(c->lists);
-    cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->node_type);
+    cudaFree(c->red); cudaFree(c->dscal); cudaFree(c->cell_cnt); cudaFree(c->sort_key); cudaFree(c->sort_src); cudaFree(c->node_type);
     for (int q = 0; q < 8; q++) cudaFree(c->sv[q]);
     if (c->push_ev0) { cudaEventDestroy(c->push_ev0); cudaEventDestroy(c->push_ev1); }
     cudaFreeHost(c->hpin);

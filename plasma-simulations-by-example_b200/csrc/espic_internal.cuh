@@ -81,6 +81,8 @@ struct espic_ctx {
     unsigned long long *dscal = nullptr;                      // small device scalars (128 x 8 B)
     void *hpin = nullptr;                                     // pinned host mirror of dscal (128 x 8 B)
     uint32_t *cell_cnt = nullptr;  long long cell_cap = 0;
+    uint32_t *sort_key = nullptr;  long long sort_key_cap = 0;   // cell sort: key of every particle, then ...
+    uint32_t *sort_src = nullptr;  long long sort_src_cap = 0;   // ... the particle that goes to every place of the new order
     // solver work vectors
     double *sv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint8_t *node_type = nullptr;

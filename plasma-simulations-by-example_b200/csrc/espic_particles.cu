@@ -438,6 +438,207 @@ __global__ void __launch_bounds__(DT_THREADS) k_deposit_tile(MeshC m, const doub
     dt_finish<MODE, STRIDE, GROUP>(m, t, acc, scale);
 }
 
+// ---- grouped deposit, second version ---------------------------------------------------------------------------------
+// k_deposit_tile above spends its time in the L1/shared-memory pipe (ncu, profiles/r2_ncu_full_push_deposit_2e8.txt: 89 % busy;
+// 2900 shared-memory wavefronts per tile, a third of them bank conflicts: the staged fractions are written with a two-particle
+// stride and read back through the sort permutation).  Same algorithm, half the shared-memory traffic:
+//   1. every thread loads FOUR CONSECUTIVE particles (one 256-bit load per array) and keeps their cell fractions in REGISTERS;
+//      the hash insertion returns the particle's rank inside its cell with the count it adds (no second pass over the table);
+//   2. one scan turns the per-cell counts into offsets;
+//   3. every particle's record goes straight to its place in cell order (the only copy shared memory ever holds), in a layout
+//      padded by one element per sixteen so that the blocked read of step 4 has no bank conflicts;
+//   4. every thread merges four consecutive records of that order, the warp merges runs, run heads issue the REDs.
+// (Measured and dropped: merging the four particles of a thread BEFORE the grouping -- after a few pushes a tile of 1024 particles
+// still holds 430-640 such entries in 36-60 cells, profiles/r2_deposit_kernel_history.txt -- and replacing the warp's shuffle
+// reduction by one thread per (run of equal cells, node) over staged entry sums: 2.55 against 2.42 ms.)
+#define DG_THREADS 256
+#define DG_TILE (4 * DG_THREADS)
+#define DG_IDX(q) ((q) + ((q) >> 4))
+#define DG_REC (DG_TILE + DG_TILE / 16)          // padded length of one record array
+static_assert(DG_TILE <= DT_SLOTS, "one hash slot per particle of the tile");
+
+struct DepGroup {
+    double rec[4][DG_REC];                            // cell fractions and weight of every record, in cell order
+    uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS];          // hash table: lower node of the cell; particle counts, then offsets
+    uint32_t skey[DG_TILE];                           // lower node of the cell of every record, in cell order
+    uint32_t wsum[DG_THREADS / 32];
+    uint32_t n_sorted;
+};
+
+__device__ __forceinline__ void ld4(const double *p, double v[4])
+{
+    asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// four consecutive particles of the stream per thread: positions -> cell keys and fractions (in place), weights to deposit
+template <int VAL>
+__device__ __forceinline__ void load_four(const MeshC &m, const double *__restrict__ x, const double *__restrict__ y,
+                                          const double *__restrict__ z, const double *__restrict__ mpw,
+                                          const double *__restrict__ vcomp, long long g, long long n,
+                                          double X[4], double Y[4], double Z[4], double W[4], uint32_t key[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; j++) { X[j] = Y[j] = Z[j] = W[j] = 0; key[j] = DT_EMPTY; }
+    if (g >= n) return;
+    ld4(x + g, X); ld4(y + g, Y); ld4(z + g, Z); ld4(mpw + g, W);          // capacity is a multiple of 1024: g+3 is allocated
+    if (VAL > 0) {
+        double V[4];
+        ld4(vcomp + g, V);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            W[j] = W[j] * V[j];                         // mpw*v
+            if (VAL == 2) W[j] = W[j] * V[j];           // (mpw*v)*v
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (g + j >= n) W[j] = 0;
+        if (W[j] != 0) {
+            int ci, cj, ck; double d0, d1, d2;
+            cell3(m, X[j], Y[j], Z[j], ci, cj, ck, d0, d1, d2);
+            if (ci >= 0 && cj >= 0 && ck >= 0) { key[j] = (uint32_t)node_u(m, ci, cj, ck); X[j] = d0; Y[j] = d1; Z[j] = d2; }
+        }
+    }
+}
+
+template <int MODE, int VAL = 0, int STRIDE = 1>
+__global__ void __launch_bounds__(DG_THREADS, 4) k_deposit_group(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                                  const double *__restrict__ z, const double *__restrict__ mpw,
+                                                                  long long n, double *acc, double scale, int ahead,
+                                                                  const double *__restrict__ vcomp = nullptr)
+{
+    typedef typename AccVal<MODE>::T T;
+    __shared__ DepGroup t;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long base = blockIdx.x * (long long)DG_TILE;
+    if (tid < 4) {
+        const long long pf = base + (long long)ahead * DG_TILE;
+        if (ahead > 0 && pf + DG_TILE <= n) l2_prefetch((tid == 0 ? x : tid == 1 ? y : tid == 2 ? z : mpw) + pf, DG_TILE * 8);
+    }
+    reinterpret_cast<uint4 *>(t.hkey)[tid] = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
+    reinterpret_cast<uint4 *>(t.hcnt)[tid] = make_uint4(0, 0, 0, 0);
+    // ---- 1. load, cells; every particle enters the hash table (lanes of one cell through one leader) and learns its rank
+    double X[4], Y[4], Z[4], W[4];
+    uint32_t key[4], sr[4];
+    load_four<VAL>(m, x, y, z, mpw, vcomp, base + 4 * tid, n, X, Y, Z, W, key);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t kk = key[j];
+        const unsigned peers = __match_any_sync(FULL, kk);
+        const int leader = __ffs(peers) - 1;
+        uint32_t v = 0;
+        if (kk != DT_EMPTY && lane == leader) {
+            uint32_t h = (kk * 2654435761u) >> (32 - DT_SLOT_BITS);
+            for (int probe = 0; probe < DT_SLOTS; probe++) {          // the table has a slot per particle of the tile: it cannot fill up
+                const uint32_t old = atomicCAS(&t.hkey[h], DT_EMPTY, kk);
+                if (old == DT_EMPTY || old == kk) break;
+                h = (h + 1) & (DT_SLOTS - 1);
+            }
+            v = h | (atomicAdd(&t.hcnt[h], (uint32_t)__popc(peers)) << 16);
+        }
+        v = __shfl_sync(FULL, v, leader);
+        sr[j] = v + ((uint32_t)__popc(peers & ((1u << lane) - 1u)) << 16);      // slot | rank of this particle in its cell
+    }
+    __syncthreads();
+    // ---- 2. counts -> offsets
+    {
+        const uint4 c4 = reinterpret_cast<const uint4 *>(t.hcnt)[tid];
+        const uint32_t tsum = c4.x + c4.y + c4.z + c4.w;
+        uint32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) t.wsum[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t run = inc - tsum;
+        for (int w = 0; w < (tid >> 5); w++) run += t.wsum[w];
+        reinterpret_cast<uint4 *>(t.hcnt)[tid] = make_uint4(run, run + c4.x, run + c4.x + c4.y, run + c4.x + c4.y + c4.z);
+        if (tid == DG_THREADS - 1) t.n_sorted = run + tsum;
+    }
+    __syncthreads();
+    // ---- 3. records to their place in cell order
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (key[j] == DT_EMPTY) continue;
+        const uint32_t pos = t.hcnt[sr[j] & 0xffffu] + (sr[j] >> 16);
+        const uint32_t at = DG_IDX(pos);
+        t.rec[0][at] = X[j]; t.rec[1][at] = Y[j]; t.rec[2][at] = Z[j]; t.rec[3][at] = W[j];
+        t.skey[pos] = key[j];
+    }
+    __syncthreads();
+    // ---- 4. four consecutive records per thread, merged in registers; runs across lanes merged by the warp
+    const int M = (int)t.n_sorted;
+    const uint4 k4 = reinterpret_cast<const uint4 *>(t.skey)[tid];
+    const uint32_t kq[4] = {k4.x, k4.y, k4.z, k4.w};
+    T a[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = 0;
+    long long ua = -1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int q = tid * 4 + j;
+        if (q >= M) break;
+        const long long u = (long long)kq[j];
+        const int at = DG_IDX(q);
+        T v[8];
+        weights_from_fractions<MODE>(t.rec[0][at], t.rec[1][at], t.rec[2][at], t.rec[3][at], scale, v);
+        if (u != ua) {
+            if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);       // a cell boundary inside this thread's four records
+            ua = u;
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = v[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] += v[c];
+        }
+    }
+    warp_deposit<MODE, STRIDE>(m, acc, ua, a);
+}
+
+// The stream is in cell order (directly after a sort): no grouping, no shared memory.  Four consecutive particles per thread are
+// merged in registers, the warp merges runs across lanes (warp_deposit), run heads issue the REDs.
+template <int MODE, int VAL = 0, int STRIDE = 1>
+__global__ void __launch_bounds__(DG_THREADS) k_deposit_runs(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
+                                                              const double *__restrict__ z, const double *__restrict__ mpw,
+                                                              long long n, double *acc, double scale, int ahead,
+                                                              const double *__restrict__ vcomp = nullptr)
+{
+    typedef typename AccVal<MODE>::T T;
+    const int tid = threadIdx.x;
+    const long long base = blockIdx.x * (long long)DG_TILE;
+    if (tid < 4) {
+        const long long pf = base + (long long)ahead * DG_TILE;
+        if (ahead > 0 && pf + DG_TILE <= n) l2_prefetch((tid == 0 ? x : tid == 1 ? y : tid == 2 ? z : mpw) + pf, DG_TILE * 8);
+    }
+    double X[4], Y[4], Z[4], W[4];
+    uint32_t key[4];
+    load_four<VAL>(m, x, y, z, mpw, vcomp, base + 4 * tid, n, X, Y, Z, W, key);
+    T a[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = 0;
+    long long ua = -1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (key[j] == DT_EMPTY) continue;
+        T v[8];
+        weights_from_fractions<MODE>(X[j], Y[j], Z[j], W[j], scale, v);
+        if ((long long)key[j] != ua) {
+            if (ua >= 0) red8<MODE, STRIDE>(m, acc, ua, a);           // rare: a cell boundary inside this thread's four particles
+            ua = (long long)key[j];
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] = v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] += v[q];
+        }
+    }
+    warp_deposit<MODE, STRIDE>(m, acc, ua, a);
+}
+
 // den = acc / node_vol (0 where node_vol == 0): Field::operator/= (Field.h:125-134)
 template <int MODE>
 __global__ void k_den_finalize(long long nn, const double *__restrict__ acc, const double *__restrict__ node_vol,
@@ -524,7 +725,7 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
         }
     }
     const bool warp_live = wbase < n;
-    if (!DIAG && !warp_live) return;                          // (with DIAG every warp stays for the block reduction)
+    if (!warp_live) return;
     const bool v0 = i0 < n, v1 = i0 + 1 < n;
     double2 X = make_double2(m.x0[0], m.x0[0]), Y = make_double2(m.x0[1], m.x0[1]), Z = make_double2(m.x0[2], m.x0[2]);
     double2 VX = make_double2(0, 0), VY = VX, VZ = VX, W = VX;
@@ -572,42 +773,54 @@ __global__ void __launch_bounds__(256, FUSE ? 2 : 4) k_push(MeshC m, const doubl
     }
     if (FUSE) deposit_pair<MODE>(m, acc, scale, v0 && !dead0, X.x, Y.x, Z.x, W.x, v1 && !dead1, X.y, Y.y, Z.y, W.y);
     if (DIAG) {
-        __shared__ double sh_diag[40];
-        double a[5] = {0, 0, 0, 0, 0};
+        double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (v0 && !dead0) {          // the expressions of k_diag
-            a[0] += W.x; a[1] += VX.x * W.x; a[2] += VY.x * W.x; a[3] += VZ.x * W.x;
-            a[4] += W.x * (VX.x * VX.x + VY.x * VY.x + VZ.x * VZ.x);
+            b[0] += W.x; b[1] += VX.x * W.x; b[2] += VY.x * W.x; b[3] += VZ.x * W.x;
+            b[4] += W.x * (VX.x * VX.x + VY.x * VY.x + VZ.x * VZ.x);
         }
         if (v1 && !dead1) {
-            a[0] += W.y; a[1] += VX.y * W.y; a[2] += VY.y * W.y; a[3] += VZ.y * W.y;
-            a[4] += W.y * (VX.y * VX.y + VY.y * VY.y + VZ.y * VZ.y);
+            b[0] += W.y; b[1] += VX.y * W.y; b[2] += VY.y * W.y; b[3] += VZ.y * W.y;
+            b[4] += W.y * (VX.y * VX.y + VY.y * VY.y + VZ.y * VZ.y);
         }
-        // one block barrier instead of ten (five block_sum calls cost this 3.5 ms kernel as much as the separate k_diag pass):
-        // warp sums by shuffle, eight partials per quantity through shared memory, added in a fixed order
-        double (*shq)[8] = reinterpret_cast<double (*)[8]>(sh_diag);
+        // Five warp sums in nine shuffles instead of twenty-five: every exchange halves the number of quantities a lane carries
+        // (lanes 16-31 take over b[4..7], then bit 3 and bit 2 of the lane split what is left), two plain butterfly steps finish.
+        // Lane 4q ends up with the warp's sum of quantity q.  One partial per WARP and quantity, no block barrier: the warps of
+        // this memory-bound kernel retire independently (five block_sum calls cost it as much as the separate k_diag pass).
+        const unsigned FULL = 0xffffffffu;
+        double c4[4], d2[2], e1;
 #pragma unroll
-        for (int q = 0; q < 5; q++) {
-            const double t = warp_sum(a[q]);
-            if (lane == 0) shq[q][threadIdx.x >> 5] = t;
+        for (int i = 0; i < 4; i++) {
+            const double r = __shfl_xor_sync(FULL, (lane & 16) ? b[i] : b[i + 4], 16);
+            c4[i] = ((lane & 16) ? b[i + 4] : b[i]) + r;
         }
-        __syncthreads();
-        if (threadIdx.x < 5) {
-            double t = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) t += shq[threadIdx.x][w];
-            diag_part[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+        for (int i = 0; i < 2; i++) {
+            const double r = __shfl_xor_sync(FULL, (lane & 8) ? c4[i] : c4[i + 2], 8);
+            d2[i] = ((lane & 8) ? c4[i + 2] : c4[i]) + r;
         }
+        {
+            const double r = __shfl_xor_sync(FULL, (lane & 4) ? d2[0] : d2[1], 4);
+            e1 = ((lane & 4) ? d2[1] : d2[0]) + r;
+        }
+        e1 += __shfl_xor_sync(FULL, e1, 2);
+        e1 += __shfl_xor_sync(FULL, e1, 1);
+        if ((lane & 3) == 0) diag_part[(wbase >> 6) * 8 + (lane >> 2)] = e1;      // one 64-byte record per warp (slots 5-7 are zero)
     }
 }
 
-// first fold of the per-block partials of a DIAG push: nq x nparts -> nq x gridDim (fixed order: reproducible)
+// first fold of the per-warp partials of a DIAG push: nparts records of 8 doubles (nq <= 8 used) -> nq x gridDim (fixed order:
+// reproducible).  Every thread walks whole records, so a warp reads 2 KB of consecutive memory per step.
 __global__ void __launch_bounds__(256) k_diag_fold(const double *__restrict__ part, long long nparts, int nq, double *__restrict__ out)
 {
     __shared__ double sh[32];
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nparts; i += (long long)gridDim.x * 256) {
+        const double4 lo = *reinterpret_cast<const double4 *>(part + i * 8);
+        const double4 hi = *reinterpret_cast<const double4 *>(part + i * 8 + 4);
+        a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+    }
     for (int q = 0; q < nq; q++) {
-        double a = 0;
-        for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nparts; i += (long long)gridDim.x * 256) a += part[(size_t)q * nparts + i];
-        const double t = block_sum(a, sh);
+        const double t = block_sum(a[q], sh);
         if (threadIdx.x == 0) out[(size_t)q * gridDim.x + blockIdx.x] = t;
     }
 }
@@ -810,7 +1023,9 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
     if (wall_mode == ESPIC_WALL_ABSORB) { if ((r = ensure_buf(&s.kill_words, &s.kill_cap, mig ? nw + nw / 16 + 1024 : nw, c->stream))) return r; }
     if (mig) { if ((r = ensure_buf(&s.leave_words, &s.leave_cap, nw, c->stream))) return r; }
     const unsigned grid = nblk((n + 1) / 2, 256);
-    if (diag && (r = ensure_buf(&c->red, &c->red_cap, 5ll * grid + 5 * 64, c->stream))) return r;
+    const long long nwarp = (n + 63) / 64;           // one partial record (8 doubles, 5 used) per warp of the push
+    const int fold_blocks = 4 * c->sm_count;
+    if (diag && (r = ensure_buf(&c->red, &c->red_cap, 8 * nwarp + 5 * fold_blocks, c->stream))) return r;
     if (!c->push_ev0) { CK(cudaEventCreate(&c->push_ev0)); CK(cudaEventCreate(&c->push_ev1)); }
     CK(cudaEventRecord(c->push_ev0, c->stream));
     static const int ahead_env = getenv("ESPIC_PUSH_PREFETCH") ? atoi(getenv("ESPIC_PUSH_PREFETCH")) : -1;
@@ -849,10 +1064,10 @@ extern "C" int espic_push(espic_ctx *c, int sp, double dt, int wall_mode, int fl
 
     double *hd = reinterpret_cast<double *>(c->hpin) + 100;
     if (diag) {
-        double *fold = c->red + 5ll * grid, *dout = reinterpret_cast<double *>(c->dscal + 100);
-        k_diag_fold<<<64, 256, 0, c->stream>>>(c->red, grid, 5, fold);
+        double *fold = c->red + 8 * nwarp, *dout = reinterpret_cast<double *>(c->dscal + 100);
+        k_diag_fold<<<fold_blocks, 256, 0, c->stream>>>(c->red, nwarp, 5, fold);
         LAUNCH_CHECK(c);
-        k_reduce_final<<<1, 256, 0, c->stream>>>(fold, 64, 5, dout);
+        k_reduce_final<<<1, 256, 0, c->stream>>>(fold, fold_blocks, 5, dout);
         LAUNCH_CHECK(c);
         CK(cudaMemcpyAsync(hd, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // arrives with the removal's count
     }
@@ -899,13 +1114,18 @@ extern "C" int espic_deposit(espic_ctx *c, int sp, int mode)
             static const int ahead_env = getenv("ESPIC_DEPOSIT_PREFETCH") ? atoi(getenv("ESPIC_DEPOSIT_PREFETCH")) : -1;
             const int ahead = ahead_env >= 0 ? ahead_env : 2 * c->sm_count;
             const unsigned tgrid = nblk(s.np, DT_TILE);
+            static const bool v1 = getenv("ESPIC_DEPOSIT_V1") != nullptr;      // the round-1 tile kernel, for A/B measurements
 #define DEP_ARGS c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, s.acc, scale, ahead
             if (mode == ESPIC_DEPOSIT_FP64) {
-                if (ordered) k_deposit_tile<ESPIC_DEPOSIT_FP64, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
-                else k_deposit_tile<ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                if (v1 && ordered) k_deposit_tile<ESPIC_DEPOSIT_FP64, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else if (v1) k_deposit_tile<ESPIC_DEPOSIT_FP64><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else if (ordered) k_deposit_runs<ESPIC_DEPOSIT_FP64><<<tgrid, DG_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else k_deposit_group<ESPIC_DEPOSIT_FP64><<<tgrid, DG_THREADS, 0, c->stream>>>(DEP_ARGS);
             } else {
-                if (ordered) k_deposit_tile<ESPIC_DEPOSIT_FIXED, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
-                else k_deposit_tile<ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                if (v1 && ordered) k_deposit_tile<ESPIC_DEPOSIT_FIXED, 0, 1, false><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else if (v1) k_deposit_tile<ESPIC_DEPOSIT_FIXED><<<tgrid, DT_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else if (ordered) k_deposit_runs<ESPIC_DEPOSIT_FIXED><<<tgrid, DG_THREADS, 0, c->stream>>>(DEP_ARGS);
+                else k_deposit_group<ESPIC_DEPOSIT_FIXED><<<tgrid, DG_THREADS, 0, c->stream>>>(DEP_ARGS);
             }
 #undef DEP_ARGS
             LAUNCH_CHECK(c);
@@ -1030,12 +1250,12 @@ extern "C" int espic_sample_moments(espic_ctx *c, int sp)
     const unsigned grid = nblk(s.np, DT_TILE);
     const int ahead = 0;
 #define TILE_ARGS(dst, v) c->m, s.p[0], s.p[1], s.p[2], s.p[6], s.np, (dst), 1.0, ahead, (v)
-    k_deposit_tile<ESPIC_DEPOSIT_FP64, 0, 1><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom, nullptr));              // n_sum
+    k_deposit_group<ESPIC_DEPOSIT_FP64, 0, 1><<<grid, DG_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom, nullptr));              // n_sum
     LAUNCH_CHECK(c);
     for (int q = 0; q < 3; q++) {
-        k_deposit_tile<ESPIC_DEPOSIT_FP64, 1, 3><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + nn + q, s.p[3 + q]));  // nv_sum
+        k_deposit_group<ESPIC_DEPOSIT_FP64, 1, 3><<<grid, DG_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + nn + q, s.p[3 + q]));  // nv_sum
         LAUNCH_CHECK(c);
-        k_deposit_tile<ESPIC_DEPOSIT_FP64, 2, 1><<<grid, DT_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + (4 + q) * nn, s.p[3 + q]));   // nuu, nvv, nww
+        k_deposit_group<ESPIC_DEPOSIT_FP64, 2, 1><<<grid, DG_THREADS, 0, c->stream>>>(TILE_ARGS(s.mom + (4 + q) * nn, s.p[3 + q]));   // nuu, nvv, nww
         LAUNCH_CHECK(c);
     }
 #undef TILE_ARGS
@@ -1083,18 +1303,29 @@ __device__ __forceinline__ long long cell_key(const MeshC &m, double x, double y
     if (i < 0) i = 0;
     if (j < 0) j = 0;
     if (k < 0) { k = 0; d2 = 0; }
-    int zb = (int)(d2 * SORT_ZBINS);
-    zb = zb < 0 ? 0 : (zb > SORT_ZBINS - 1 ? SORT_ZBINS - 1 : zb);
-    if (order == 1) return (((long long)j * (m.ni - 1) + i) * (long long)(m.nk - 1) + k) * SORT_ZBINS + zb;
-    return (((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i) * SORT_ZBINS + zb;
+    const int zbins = order >> 8;                       // (the callers pack the number of z slabs per cell above the order)
+    int zb = (int)(d2 * zbins);
+    zb = zb < 0 ? 0 : (zb > zbins - 1 ? zbins - 1 : zb);
+    if ((order & 255) == 1) return (((long long)j * (m.ni - 1) + i) * (long long)(m.nk - 1) + k) * zbins + zb;
+    return (((long long)k * (m.nj - 1) + j) * (long long)(m.ni - 1) + i) * zbins + zb;
 }
 
+// The sort runs in three passes (round 2; the one-pass scatter it replaces wrote every particle's seven values to its new
+// place with 8-byte stores spread over many cache lines -- ncu: 17 sectors per store request, 5 GB of read-for-write fills,
+// 35 % of the DRAM bandwidth, every warp waiting on its atomic -- and took 10.9 of the sort's 12.5 ms at 2e8 particles):
+//   1. k_cell_count  keys of all particles (stored, 4 bytes each) and the population of every key;
+//   2. k_cell_rank   every particle draws its place inside its key (one atomic per warp and key) and writes ITS INDEX there:
+//                    the only scattered stores of the sort are 4 bytes wide;
+//   3. k_cell_gather place j of the new order reads the particle src[j]: seven gathers whose neighbours in j are mostly
+//                    neighbours in memory (the stream was in order a few steps ago), seven fully coalesced streaming stores.
 __global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__restrict__ x, const double *__restrict__ y,
-                                                    const double *__restrict__ z, long long n, uint32_t *__restrict__ cnt, int order)
+                                                    const double *__restrict__ z, long long n, uint32_t *__restrict__ cnt,
+                                                    uint32_t *__restrict__ keys, int order)
 {
     long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= n) return;
-    long long cell = cell_key(m, x[idx], y[idx], z[idx], order);
+    const uint32_t cell = (uint32_t)cell_key(m, __ldcs(x + idx), __ldcs(y + idx), __ldcs(z + idx), order);
+    keys[idx] = cell;
     // warp-aggregate equal keys (sorted input: most of a warp shares a cell)
     unsigned act = __activemask();
     unsigned peers = __match_any_sync(act, cell);
@@ -1102,31 +1333,39 @@ __global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__res
     if ((threadIdx.x & 31) == leader) atomicAdd(cnt + cell, (uint32_t)__popc(peers));
 }
 
-__global__ void __launch_bounds__(256) k_cell_scatter(MeshC m, long long n, uint32_t *__restrict__ cnt,
-                                                      const uint32_t *__restrict__ pre, const uint32_t *__restrict__ coff,
-                                                      const double *__restrict__ s0, const double *__restrict__ s1, const double *__restrict__ s2,
-                                                      const double *__restrict__ s3, const double *__restrict__ s4, const double *__restrict__ s5,
-                                                      const double *__restrict__ s6,
-                                                      double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
-                                                      double *__restrict__ d3, double *__restrict__ d4, double *__restrict__ d5,
-                                                      double *__restrict__ d6, int order)
+__global__ void __launch_bounds__(256) k_cell_rank(long long n, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ pre,
+                                                   const uint32_t *__restrict__ coff, const uint32_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ src)
 {
     long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= n) return;
-    double x = s0[idx], y = s1[idx], z = s2[idx];
-    long long cell = cell_key(m, x, y, z, order);
+    const uint32_t cell = keys[idx];
     unsigned act = __activemask();
     unsigned peers = __match_any_sync(act, cell);
     int lane = threadIdx.x & 31;
     int leader = __ffs(peers) - 1;
     uint32_t basec = 0;
-    if (lane == leader) basec = atomicSub(cnt + cell, (uint32_t)__popc(peers));
+    if (lane == leader) basec = atomicSub(cnt + cell, (uint32_t)__popc(peers)) + scan_at(pre, coff, cell);
     basec = __shfl_sync(peers, basec, leader);
-    // slots [basec - popc, basec) of the cell; ranks in lane order keep the previous relative order inside a warp
-    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    long long dst = (long long)scan_at(pre, coff, cell) + (basec - __popc(peers)) + rank;
-    d0[dst] = x; d1[dst] = y; d2[dst] = z;
-    d3[dst] = s3[idx]; d4[dst] = s4[idx]; d5[dst] = s5[idx]; d6[dst] = s6[idx];
+    // places [basec - popc, basec) of the key; ranks in lane order keep the previous relative order inside a warp
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    src[basec - __popc(peers) + rank] = (uint32_t)idx;
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather(long long n, const uint32_t *__restrict__ src,
+                                                     const double *__restrict__ s0, const double *__restrict__ s1, const double *__restrict__ s2,
+                                                     const double *__restrict__ s3, const double *__restrict__ s4, const double *__restrict__ s5,
+                                                     const double *__restrict__ s6,
+                                                     double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
+                                                     double *__restrict__ d3, double *__restrict__ d4, double *__restrict__ d5,
+                                                     double *__restrict__ d6)
+{
+    long long j = blockIdx.x * 256ll + threadIdx.x;
+    if (j >= n) return;
+    const long long i = src[j];
+    const double a0 = s0[i], a1 = s1[i], a2 = s2[i], a3 = s3[i], a4 = s4[i], a5 = s5[i], a6 = s6[i];
+    __stcs(d0 + j, a0); __stcs(d1 + j, a1); __stcs(d2 + j, a2); __stcs(d3 + j, a3);
+    __stcs(d4 + j, a4); __stcs(d5 + j, a5); __stcs(d6 + j, a6);
 }
 
 extern "C" int espic_sort_by_cell(espic_ctx *c, int sp) { return espic_sort_particles(c, sp, ESPIC_SORT_XTOC); }
@@ -1145,7 +1384,10 @@ extern "C" int espic_sort_particles(espic_ctx *c, int sp, int order)
                         "Particle::dt is tracked by index -- sort after the advance", sp);
         return -1;
     }
-    const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1) * SORT_ZBINS;
+    static const int zbins_env = getenv("ESPIC_SORT_ZBINS") ? atoi(getenv("ESPIC_SORT_ZBINS")) : SORT_ZBINS;
+    const int zbins = zbins_env < 1 ? 1 : (zbins_env > 64 ? 64 : zbins_env);
+    const long long nc = (long long)(c->m.ni - 1) * (c->m.nj - 1) * (c->m.nk - 1) * zbins;
+    const int korder = order | (zbins << 8);
     int r;
     if (s.alt_cap < s.cap) {
         for (int q = 0; q < 7; q++) {
@@ -1154,14 +1396,18 @@ extern "C" int espic_sort_particles(espic_ctx *c, int sp, int order)
         }
         s.alt_cap = s.cap;
     }
+    if (nc >= (1ll << 32) || n >= (1ll << 32)) { espic_set_error("espic_sort_particles: more than 2^32 keys or particles"); return -1; }
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, nc, c->stream))) return r;
+    if ((r = ensure_buf(&c->sort_key, &c->sort_key_cap, n, c->stream))) return r;
+    if ((r = ensure_buf(&c->sort_src, &c->sort_src_cap, n, c->stream))) return r;
     CK(cudaMemsetAsync(c->cell_cnt, 0, (size_t)nc * sizeof(uint32_t), c->stream));
-    k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt, order);
+    k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt, c->sort_key, korder);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nc, c->dscal + 1))) return r;
-    k_cell_scatter<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, n, c->cell_cnt, c->scan_pre, c->scan_coff,
-                                                        s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
-                                                        s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6], order);
+    k_cell_rank<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->cell_cnt, c->scan_pre, c->scan_coff, c->sort_key, c->sort_src);
+    LAUNCH_CHECK(c);
+    k_cell_gather<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->sort_src, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
+                                                       s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6]);
     LAUNCH_CHECK(c);
     for (int q = 0; q < 7; q++) std::swap(s.p[q], s.alt[q]);
     std::swap(s.cap, s.alt_cap);
@@ -1236,13 +1482,27 @@ __device__ __forceinline__ void add_candidate(const MeshC &m, const AddSrc &a, l
     }
 }
 
-__global__ void __launch_bounds__(256) k_add_flags(MeshC m, AddSrc a, long long n, uint32_t *__restrict__ flags)
+// wmax (caller-supplied candidates only): largest weight among the candidates, as the bit pattern of a non-negative double
+// (the fixed-point scatter scales by it; the host used to walk the pinned array for this while the GPU sat idle)
+__global__ void __launch_bounds__(256) k_add_flags(MeshC m, AddSrc a, long long n, uint32_t *__restrict__ flags,
+                                                   unsigned long long *__restrict__ wmax)
 {
     long long i = blockIdx.x * 256ll + threadIdx.x;
-    if (i >= n) return;
     double q[7];
-    add_candidate(m, a, i, q);
-    flags[i] = in_bounds(m, q[0], q[1], q[2]) ? 1u : 0u;
+    q[6] = 0;
+    if (i < n) {
+        add_candidate(m, a, i, q);
+        flags[i] = in_bounds(m, q[0], q[1], q[2]) ? 1u : 0u;
+    }
+    if (wmax) {
+        unsigned long long b = q[6] > 0 ? (unsigned long long)__double_as_longlong(q[6]) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+            b = t > b ? t : b;
+        }
+        if ((threadIdx.x & 31) == 0 && b) atomicMax(wmax, b);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_add_write(MeshC m, AddSrc a, long long n, const double *__restrict__ ef4,
@@ -1277,7 +1537,9 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
     int r;
     if ((r = espic_species_reserve(c, sp, s.np + n))) return r;
     if ((r = ensure_buf(&c->cell_cnt, &c->cell_cap, n, c->stream))) return r;
-    k_add_flags<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->cell_cnt);
+    unsigned long long *wmax = a.philox == 0 ? c->dscal + 110 : nullptr;
+    if (wmax) CK(cudaMemsetAsync(wmax, 0, sizeof(unsigned long long), c->stream));
+    k_add_flags<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, a, n, c->cell_cnt, wmax);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, n, c->dscal + 2))) return r;
     const double qm = s.charge / s.mass, hdt = 0.5 * dt;
@@ -1286,7 +1548,13 @@ static int add_common(espic_ctx *c, int sp, AddSrc &a, long long n, double dt, l
     LAUNCH_CHECK(c);
     unsigned long long *h = (unsigned long long *)c->hpin;
     CK(cudaMemcpyAsync(h + 2, c->dscal + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    if (wmax) CK(cudaMemcpyAsync(h + 110, wmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (wmax) {
+        double w;
+        memcpy(&w, h + 110, sizeof(double));
+        if (w > s.mpw_max) s.mpw_max = w;
+    }
     s.np += (long long)h[2];
     s.acc_fresh = false;
     if (n_added) *n_added = (long long)h[2];
@@ -1323,7 +1591,6 @@ extern "C" int espic_species_add(espic_ctx *c, int sp, const double *const comp[
     SP_CHECK(c, sp);
     CK(cudaSetDevice(c->device));
     if (n <= 0) { if (n_added) *n_added = 0; return 0; }
-    Species &s = c->sp[sp];
     int r;
     AddSrc a;
     memset(&a, 0, sizeof(a));
@@ -1341,8 +1608,7 @@ extern "C" int espic_species_add(espic_ctx *c, int sp, const double *const comp[
             a.in[q] = c->red + q * n;
         }
     }
-    for (long long i = 0; i < n; i++) if (comp[6][i] > s.mpw_max) s.mpw_max = comp[6][i];
-    return add_common(c, sp, a, n, dt, n_added);
+    return add_common(c, sp, a, n, dt, n_added);      // (the largest weight comes back with the admission count)
 }
 
 extern "C" int espic_inject_cold_beam(espic_ctx *c, int sp, double v_drift, double den, double dt,
