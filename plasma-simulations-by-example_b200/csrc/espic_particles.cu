@@ -1333,23 +1333,39 @@ __global__ void __launch_bounds__(256) k_cell_count(MeshC m, const double *__res
     if ((threadIdx.x & 31) == leader) atomicAdd(cnt + cell, (uint32_t)__popc(peers));
 }
 
+// four consecutive particles per thread: the four atomics of a thread are independent and stay in flight together (the pass is
+// bound by their latency, not by its 8 bytes per particle)
 __global__ void __launch_bounds__(256) k_cell_rank(long long n, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ pre,
                                                    const uint32_t *__restrict__ coff, const uint32_t *__restrict__ keys,
                                                    uint32_t *__restrict__ src)
 {
-    long long idx = blockIdx.x * 256ll + threadIdx.x;
-    if (idx >= n) return;
-    const uint32_t cell = keys[idx];
-    unsigned act = __activemask();
-    unsigned peers = __match_any_sync(act, cell);
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(peers) - 1;
-    uint32_t basec = 0;
-    if (lane == leader) basec = atomicSub(cnt + cell, (uint32_t)__popc(peers)) + scan_at(pre, coff, cell);
-    basec = __shfl_sync(peers, basec, leader);
-    // places [basec - popc, basec) of the key; ranks in lane order keep the previous relative order inside a warp
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    src[basec - __popc(peers) + rank] = (uint32_t)idx;
+    const unsigned FULL = 0xffffffffu;
+    const long long i0 = 4 * (blockIdx.x * 256ll + threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    if (i0 - 4 * lane >= n) return;                               // whole warp past the end
+    uint32_t k[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (i0 + 3 < n) {
+        const uint4 k4 = *reinterpret_cast<const uint4 *>(keys + i0);
+        k[0] = k4.x; k[1] = k4.y; k[2] = k4.z; k[3] = k4.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (i0 + j < n) k[j] = keys[i0 + j];
+    }
+    unsigned peers[4];
+    uint32_t basec[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        peers[j] = __match_any_sync(FULL, k[j]);
+        basec[j] = 0;
+        if (k[j] != 0xffffffffu && lane == __ffs(peers[j]) - 1)
+            basec[j] = atomicSub(cnt + k[j], (uint32_t)__popc(peers[j])) + scan_at(pre, coff, k[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t b = __shfl_sync(FULL, basec[j], __ffs(peers[j]) - 1);
+        // places [b - popc, b) of the key; ranks in lane order
+        if (k[j] != 0xffffffffu) src[b - __popc(peers[j]) + __popc(peers[j] & ((1u << lane) - 1u))] = (uint32_t)(i0 + j);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_cell_gather(long long n, const uint32_t *__restrict__ src,
@@ -1404,7 +1420,7 @@ extern "C" int espic_sort_particles(espic_ctx *c, int sp, int order)
     k_cell_count<<<nblk(n, 256), 256, 0, c->stream>>>(c->m, s.p[0], s.p[1], s.p[2], n, c->cell_cnt, c->sort_key, korder);
     LAUNCH_CHECK(c);
     if ((r = espic_scan_u32(c, c->cell_cnt, nc, c->dscal + 1))) return r;
-    k_cell_rank<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->cell_cnt, c->scan_pre, c->scan_coff, c->sort_key, c->sort_src);
+    k_cell_rank<<<nblk((n + 3) / 4, 256), 256, 0, c->stream>>>(n, c->cell_cnt, c->scan_pre, c->scan_coff, c->sort_key, c->sort_src);
     LAUNCH_CHECK(c);
     k_cell_gather<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->sort_src, s.p[0], s.p[1], s.p[2], s.p[3], s.p[4], s.p[5], s.p[6],
                                                        s.alt[0], s.alt[1], s.alt[2], s.alt[3], s.alt[4], s.alt[5], s.alt[6]);
