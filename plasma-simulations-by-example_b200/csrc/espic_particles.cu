@@ -196,6 +196,7 @@ __device__ __forceinline__ void warp_deposit(const MeshC &m, double *acc, long l
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const bool take = lane + o <= run_end;
+        if (!__any_sync(FULL, take)) break;        // no run of this warp is longer than o lanes: the remaining rounds add nothing
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             typename AccVal<MODE>::T t = __shfl_down_sync(FULL, w[q], o);
