@@ -138,8 +138,57 @@ def residual(p, phi, rho):
 
 BASE = dict(w=0.9, nu0=1, nu=1, coarsest=7, gamma=1, gamma_from=1, alpha=1.0, scale=0.6)
 
+def newton(p, phi, rho, tol=1e-4, nr_tol=1e-3, eta0=1e-2, eta_max=0.1, gamma=0.9, eta_pow=1.5, tight_after=None, verbose=True):
+    """the Newton loop of mgn_body (inexact, Eisenstat-Walker forcing); tight_after = k: from Newton step k on the linear solve
+    goes straight to tol/2 (two steps instead of three when the first one already lands in the quadratic regime)"""
+    phi = phi.copy()
+    o = dict(BASE)
+    total, hist, Rprev, ynorm, last_full = 0, [], 0.0, 0.0, False
+    for nit in range(25):
+        R = residual(p, phi, rho)
+        Rn = np.sqrt((R * R).sum() / R.size)
+        if (nit == 0 and Rn < tol) or (nit > 0 and ynorm < nr_tol and (Rn < tol or last_full)):
+            break
+        lv = hierarchy(p, fine_split(p, phi), o["scale"])
+        eta = eta0 if nit == 0 else min(eta_max, gamma * (Rn / Rprev) ** eta_pow)
+        if tight_after is not None and nit >= tight_after:
+            eta = 0.0
+        stop = max(0.5 * tol, eta * Rn)
+        last_full = stop <= 0.5 * tol
+        Rprev = Rn
+        y, it, l2 = M.pcg(lv[0], R, lambda r: cycle(lv, 0, r, o), stop, 500) if Rn >= stop else (np.zeros_like(R), 0, Rn)
+        total += it
+        phi = phi + y
+        ynorm = np.sqrt((y * y).sum() / y.size)
+        hist.append((Rn, it, l2, ynorm))
+        if verbose:
+            print("   newton %d: |R| %.3e  eta %.1e  -> %d its (l2 %.2e)  |y| %.2e" % (nit, Rn, eta, it, l2, ynorm), flush=True)
+    Rf = residual(p, phi, rho)
+    return phi, total, len(hist), np.sqrt((Rf * Rf).sum() / Rf.size)
+
+
+def newton_study(path):
+    d = np.load(path)
+    n = int(d["mesh"])
+    p = M.build(n)
+    to3 = lambda a: a.reshape(n, n, n).transpose(2, 1, 0).copy()
+    phi0, rho1 = to3(d["phi"]), to3(d["rho_next"])
+    for name, kw in (("as built (eta0 1e-2, EW 0.9 x ratio^1.5)", {}),
+                     ("tight from the second step", dict(tight_after=1)),
+                     ("eta0 3e-3, tight from the second step", dict(eta0=3e-3, tight_after=1)),
+                     ("eta0 1e-3, tight from the second step", dict(eta0=1e-3, tight_after=1)),
+                     ("eta0 3e-2, tight from the second step", dict(eta0=3e-2, tight_after=1)),
+                     ("one tight step", dict(tight_after=0))):
+        t = time.time()
+        phi, total, steps, Rf = newton(p, phi0, rho1, **kw)
+        print("%-45s: %d Newton steps, %d CG iterations, final |R| %.2e  (%.0f s)" % (name, steps, total, Rf, time.time() - t), flush=True)
+
+
 if __name__ == "__main__":
     path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/warm_128.npz"
+    if len(sys.argv) > 2 and sys.argv[2] == "newton":
+        newton_study(path)
+        sys.exit(0)
     d = np.load(path)
     n = int(d["mesh"])
     p = M.build(n)
