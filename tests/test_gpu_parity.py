@@ -681,3 +681,69 @@ def test_prefetched_add_and_async_field_download():
     a.e.set_field(es.RHO, np.zeros(w.nn))              # unrelated work on the compute stream meanwhile
     a.e.copy_sync()
     assert_bits(out, a.e.field(es.DEN, a.species[0]), "asynchronously downloaded field")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 63, 65, 127, 1023, 1025, 4099, 70001])
+def test_sort_and_diag_at_ragged_sizes(n):
+    """The three-pass cell sort (four keys per thread in the rank pass, 256-bit loads in the scatter behind it) and the
+    in-push diagnostics (one record per warp of 64 particles) around the boundaries of their vector widths."""
+    es = _espic()
+    w, sp = cases.sphere_case(seed=60 + n % 5, n=n, near_walls=0.3)
+    st = sf.state_from_oracle(w, [sp], 2e-6)
+    a, b = GpuEngine(st), GpuEngine(st)
+    a.e.sort_by_cell(a.species[0])
+    got = a.e.download(a.species[0])
+    assert_bits(sort_rows(got), sort_rows(sp.particles()), "multiset preserved by the sort")
+    cell = [np.minimum(((got[c] - w.x0[c]) / w.dh[c]).astype(np.int64), m - 2) for c, m in enumerate((w.ni, w.nj, w.nk))]
+    assert np.all(np.diff((cell[2] * (w.nj - 1) + cell[1]) * (w.ni - 1) + cell[0]) >= 0), "keys sorted"
+    a.e.deposit(a.species[0], es.DEPOSIT_FP64)             # directly after a sort: the ungrouped scatter
+    sp.compute_number_density()
+    assert_close(a.e.field(es.DEN, a.species[0]), sp.den, DEN_RTOL, "den right after the sort")
+    for step in range(2):
+        a.e.push(a.species[0], 2e-6, es.WALL_ABSORB, es.PUSH_DIAG)
+        b.e.push(b.species[0], 2e-6, es.WALL_ABSORB, 0)
+        sp.advance(2e-6)
+        assert a.e.count(a.species[0]) == b.e.count(b.species[0]) == sp.np
+        da, db = a.e.diag(a.species[0]), b.e.diag(b.species[0])
+        assert np.abs(da - db).max() <= 1e-12 * max(np.abs(db).max(), 1e-300), (step, da, db)
+    assert_bits(sort_rows(a.e.download(a.species[0])), sort_rows(sp.particles()), "pushed multiset")
+    a.e.deposit(a.species[0], es.DEPOSIT_FP64)             # two pushes after the sort: the grouping scatter
+    sp.compute_number_density()
+    assert_close(a.e.field(es.DEN, a.species[0]), sp.den, DEN_RTOL, "den after two pushes")
+
+
+@pytest.mark.parametrize("fixed", [False, True], ids=["fp64", "fixed"])
+@pytest.mark.parametrize("kind", ["one cell", "own cell each", "two cells alternating", "tile boundary"])
+def test_grouped_deposit_on_adversarial_streams(kind, fixed):
+    """k_deposit_group on streams that stress its shared-memory grouping: every particle of a tile in ONE cell (one hash slot,
+    1024 ranks), every particle in a cell of its own (1024 slots, no run longer than one), two cells alternating particle by
+    particle (runs of one, two slots), and a population that ends 3 particles into a new tile."""
+    es = _espic()
+    rng = np.random.default_rng(77)
+    w = cases.sphere_world(17, 15, 19, sphere=False)        # no sphere: the frozen push below must not kill anything
+    cases.smooth_phi(w, rng, amp=5.0)
+    w.compute_ef()
+    n = {"one cell": 5000, "own cell each": 3000, "two cells alternating": 4096, "tile boundary": 2051}[kind]
+    dh, x0 = w.dh, w.x0
+    ncell = (w.ni - 1, w.nj - 1, w.nk - 1)
+    if kind == "one cell":
+        cells = np.tile(np.array([[3], [2], [1]]), (1, n))
+    elif kind == "two cells alternating":
+        cells = np.where(np.arange(n)[None, :] % 2 == 0, np.array([[3], [2], [1]]), np.array([[4], [2], [1]]))
+    else:
+        flat = rng.permutation(ncell[0] * ncell[1] * ncell[2])[:n] if kind == "own cell each" else rng.integers(0, ncell[0] * ncell[1] * ncell[2], n)
+        cells = np.array([flat % ncell[0], (flat // ncell[0]) % ncell[1], flat // (ncell[0] * ncell[1])])
+    pos = x0[:, None] + (cells + rng.uniform(0.01, 0.99, size=(3, n))) * dh[:, None]
+    soa = np.vstack([pos, rng.normal(0, 300.0, size=(3, n)), rng.uniform(10.0, 90.0, size=(1, n))])
+    sp = orc.Species(w, 16 * AMU, QE, mpw0=50.0, cap=2 * n)
+    sp.set_particles(soa)
+    st = sf.state_from_oracle(w, [sp], 1e-7)
+    g = GpuEngine(st, fixed=fixed)
+    # one frozen push first: espic_deposit picks the grouping kernel only after a push since the last sort
+    mode = es.DEPOSIT_FIXED if fixed else es.DEPOSIT_FP64
+    if kind == "tile boundary":
+        g.e.sort_by_cell(g.species[0])
+    g.e.push(g.species[0], 0.0, es.WALL_ABSORB, es.PUSH_NO_COMPACT)
+    g.e.deposit(g.species[0], mode)
+    sp.compute_number_density()
+    assert_close(g.e.field(es.DEN, g.species[0]), sp.den, 1e-10 if fixed else DEN_RTOL, "den (%s)" % kind)
