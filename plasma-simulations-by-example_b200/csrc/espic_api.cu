@@ -100,6 +100,13 @@ extern "C" int espic_create(espic_ctx **out, int ni, int nj, int nk, const doubl
     }
     if (device < 0 || device >= ndev) { espic_set_error("espic_create: device %d of %d", device, ndev); return -3; }
     CK(cudaSetDevice(device));
+    // ESPIC_SYNC_MODE=block|yield: how host threads wait in cudaStreamSynchronize (default: the driver's choice, which spins).
+    // With one process per GPU and fewer host cores than waiting threads, spinning ranks steal each other's time slices.
+    if (const char *sm = getenv("ESPIC_SYNC_MODE")) {
+        if (!strcmp(sm, "block")) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+        else if (!strcmp(sm, "yield")) cudaSetDeviceFlags(cudaDeviceScheduleYield);
+        cudaGetLastError();      // (a context created with other flags keeps them on older drivers: not an error for us)
+    }
     espic_ctx *c = new espic_ctx();
     c->device = device;
     cudaDeviceProp prop;
