@@ -1131,8 +1131,13 @@ __device__ __forceinline__ void mgn_body(const MgnArgs &a, Own &own, unsigned ch
         // reference itself would.
         if (nit == 0 ? Rn < a.tol : (ynorm < a.nr_tol && (Rn < a.tol || last_full))) { converged = 1; break; }
         if (nit >= a.nr_max_it) break;
-        // ---- Galerkin diagonals of the coarse levels
-        {
+        // ---- Galerkin diagonals of the coarse levels.  Only the mass term e^(phi/Te) of the diagonal depends on phi; once a Newton
+        // update is small against Te the coarse operators of the previous step are as good a preconditioner (same CG iteration
+        // counts on the bench case, scripts/mg_variants_prototype.py) and their rebuild -- one barrier per level -- is skipped.
+        // The fine-level diagonal, which defines the operator itself, is always current.  ynorm is the same number in every
+        // block and on every rank, so the branch is uniform.
+        const bool rebuild = nit == 0 || (a.n0 != 0 && ynorm > 0.1 * fabs(a.Te0));
+        if (rebuild) {
             int lr = a.nlev - 1;
             if constexpr (Own::slab) lr = a.first_redundant;
             OwnAll whole;
@@ -1148,7 +1153,7 @@ __device__ __forceinline__ void mgn_body(const MgnArgs &a, Own &own, unsigned ch
                 }
             }
         }
-        if (a.nlev > 1) mg_coarsest_stage(a.L[a.nlev - 1], smem);
+        if (rebuild && a.nlev > 1) mg_coarsest_stage(a.L[a.nlev - 1], smem);
         MG_TICK(8);
         // ---- CG on K delta = R down to the forcing level
         const double eta = nit == 0 ? a.eta0 : fmin(a.eta_max, a.gamma * pow(Rn / Rprev, a.eta_pow));

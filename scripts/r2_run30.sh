@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 L=gpurun_out/run30.log
-(timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "mg_ or multigrid" 2>&1 | tail -3) > $L
+(timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_host_shim.py -q -m gpu -k "mg_ or multigrid or solver or golden or pcg" 2>&1 | tail -3) > $L
 (ESPIC_MG_PROFILE=1 timeout 600 python bench.py --steps 16 --warmup 3 --no-e2e --no-variants --no-extra --no-cpu-baseline --no-clocks 2> gpurun_out/r30.err > gpurun_out/r30.json; echo "rc=$?" >> $L)
 grep -h "mg profile\|mg newton profile\|profile" gpurun_out/r30.err | tail -2 >> $L
 python -c "
