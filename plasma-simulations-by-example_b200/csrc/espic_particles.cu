@@ -462,9 +462,10 @@ struct DepGroup {
     double rec[4][DG_REC];                            // cell fractions and weight of every record, in cell order
     uint32_t hkey[DT_SLOTS], hcnt[DT_SLOTS];          // hash table: lower node of the cell; particle counts, then offsets
     uint32_t skey[DG_TILE];                           // lower node of the cell of every record, in cell order
-    uint32_t wsum[DG_THREADS / 32];
+    alignas(16) uint32_t wsum[DG_THREADS / 32];
     uint32_t n_sorted;
 };
+static_assert(DG_THREADS == 256, "the scan of k_deposit_group adds eight warp sums");
 
 __device__ __forceinline__ void ld4(const double *p, double v[4])
 {
@@ -524,23 +525,28 @@ __global__ void __launch_bounds__(DG_THREADS, 4) k_deposit_group(MeshC m, const 
     uint32_t key[4], sr[4];
     load_four<VAL>(m, x, y, z, mpw, vcomp, base + 4 * tid, n, X, Y, Z, W, key);
     __syncthreads();
+    // (the four rounds in three sweeps -- all matches, all table updates, all broadcasts -- so that their latencies overlap: a round's
+    // match, its leader's CAS + atomic and the shuffle behind them form one dependent chain)
+    unsigned peers[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) peers[j] = __match_any_sync(FULL, key[j]);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t kk = key[j];
-        const unsigned peers = __match_any_sync(FULL, kk);
-        const int leader = __ffs(peers) - 1;
-        uint32_t v = 0;
-        if (kk != DT_EMPTY && lane == leader) {
-            uint32_t h = (kk * 2654435761u) >> (32 - DT_SLOT_BITS);
+        sr[j] = 0;
+        if (key[j] != DT_EMPTY && lane == __ffs(peers[j]) - 1) {
+            uint32_t h = (key[j] * 2654435761u) >> (32 - DT_SLOT_BITS);
             for (int probe = 0; probe < DT_SLOTS; probe++) {          // the table has a slot per particle of the tile: it cannot fill up
-                const uint32_t old = atomicCAS(&t.hkey[h], DT_EMPTY, kk);
-                if (old == DT_EMPTY || old == kk) break;
+                const uint32_t old = atomicCAS(&t.hkey[h], DT_EMPTY, key[j]);
+                if (old == DT_EMPTY || old == key[j]) break;
                 h = (h + 1) & (DT_SLOTS - 1);
             }
-            v = h | (atomicAdd(&t.hcnt[h], (uint32_t)__popc(peers)) << 16);
+            sr[j] = h | (atomicAdd(&t.hcnt[h], (uint32_t)__popc(peers[j])) << 16);
         }
-        v = __shfl_sync(FULL, v, leader);
-        sr[j] = v + ((uint32_t)__popc(peers & ((1u << lane) - 1u)) << 16);      // slot | rank of this particle in its cell
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t v = __shfl_sync(FULL, sr[j], __ffs(peers[j]) - 1);
+        sr[j] = v + ((uint32_t)__popc(peers[j] & ((1u << lane) - 1u)) << 16);      // slot | rank of this particle in its cell
     }
     __syncthreads();
     // ---- 2. counts -> offsets
@@ -556,7 +562,12 @@ __global__ void __launch_bounds__(DG_THREADS, 4) k_deposit_group(MeshC m, const 
         if (lane == 31) t.wsum[tid >> 5] = inc;
         __syncthreads();
         uint32_t run = inc - tsum;
-        for (int w = 0; w < (tid >> 5); w++) run += t.wsum[w];
+        {       // sums of the warps below this one: two broadcast loads and predicated adds instead of a chain of up to seven loads
+            const uint4 wa = reinterpret_cast<const uint4 *>(t.wsum)[0], wb = reinterpret_cast<const uint4 *>(t.wsum)[1];
+            const int w = tid >> 5;
+            run += (w > 0 ? wa.x : 0u) + (w > 1 ? wa.y : 0u) + (w > 2 ? wa.z : 0u) + (w > 3 ? wa.w : 0u) +
+                   (w > 4 ? wb.x : 0u) + (w > 5 ? wb.y : 0u) + (w > 6 ? wb.z : 0u);
+        }
         reinterpret_cast<uint4 *>(t.hcnt)[tid] = make_uint4(run, run + c4.x, run + c4.x + c4.y, run + c4.x + c4.y + c4.z);
         if (tid == DG_THREADS - 1) t.n_sorted = run + tsum;
     }
