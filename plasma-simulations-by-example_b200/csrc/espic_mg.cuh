@@ -27,8 +27,13 @@
 #include <cuda.h>       // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no link against libcuda)
 
 #define MG_MAX_LEVELS 8
-#define MG_OMEGA 0.9
-#define MG_COARSE_SWEEPS 6
+#define MG_OMEGA 0.9                    // damped Jacobi on the fine level
+// ... and on the coarse levels: 1.0 is the largest factor for which Jacobi is a convergent smoother whatever the mesh (the
+// spectrum of D^-1 K ends just below 2: 1.993 on the 128^3 bench mesh), i.e. for which the V-cycle is guaranteed SPD.  With the
+// rescaled coarse operators it saves CG iterations at no cost (scripts/mg_variants_prototype.py: 25 -> 22 per solve together
+// with three more sweeps on the coarsest level; 1.1-1.3 would save more but are not safe, 1.6 diverges).
+#define MG_OMEGA_C 1.0
+#define MG_COARSE_SWEEPS 9
 #define MG_COARSEST_NODES 4096          // stop coarsening once a level is this small; it must fit 3 FP32 vectors in shared memory
 #define MG_SLAB_REDUNDANT_NODES 65536   // slab mode: levels up to this size are solved by every rank in full
 #define MG_THREADS 256                  // one 32 x 8 tile of columns per block and marching step
@@ -327,7 +332,7 @@ __device__ __forceinline__ void mg_down(const Own &own, const MgLevel &F, int lf
 {
     const long long first = own.lo(C, lf + 1), total = (own.hi(C, lf + 1) - first) * 8;
     const int sj = F.ni, sk = F.ni * F.nj;
-    const mgf W = (mgf)MG_OMEGA;
+    const mgf W = (mgf)MG_OMEGA_C;
     for (long long w = t0; (w & ~31LL) < total; w += stride) {
         const unsigned I = (unsigned)(first + (w >> 3));
         const int c = (int)(w & 7);
@@ -375,7 +380,7 @@ __device__ __forceinline__ void mg_up(const Own &own, const MgLevel &F, int lf, 
 {
     const long long first = own.lo(F, lf), count = own.hi(F, lf) - first;
     const int sj = F.ni, sk = F.ni * F.nj, csj = C.ni, csk = C.ni * C.nj;
-    const mgf W = (mgf)MG_OMEGA;
+    const mgf W = (mgf)MG_OMEGA_C;
     // value of the prolongated iterate at node (vi,vj,vk) = flat v; links to nodes without unknowns are zero on coarse levels,
     // so no mask is needed on the neighbours
     auto val = [&](int v, int vi, int vj, int vk) {
@@ -477,7 +482,7 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
         for (int u = threadIdx.x; u < n; u += blockDim.x) {
             const mgf b = L.b[u];
             sb[u] = b;
-            sx[u] = (mgf)MG_OMEGA * b * minv[u];
+            sx[u] = (mgf)MG_OMEGA_C * b * minv[u];
         }
         __syncthreads();
         for (int sweep = 0; sweep < sweeps; sweep++) {
@@ -490,7 +495,7 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
                 t += cy[u] * sx[u + sj];
                 t += cz[u - sk] * sx[u - sk];
                 t += cz[u] * sx[u + sk];
-                sy[u] = xc + (mgf)MG_OMEGA * minv[u] * t;          // minv = 0 on nodes without unknowns, where x stays 0
+                sy[u] = xc + (mgf)MG_OMEGA_C * minv[u] * t;          // minv = 0 on nodes without unknowns, where x stays 0
             }
             __syncthreads();
             mgf *tmp = sx; sx = sy; sy = tmp;
@@ -501,7 +506,7 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
     for (int u = threadIdx.x; u < n; u += blockDim.x) {
         const mgf b = L.b[u];
         sb[u] = b;
-        sx[u] = (mgf)MG_OMEGA * b * L.minv[u];
+        sx[u] = (mgf)MG_OMEGA_C * b * L.minv[u];
     }
     __syncthreads();
     for (int sweep = 0; sweep < sweeps; sweep++) {
@@ -515,7 +520,7 @@ __device__ __forceinline__ const mgf *mg_coarsest(const MgLevel &L, int sweeps, 
             if (q.j + 1 < L.nj) t += L.cy[u] * sx[u + sj];
             if (q.k > 0) t += L.cz[u - sk] * sx[u - sk];
             if (q.k + 1 < L.nk) t += L.cz[u] * sx[u + sk];
-            sy[u] = xc + (mgf)MG_OMEGA * L.minv[u] * t;
+            sy[u] = xc + (mgf)MG_OMEGA_C * L.minv[u] * t;
         }
         __syncthreads();
         mgf *tmp = sx; sx = sy; sy = tmp;

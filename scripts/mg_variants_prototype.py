@@ -106,20 +106,21 @@ def cheb(L, x, b, degree, lmax=2.0, ratio=0.25):
 def cycle(lv, l, b, o):
     L = lv[l]
     x = np.zeros_like(b)
+    wl = o["w"] if l == 0 else o.get("wc", o["w"])       # optional: another damping factor on the coarse levels
     if l == len(lv) - 1:
-        return jac(L, x, b, o["w"], o["coarsest"])
+        return jac(L, x, b, wl, o["coarsest"])
     nu = o["nu0"] if l == 0 else o["nu"]
     if o.get("cheb") and l == 0:
         x = cheb(L, x, b, o["cheb"])
     else:
-        x = jac(L, x, b, o["w"], nu)
+        x = jac(L, x, b, wl, nu)
     f = lv[l + 1]["f"]
     for _ in range(o["gamma"] if l >= o["gamma_from"] else 1):
         r = b - M.apply(L, x)
         x = x + o["alpha"] * prolong(cycle(lv, l + 1, restrict(r, f), o), b.shape, f) * L["mask"]
     if o.get("cheb") and l == 0:
         return cheb(L, x, b, o["cheb"])
-    return jac(L, x, b, o["w"], nu)
+    return jac(L, x, b, wl, nu)
 
 
 def residual(p, phi, rho):
